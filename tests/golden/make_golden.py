@@ -1,0 +1,313 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the LIVE, UNMODIFIED reference CPU path.
+
+Run in the dev container (where /root/reference exists) after `python oracle/build_ref.py`:
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or golden vectors of its own, so these fixtures,
+produced by importing the reference's own classes (oracle/_ref, compiled from the sources in
+/root/reference), are what pins the oracle.  Inputs are seeded; every .npz stores inputs,
+parameters, outputs and gradients.  The reference CPU path is run-to-run deterministic.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.refload import load_reference  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+R = load_reference()
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **{k: np.asarray(v) for k, v in arrs.items()})
+    print("wrote", name, {k: np.asarray(v).shape for k, v in arrs.items()})
+
+
+def conv_case(name, N, C, H, W, F, k, s, p, bias, l2s, seed):
+    g = rng(seed)
+    L = R.ConvLayer(name, filter_block_shape=(F, C, k, k), stride=s, padding=p, with_bias=bias,
+                    weight_regulariser=R.l2(l2s) if l2s else None)
+    L.learned_params["weights"] = f32(g.standard_normal((F, C, k, k)) * 0.2)
+    if bias:
+        L.learned_params["bias"] = f32(g.standard_normal(F))
+    X = f32(g.standard_normal((N, C, H, W)))
+    Y = f32(L.forward(X))
+    dY = f32(g.standard_normal(Y.shape))
+    dX = f32(L.backward(dY))
+    out = dict(X=X, W=L.learned_params["weights"], Y=Y, dY=dY, dX=dX, dW=f32(L.grads["weights"]),
+               patches=f32(L.patches), meta=np.array([N, C, H, W, F, k, s, p, int(bias)]), l2=np.float32(l2s))
+    if bias:
+        out.update(b=L.learned_params["bias"], db=f32(L.grads["bias"]))
+    save(name, **out)
+
+
+def pointwise_case(name, N, C, H, W, F, s, bias, l2s, seed):
+    g = rng(seed)
+    L = R.PointwiseConvLayer(name, stride=s, filter_block_shape=(F, C), with_bias=bias,
+                             weight_regulariser=R.l2(l2s) if l2s else None)
+    L.learned_params["weights"] = f32(g.standard_normal((F, C)) * 0.3)
+    if bias:
+        L.learned_params["bias"] = f32(g.standard_normal(F))
+    X = f32(g.standard_normal((N, C, H, W)))
+    Y = f32(L.forward(X))
+    dY = f32(g.standard_normal(Y.shape))
+    dX = f32(L.backward(dY))
+    out = dict(X=X, W=L.learned_params["weights"], Y=Y, dY=dY, dX=dX, dW=f32(L.grads["weights"]),
+               meta=np.array([N, C, H, W, F, s, int(bias)]), l2=np.float32(l2s))
+    if bias:
+        out.update(b=L.learned_params["bias"], db=f32(L.grads["bias"]))
+    save(name, **out)
+
+
+def depthwise_case(name, N, C, H, W, k, s, p, bias, seed):
+    g = rng(seed)
+    L = R.DepthwiseConvLayer(name, filter_block_shape=(C, k, k), stride=s, padding=p, with_bias=bias)
+    L.learned_params["weights"] = f32(g.standard_normal((C, k, k)) * 0.3)
+    if bias:
+        L.learned_params["bias"] = f32(g.standard_normal(C))
+    X = f32(g.standard_normal((N, C, H, W)))
+    Y = f32(L.forward(X))
+    dY = f32(g.standard_normal(Y.shape))
+    dX = f32(L.backward(dY))
+    out = dict(X=X, W=L.learned_params["weights"], Y=Y, dY=dY, dX=dX, dW=f32(L.grads["weights"]),
+               meta=np.array([N, C, H, W, k, s, p, int(bias)]))
+    if bias:
+        out.update(b=L.learned_params["bias"], db=f32(L.grads["bias"]))
+    save(name, **out)
+
+
+def bn_case(name, shape, seed):
+    g = rng(seed)
+    dim = len(shape)
+    C = shape[1]
+    L = R.BatchNormLayer(name, input_dimension=dim, incoming_chans=C)
+    # The reference's CPU branch of BatchNorm backward is 4-D only (einsum "ijkl",
+    # layers/batch_norm.py:145,162); for 2-D inputs only its `is_on_gpu` branch (xp.sum over
+    # axis 0, :147,164) works, and it runs fine on NumPy arrays -- use that branch for 2-D.
+    L.is_on_gpu = (dim == 2)
+    gam = f32(1.0 + 0.3 * g.standard_normal(C))
+    bet = f32(0.2 * g.standard_normal(C))
+    if dim == 4:
+        gam, bet = gam[None, :, None, None], bet[None, :, None, None]
+    L.learned_params["gamma"], L.learned_params["beta"] = gam, bet
+    X1 = f32(g.standard_normal(shape) * 2.0 + 0.7)
+    X2 = f32(g.standard_normal(shape) * 0.5 - 1.1)
+    Y1 = f32(L.forward(X1))
+    rm1, rs1 = f32(L.non_learned_params["running_mean"]), f32(L.non_learned_params["running_std"])
+    dY1 = f32(g.standard_normal(shape))
+    dX1 = f32(L.backward(dY1))
+    dg1, db1 = f32(L.grads["gamma"]), f32(L.grads["beta"])
+    Y2 = f32(L.forward(X2))
+    rm2, rs2 = f32(L.non_learned_params["running_mean"]), f32(L.non_learned_params["running_std"])
+    Yt = f32(L.forward(X1, test_mode=True))
+    save(name, X1=X1, X2=X2, gamma=gam, beta=bet, Y1=Y1, rm1=rm1, rs1=rs1, dY1=dY1, dX1=dX1,
+         dgamma1=dg1, dbeta1=db1, Y2=Y2, rm2=rm2, rs2=rs2, Ytest=Yt)
+
+
+def relu_case(name, shape, seed):
+    g = rng(seed)
+    X = f32(g.standard_normal(shape))
+    X.flat[::7] = 0.0  # exact zeros: gradient must be 0 there
+    L = R.ReLu(name)
+    Y = f32(L.forward(X))
+    mask = f32(L.positive_locs)
+    dY = f32(g.standard_normal(shape))
+    dX = f32(L.backward(dY))
+    Yt = f32(L.forward(X, test_mode=True))
+    save(name, X=X, Y=Y, mask=mask, dY=dY, dX=dX, Ytest=Yt)
+
+
+def pool_cases():
+    g = rng(40)
+    X = f32(g.standard_normal((2, 3, 8, 6)))
+    L = R.GlobalAveragePoolingLayer("gap")
+    Y = f32(L.forward(X))
+    dY = f32(g.standard_normal(Y.shape))
+    dX = f32(L.backward(dY))
+    save("gap", X=X, Y=Y, dY=dY, dX=dX)
+    # max pool: includes the SURVEY A.8 tie pattern in plane (0,0)
+    Xm = f32(g.integers(-3, 4, size=(2, 3, 8, 12)))  # many ties
+    Xm[0, 0, :4, :4] = np.array([[1, 1, 2, 2], [1, 1, 2, 3], [5, 4, 0, 0], [4, 5, 0, -1]], np.float32)
+    for s in (2, 4):
+        M = R.MaxPoolLayer("mp", None, stride=s)
+        Yp = f32(M.forward(Xm))
+        mask = np.asarray(M.max_locations).astype(np.int32)
+        dYp = f32(g.standard_normal(Yp.shape))
+        dXp = f32(M.backward(dYp))
+        Yt = f32(M.forward(Xm, test_mode=True))
+        save("maxpool_s%d" % s, X=Xm, Y=Yp, mask=mask, dY=dYp, dX=dXp, Ytest=Yt)
+
+
+def dense_loss_cases():
+    g = rng(50)
+    L = R.DenseLayer("d", incoming_chans=12, output_dim=7, with_bias=True, weight_regulariser=R.l2(0.01))
+    L.learned_params["weights"] = f32(g.standard_normal((12, 7)) * 0.4)
+    L.learned_params["bias"] = f32(g.standard_normal(7))
+    X = f32(g.standard_normal((5, 12)))
+    Y = f32(L.forward(X))
+    dY = f32(g.standard_normal(Y.shape))
+    dX = f32(L.backward(dY))
+    save("dense", X=X, W=L.learned_params["weights"], b=L.learned_params["bias"], Y=Y, dY=dY, dX=dX,
+         dW=f32(L.grads["weights"]), db=f32(L.grads["bias"]), l2=np.float32(0.01),
+         reg=np.float32(L.regulariser_forward()))
+    S = R.SoftmaxWithCrossEntropy("s")
+    logits = f32(g.standard_normal((6, 9)) * 2)
+    hard = np.eye(9, dtype=np.float32)[g.integers(0, 9, 6)]
+    soft = f32(0.8 * hard + 0.2 * np.eye(9, dtype=np.float32)[g.integers(0, 9, 6)])  # mixup-style labels
+    for nm, y in (("softmax_hard", hard), ("softmax_soft", soft)):
+        loss, p = S.forward(logits, y)
+        d = f32(S.backward())
+        _, pt = S.forward(logits, None, test_mode=True)
+        save(nm, X=logits, y=y, loss=np.float32(loss), p=f32(p), dX=d, ptest=f32(pt))
+
+
+def optimiser_cases():
+    g = rng(60)
+
+    class FakeLayer:
+        def __init__(self):
+            self.learned_params = {"weights": f32(g.standard_normal((4, 5))), "bias": f32(g.standard_normal(5))}
+            self.grads = {k: np.zeros_like(v) for k, v in self.learned_params.items()}
+
+    class FakeNet:
+        pass
+
+    grads_seq = [{"weights": f32(g.standard_normal((4, 5))), "bias": f32(g.standard_normal(5))} for _ in range(3)]
+    for nm, mk in (("opt_sgd", lambda n: R.SGD(n, 0.1)), ("opt_sgdm", lambda n: R.SGDMomentum(n, 0.1, 0.9)),
+                   ("opt_rmsprop", lambda n: R.RMSProp(n, 0.01, 0.9))):
+        net = FakeNet()
+        lay = FakeLayer()
+        w0 = {k: v.copy() for k, v in lay.learned_params.items()}
+        net.layers = [lay]
+        opt = mk(net)
+        out = {"w0": w0["weights"], "b0": w0["bias"]}
+        for i, gr in enumerate(grads_seq):
+            lay.grads = {k: v.copy() for k, v in gr.items()}
+            opt.update_weights()
+            out["gw%d" % i], out["gb%d" % i] = gr["weights"], gr["bias"]
+            out["w%d" % (i + 1)] = f32(lay.learned_params["weights"]).copy()
+            out["b%d" % (i + 1)] = f32(lay.learned_params["bias"]).copy()
+        save(nm, **out)
+
+
+def build_small_net(M, seed):
+    """A miniature of the ResNet-18-depsep pattern (examples/imagenet_dogs_225_resnet_18_depsep.py):
+    conv s2 - BN - ReLU - pw s2 - BN - ReLU - ResidualBlock(identity) - ResidualBlock(downsample,
+    pw-s2 skip) - GAP - dense - softmax.  `M` is a namespace of layer classes (reference or ours)."""
+    np.random.seed(seed)
+    net = M.FeedForwardNetwork("mini")
+    net.add_layer(M.ConvLayer("conv0", filter_block_shape=(8, 3, 5, 5), with_bias=False, stride=2, padding=1,
+                              weight_regulariser=M.l2(1e-3)))
+    net.add_layer(M.BatchNormLayer("conv0_bn", input_dimension=4, incoming_chans=8))
+    net.add_layer(M.ReLu("conv0_relu"))
+    net.add_layer(M.PointwiseConvLayer("pw0", filter_block_shape=(8, 8), with_bias=False, stride=2,
+                                       weight_regulariser=M.l2(1e-3)))
+    net.add_layer(M.BatchNormLayer("pw0_bn", input_dimension=4, incoming_chans=8))
+    net.add_layer(M.ReLu("pw0_relu"))
+
+    def unit(nm, cin, cout, stride, final_relu):
+        ll = [M.DepthwiseConvLayer(nm + "_dw", filter_block_shape=(cin, 3, 3), stride=stride, padding=1, with_bias=False),
+              M.BatchNormLayer(nm + "_dw_bn", input_dimension=4, incoming_chans=cin),
+              M.PointwiseConvLayer(nm + "_pw", filter_block_shape=(cout, cin), with_bias=False,
+                                   weight_regulariser=M.l2(1e-3)),
+              M.BatchNormLayer(nm + "_pw_bn", input_dimension=4, incoming_chans=cout)]
+        if final_relu:
+            ll.append(M.ReLu(nm + "_relu"))
+        return ll
+
+    net.add_layer(M.ResidualBlock("res1", layer_list=unit("res1_a", 8, 8, 1, True) + unit("res1_b", 8, 8, 1, False),
+                                  skip_projection=None, post_skip_activation=M.ReLu("res1_relu2")))
+    net.add_layer(M.ResidualBlock("res2", layer_list=unit("res2_a", 8, 16, 2, True) + unit("res2_b", 16, 16, 1, False),
+                                  skip_projection=M.PointwiseConvLayer("res2_skip", filter_block_shape=(16, 8), stride=2,
+                                                                       with_bias=False, weight_regulariser=M.l2(1e-3)),
+                                  post_skip_activation=M.ReLu("res2_relu2")))
+    net.add_layer(M.GlobalAveragePoolingLayer("gap"))
+    net.add_layer(M.DenseLayer("dense1", incoming_chans=16, output_dim=5, weight_regulariser=M.l2(1e-3)))
+    net.set_loss_layer(M.SoftmaxWithCrossEntropy("softmax1"))
+    return net
+
+
+def iter_param_layers(net):
+    for l in net.layers:
+        if getattr(l, "learned_params", None):
+            yield l
+        if hasattr(l, "layer_list"):
+            for m in l.layer_list:
+                if getattr(m, "learned_params", None):
+                    yield m
+            if l.skip_projection is not None:
+                yield l.skip_projection
+
+
+def net_case():
+    """3 SGDMomentum steps on the miniature net at 33x33 (the reference's odd-size geometry:
+    33 -(5x5 s2 p1)-> 16 -(pw s2)-> 8 -> 8 -(dw s2)-> 4)."""
+    g = rng(70)
+    net = build_small_net(R, seed=123)
+    out = {}
+    for l in iter_param_layers(net):
+        for k, v in l.learned_params.items():
+            out["init/%s/%s" % (l.layer_name, k)] = f32(v).copy()
+    opt = R.SGDMomentum(net, 0.02, 0.9)
+    X = f32(g.uniform(0, 255, (8, 3, 33, 33)) - 128.0)
+    y = np.eye(5, dtype=np.float32)[g.integers(0, 5, 8)]
+    out["X"], out["y"] = X, y
+    losses = []
+    for step in range(3):
+        loss, scores = net.forward(X, y)
+        losses.append(loss)
+        net.backward()
+        if step == 0:
+            out["scores0"] = f32(scores)
+            for l in iter_param_layers(net):
+                for k, v in l.grads.items():
+                    out["grad0/%s/%s" % (l.layer_name, k)] = f32(v).copy()
+        opt.update_weights()
+    out["losses"] = np.array(losses, np.float64)
+    for l in iter_param_layers(net):
+        for k, v in l.learned_params.items():
+            out["final/%s/%s" % (l.layer_name, k)] = f32(v).copy()
+    _, st = net.forward(X, None, test_mode=True)
+    out["scores_test"] = f32(st)
+    _, lt = net.forward(X, None, test_mode=True, terminal_layer_name="dense1")
+    out["logits_test"] = f32(lt)
+    save("mini_net", **out)
+
+
+def main():
+    conv_case("conv_k3s1p1", 2, 3, 9, 10, 4, 3, 1, 1, False, 0.0, 1)
+    conv_case("conv_k5s2p1_half", 2, 3, 10, 12, 5, 5, 2, 1, True, 0.01, 2)   # (10+2-5)/2 = 3.5 -> floor
+    conv_case("conv_k4s2p1", 2, 4, 8, 8, 6, 4, 2, 1, False, 1e-4, 3)         # MNIST 4x4 s2
+    conv_case("conv_k3s1p0", 1, 2, 6, 7, 3, 3, 1, 0, True, 0.0, 4)
+    pointwise_case("pw_s1", 2, 6, 5, 7, 9, 1, True, 0.01, 10)
+    pointwise_case("pw_s2_even", 2, 4, 6, 8, 5, 2, False, 1e-3, 11)
+    pointwise_case("pw_s2_odd", 2, 4, 7, 9, 5, 2, False, 0.0, 12)            # dX is 8x10, not 7x9
+    depthwise_case("dw_k3s1p1", 2, 5, 7, 9, 3, 1, 1, False, 20)
+    depthwise_case("dw_k3s2p1_half", 2, 4, 8, 10, 3, 2, 1, True, 21)         # (8+2-3)/2 = 3.5
+    depthwise_case("dw_k3s2p1_int", 2, 4, 7, 9, 3, 2, 1, False, 22)
+    depthwise_case("dw_k5s1p2", 1, 3, 9, 8, 5, 1, 2, False, 23)
+    bn_case("bn_4d", (3, 5, 6, 7), 30)
+    bn_case("bn_2d", (16, 6), 31)
+    relu_case("relu_4d", (2, 3, 5, 7), 35)
+    relu_case("relu_2d", (6, 11), 36)
+    pool_cases()
+    dense_loss_cases()
+    optimiser_cases()
+    net_case()
+
+
+if __name__ == "__main__":
+    main()
