@@ -1,0 +1,209 @@
+"""DeviceArray: the array type the layers exchange on the B200 path.
+
+It plays the role CuPy arrays play on the reference's GPU path (the reference's layers only rely on
+`.shape`, `+`, and passing arrays along; the example loops use `cp.asarray` / `cp.asnumpy`).
+Storage is a torch CUDA tensor used purely as an allocation + stream handle: no torch op touches
+the data on the hot path -- every computation goes through the C ABI on `.ptr`.
+"""
+import numpy as np
+
+from . import runtime
+
+_NP2TORCH = None
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _torch_dtype(dtype):
+    global _NP2TORCH
+    torch = _torch()
+    if _NP2TORCH is None:
+        _NP2TORCH = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32,
+                     np.dtype(np.int64): torch.int64, np.dtype(np.uint8): torch.uint8}
+    return _NP2TORCH[np.dtype(dtype)]
+
+
+class DeviceArray:
+    """A contiguous device buffer with a shape.  float32 unless stated."""
+
+    __slots__ = ("t", "shape", "dtype")
+    __array_priority__ = 100.0
+
+    def __init__(self, t, shape=None, dtype=np.float32):
+        self.t = t
+        self.shape = tuple(int(s) for s in (shape if shape is not None else t.shape))
+        self.dtype = np.dtype(dtype)
+
+    # -- metadata ------------------------------------------------------------------------
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __repr__(self):
+        return "DeviceArray(shape=%s, dtype=%s)" % (self.shape, self.dtype)
+
+    # -- host <-> device -------------------------------------------------------------------
+    def get(self):
+        """Synchronous device -> host copy as a NumPy array."""
+        return self.t.detach().reshape(self.shape).cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.get()
+        return a.astype(dtype) if dtype is not None else a
+
+    def set(self, host):
+        """Host -> device copy into this buffer (shape must match)."""
+        torch = _torch()
+        h = np.ascontiguousarray(host, dtype=self.dtype)
+        if h.size != self.size:
+            raise ValueError("DeviceArray.set: size mismatch %s vs %s" % (h.shape, self.shape))
+        self.t.reshape(-1).copy_(torch.from_numpy(h.reshape(-1)), non_blocking=False)
+        return self
+
+    def copy_from(self, other):
+        """Device -> device copy (cudaMemcpyAsync on the current stream)."""
+        self.t.reshape(-1).copy_(other.t.reshape(-1), non_blocking=True)
+        return self
+
+    def copy(self):
+        out = empty(self.shape, self.dtype)
+        return out.copy_from(self)
+
+    # -- views -----------------------------------------------------------------------------
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        shape = list(shape)
+        if -1 in shape:
+            known = 1
+            for s in shape:
+                if s != -1:
+                    known *= s
+            shape[shape.index(-1)] = self.size // known
+        n = 1
+        for s in shape:
+            n *= s
+        if n != self.size:
+            raise ValueError("cannot reshape %s into %s" % (self.shape, tuple(shape)))
+        return DeviceArray(self.t, shape, self.dtype)
+
+    # -- the one arithmetic op the reference's layers use on activations (residual join) -----
+    def __add__(self, other):
+        from ._lib import api
+        other = asarray(other)
+        if other.shape != self.shape:
+            raise ValueError("operands could not be broadcast together with shapes %s %s" % (self.shape, other.shape))
+        out = empty(self.shape)
+        api.dk_add(self.ptr, other.ptr, out.ptr, self.size, runtime.stream())
+        return out
+
+    __radd__ = __add__
+
+
+def empty(shape, dtype=np.float32):
+    torch = _torch()
+    runtime.ensure_init()
+    shape = tuple(int(s) for s in shape)
+    n = 1
+    for s in shape:
+        n *= s
+    t = torch.empty(max(n, 1), dtype=_torch_dtype(dtype), device=runtime.device())
+    return DeviceArray(t, shape, dtype)
+
+
+def zeros(shape, dtype=np.float32):
+    a = empty(shape, dtype)
+    a.t.zero_()
+    return a
+
+
+def asarray(a, dtype=np.float32):
+    """Host array -> DeviceArray (synchronous H2D copy); DeviceArray passes through."""
+    if isinstance(a, DeviceArray):
+        return a
+    torch = _torch()
+    runtime.ensure_init()
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda:
+            a = a.to(runtime.device())
+        return DeviceArray(a.contiguous(), a.shape, np.float32 if a.dtype == torch.float32 else np.int32)
+    h = np.ascontiguousarray(a, dtype=dtype)
+    t = torch.from_numpy(h.reshape(-1) if h.ndim else h.reshape(1)).to(runtime.device())
+    return DeviceArray(t, h.shape, dtype)
+
+
+def asnumpy(a):
+    if isinstance(a, DeviceArray):
+        return a.get()
+    return np.asarray(a)
+
+
+class DeviceScalar:
+    """A lazily-evaluated float living on the device: sum_i coeff_i * slot_i + const.
+
+    The loss (losses.py:23-27) and every layer's l2 term (regularisers/l2.py:12-14) are produced by
+    kernels into one-float device slots; `network.forward` adds them up with Python `+`
+    (feed_forward_network.py:59-60), which here only concatenates term lists -- no kernel, no sync.
+    float(x) synchronises once and reads the slots.
+    """
+
+    __slots__ = ("terms", "const")
+    __array_priority__ = 100.0
+
+    def __init__(self, terms=(), const=0.0):
+        self.terms = list(terms)  # [(DeviceArray one-float slot, coeff)]
+        self.const = float(const)
+
+    def _combine(self, other, sign=1.0):
+        if isinstance(other, DeviceScalar):
+            return DeviceScalar(self.terms + [(s, sign * c) for s, c in other.terms], self.const + sign * other.const)
+        return DeviceScalar(self.terms, self.const + sign * float(other))
+
+    def __add__(self, other):
+        return self._combine(other)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self._combine(other, -1.0)
+
+    def __mul__(self, k):
+        k = float(k)
+        return DeviceScalar([(s, c * k) for s, c in self.terms], self.const * k)
+
+    __rmul__ = __mul__
+
+    def __float__(self):
+        total = np.float64(self.const)
+        for slot, coeff in self.terms:
+            total += coeff * float(slot.get().reshape(-1)[0])
+        return float(total)
+
+    def get(self):
+        return np.float32(float(self))
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(float(self), dtype=dtype or np.float32)
+
+    def __repr__(self):
+        return "DeviceScalar(%d terms)" % len(self.terms)
+
+    def __format__(self, spec):
+        return format(float(self), spec)

@@ -1,0 +1,38 @@
+// gemm.cuh -- internal interface between the C-ABI dispatch (conv_api.cu) and the two GEMM backends.
+#pragma once
+#include "common.cuh"
+
+namespace dk {
+
+// ---- SIMT implicit GEMM (gemm_simt.cu) ------------------------------------------------------------
+int simt_conv_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
+                  int kh, int kw, int s, int p, cudaStream_t st);
+int simt_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw,
+                    int s, int p, int OH, int OW, cudaStream_t st);
+int simt_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W,
+                    int F, int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st);
+int simt_dense_fwd(const float *x, const float *w, const float *bias, float *y, int B, int in_dim, int out_dim,
+                   cudaStream_t st);
+int simt_dense_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float l2, int B, int in_dim,
+                   int out_dim, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t simt_wgrad_ws_bytes(int64_t M, int Nn, int64_t K);
+size_t simt_dense_ws_bytes(int B, int in_dim, int out_dim);
+int simt_im2col(const float *x, float *P, int N, int C, int H, int W, int kh, int kw, int s, int p, cudaStream_t st);
+
+// ---- tcgen05 / TMEM / TMA GEMM (gemm_tcgen05.cu) --------------------------------------------------
+// Each returns DK_ERR_UNSUPPORTED (without setting an error) when the shape is outside what the
+// tensor-core kernels cover; the dispatcher then uses the SIMT kernel for that call.
+int tc_conv_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F,
+                int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st);
+int tc_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw,
+                  int s, int p, int OH, int OW, void *ws, size_t ws_bytes, cudaStream_t st);
+int tc_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W,
+                  int F, int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st);
+int tc_dense_fwd(const float *x, const float *w, const float *bias, float *y, int B, int in_dim, int out_dim,
+                 void *ws, size_t ws_bytes, cudaStream_t st);
+int tc_dense_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float l2, int B, int in_dim,
+                 int out_dim, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
+size_t tc_dense_ws_bytes(int B, int in_dim, int out_dim);
+
+}  // namespace dk

@@ -1,0 +1,40 @@
+"""ReLu (reference: layers/activations.py:6-53, layers/relu_cy.pyx)."""
+from .layer import Layer, api, runtime, asarray
+
+
+class ReLu(Layer):
+
+    def __init__(self, layer_name):
+        super().__init__(layer_name)
+        self._y = None
+
+    def __repr__(self):
+        return "ReLu({})".format(self.layer_name)
+
+    def forward(self, X, test_mode=False):
+        """out = max(x, 0) (activations.py:14-29).  The reference also stores a float 0/1 mask
+        (`positive_locs`); here the mask is implied by the output (y > 0 <=> x > 0), so the forward
+        moves 2n bytes instead of 3n and `positive_locs` is materialised only if somebody reads it."""
+        self._ensure_gpu()
+        X = asarray(X)
+        y = self._buf("y", X.shape)
+        api.dk_relu_fwd(X.ptr, y.ptr, None, X.size, runtime.stream())
+        if not test_mode:
+            self._y = y
+        return y
+
+    @property
+    def positive_locs(self):
+        if self._y is None:
+            return None
+        m = self._buf("mask", self._y.shape)
+        tmp = self._buf("mask_tmp", self._y.shape)
+        api.dk_relu_fwd(self._y.ptr, tmp.ptr, m.ptr, self._y.size, runtime.stream())
+        return m
+
+    def backward(self, upstream_dx):
+        """dY * mask (activations.py:44-47)"""
+        upstream_dx = asarray(upstream_dx)
+        dx = self._buf("dx", upstream_dx.shape)
+        api.dk_relu_bwd(upstream_dx.ptr, self._y.ptr, dx.ptr, upstream_dx.size, runtime.stream())
+        return dx

@@ -1,0 +1,100 @@
+"""BatchNormLayer (reference: layers/batch_norm.py:9-232, layers/batch_norm_stats_cy.pyx)."""
+import numpy as np
+
+from .layer import Layer, api, runtime, asarray, empty
+
+
+class BatchNormLayer(Layer):
+    """https://arxiv.org/pdf/1502.03167.pdf -- same constructor as batch_norm.py:13-14."""
+
+    def __init__(self, layer_name, input_dimension=4, incoming_chans=None, run_momentum=0.95, is_on_gpu=True):
+        super().__init__(layer_name)
+        self.eps = 1e-5
+        self.input_dimension = input_dimension
+        self.non_learned_params = {"running_mean": None, "running_std": None}
+        self.run_momentum = run_momentum
+        if self.input_dimension not in {2, 4}:
+            raise ValueError("BatchNorm input_dimension should have length 2 or 4...")
+        self.av_axis = (0, 2, 3) if self.input_dimension == 4 else 0
+        self.incoming_chans = incoming_chans
+        if incoming_chans is not None:
+            gamma = np.ones(incoming_chans, dtype=np.float32)
+            beta = np.zeros(incoming_chans, dtype=np.float32)
+            if self.input_dimension == 4:
+                gamma = gamma[np.newaxis, :, np.newaxis, np.newaxis]
+                beta = beta[np.newaxis, :, np.newaxis, np.newaxis]
+            self.learned_params = {"gamma": gamma, "beta": beta}
+            self.grads = {"gamma": np.zeros_like(gamma), "beta": np.zeros_like(beta)}
+        else:
+            self.learned_params = {}
+            self.grads = {}
+        self._x = None
+
+    def __repr__(self):
+        return "BatchNormLayer({}, input_dimension={}, incoming_chans={}, run_momentum={})".format(
+            self.layer_name, self.input_dimension, self.incoming_chans, self.run_momentum)
+
+    @staticmethod
+    def _dims(shape):
+        if len(shape) == 4:
+            return shape[0], shape[1], shape[2] * shape[3]
+        return shape[0], shape[1], 1
+
+    def _stat_shape(self, C):
+        return (1, C, 1, 1) if self.input_dimension == 4 else (C,)
+
+    def forward(self, X, test_mode=False, use_express=False):
+        """batch_norm.py:54-115.  Train: batch mean / biased var (one pass, Chan-merged), std =
+        sqrt(var+eps), running mean / running STD EMA, y = gamma*x_hat + beta.  Instead of caching
+        X_demean and X_hat (two extra activation-sized writes) only mean/invstd/scale/shift per
+        channel are kept and x_hat is recomputed from the saved input in backward."""
+        self._ensure_gpu()
+        X = asarray(X)
+        if X.ndim != self.input_dimension:
+            raise ValueError("BatchNormLayer {} expects {}-D input, got shape {}".format(
+                self.layer_name, self.input_dimension, X.shape))
+        N, C, HW = self._dims(X.shape)
+        self.input_shape = X.shape
+        gamma, beta = self._param("gamma"), self._param("beta")
+        y = self._buf("y", X.shape)
+        st = runtime.stream()
+        if not test_mode:
+            first = self.non_learned_params["running_mean"] is None
+            if first:
+                self.non_learned_params["running_mean"] = empty(self._stat_shape(C))
+                self.non_learned_params["running_std"] = empty(self._stat_shape(C))
+            rm, rs = self.non_learned_params["running_mean"], self.non_learned_params["running_std"]
+            sv = self._buf("saved", (4, C))  # mean, invstd, scale, shift
+            ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
+            base = sv.ptr
+            api.dk_bn_fwd_train(X.ptr, y.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first),
+                                float(self.run_momentum), float(self.eps),
+                                base, base + 4 * C, base + 8 * C, base + 12 * C, 0, N, C, HW, ws, wsn, st)
+            self._x = X
+        else:
+            rm, rs = self.non_learned_params["running_mean"], self.non_learned_params["running_std"]
+            if rm is None:
+                raise ValueError("BatchNormLayer {}: test_mode forward before any training batch".format(self.layer_name))
+            rm, rs = asarray(rm), asarray(rs)
+            api.dk_bn_fwd_infer(X.ptr, y.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, 0, N, C, HW, st)
+        return y
+
+    def backward(self, upstream_dx):
+        """batch_norm.py:118-174: grads["gamma"], grads["beta"] and dx in two passes over (dY, X)."""
+        dY = asarray(upstream_dx)
+        N, C, HW = self._dims(self.input_shape)
+        sv = self._bufs["saved"]
+        base = sv.ptr
+        dx = self._buf("dx", self.input_shape)
+        dg, db = self._grad("gamma"), self._grad("beta")
+        ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
+        api.dk_bn_bwd(dY.ptr, self._x.ptr, self._param("gamma").ptr, base, base + 4 * C, base + 8 * C, base + 12 * C,
+                      dx.ptr, dg.ptr, db.ptr, 0, N, C, HW, ws, wsn, runtime.stream())
+        return dx
+
+    # the reference exposes these pieces separately (batch_norm.py:124-174)
+    @property
+    def std(self):
+        """sqrt(var + eps) of the last training batch, shape (1,C,1,1) / (C,) (batch_norm.py:69-72)."""
+        sv = self._bufs["saved"].get()
+        return (1.0 / sv[1]).reshape(self._stat_shape(sv.shape[1])).astype(np.float32)

@@ -1,0 +1,39 @@
+"""SoftmaxWithCrossEntropy (reference: layers/losses.py:5-41)."""
+from .layer import Layer, api, runtime, asarray, DeviceScalar
+
+
+class SoftmaxWithCrossEntropy(Layer):
+
+    def __init__(self, layer_name):
+        super().__init__(layer_name)
+
+    def __repr__(self):
+        return "SoftmaxWithCrossEntropy({})".format(self.layer_name)
+
+    def forward(self, X, y_one_hot=None, test_mode=False):
+        """Returns (loss, softmax scores) like losses.py:13-27 (softmax without max subtraction;
+        loss = mean(-log(sum_j p_j*y_j)), so soft / mixup labels behave as in the reference).
+        `loss` is a DeviceScalar: adding the regularisation terms to it costs no kernel and float()
+        is the only synchronisation point."""
+        self._ensure_gpu()
+        X = asarray(X)
+        B, K = X.shape
+        p = self._buf("p", (B, K))
+        if test_mode:
+            api.dk_softmax_xent_fwd(X.ptr, None, p.ptr, None, B, K, runtime.stream())
+            return 0, p
+        self.y_one_hot = asarray(y_one_hot)
+        if self.y_one_hot.shape != (B, K):
+            raise ValueError("SoftmaxWithCrossEntropy: labels {} do not match scores {}".format(
+                self.y_one_hot.shape, (B, K)))
+        loss = self._buf("loss", (1,))
+        api.dk_softmax_xent_fwd(X.ptr, self.y_one_hot.ptr, p.ptr, loss.ptr, B, K, runtime.stream())
+        self.downstream_x = p
+        return DeviceScalar([(loss, 1.0)]), p
+
+    def backward(self, upstream_dx=None):
+        """(p - y)/B (losses.py:29-34); upstream_dx is not used."""
+        B, K = self.downstream_x.shape
+        dx = self._buf("dx", (B, K))
+        api.dk_softmax_xent_bwd(self.downstream_x.ptr, self.y_one_hot.ptr, dx.ptr, B, K, runtime.stream())
+        return dx

@@ -1,0 +1,81 @@
+"""PointwiseConvLayer (reference: layers/pointwise_convolution.py:6-129)."""
+import numpy as np
+
+from .layer import Layer, api, runtime, asarray
+
+
+class PointwiseConvLayer(Layer):
+    """1x1 convolution.  The reference transposes to NHWC, calls a GEMM and transposes back
+    (pointwise_convolution.py:46-55); here the GEMM runs directly on the NCHW tensor
+    (Y[n] = W[F,C] . X[n][C,HW]), so no transposed copy exists in either direction."""
+
+    def __init__(self, layer_name, stride=1, filter_block_shape=None, with_bias=True,
+                 weight_regulariser=None, weight_initialiser="normal"):
+        super().__init__(layer_name)
+        self.stride = stride
+        self.with_bias = with_bias
+        self.weight_regulariser = weight_regulariser
+        self.weight_initialiser = weight_initialiser
+        if filter_block_shape is not None:
+            self.num_filters, self.num_channels = filter_block_shape
+            if self.weight_initialiser == "glorot_uniform":
+                limit = np.sqrt(6.0 / (self.num_channels + self.num_filters))
+                weights = np.random.uniform(low=-limit, high=limit, size=filter_block_shape).astype(np.float32)
+            elif self.weight_initialiser == "normal":
+                weights = 0.01 * np.random.randn(*filter_block_shape).astype(np.float32)
+            else:
+                raise ValueError("unknown weight_initialiser {!r}".format(weight_initialiser))
+            self.learned_params = {"weights": weights}
+            self.grads = {"weights": np.zeros_like(weights).astype(np.float32)}
+            if with_bias:
+                bias = np.zeros(self.num_filters).astype(np.float32)
+                self.learned_params.update({"bias": bias})
+                self.grads.update({"bias": np.zeros_like(bias)})
+        else:
+            self.num_filters = None
+            self.learned_params = {}
+            self.grads = {}
+        self._x = None
+
+    def __repr__(self):
+        out = "PointwiseConvLayer({}, ".format(self.layer_name)
+        if self.num_filters is not None:
+            out += "filter_block_shape=({}, {}), ".format(self.num_filters, self.num_channels)
+        out += "stride={}, with_bias={}, weight_regulariser={}, is_on_gpu={})".format(
+            self.stride, self.with_bias, repr(self.weight_regulariser), self.is_on_gpu)
+        return out
+
+    def forward(self, X, test_mode=False):
+        self._ensure_gpu()
+        X = asarray(X)
+        N, C, H, W = X.shape
+        if C != self.num_channels:
+            raise ValueError("PointwiseConvLayer {}: input has {} channels, filters expect {}".format(
+                self.layer_name, C, self.num_channels))
+        s = int(self.stride)
+        OH, OW = (H - 1) // s + 1, (W - 1) // s + 1  # X[:, :, ::s, ::s]
+        self.input_shape = X.shape
+        y = self._buf("y", (N, self.num_filters, OH, OW))
+        bias = self._param("bias").ptr if self.with_bias else None
+        ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, H, W, self.num_filters, s))
+        api.dk_pwconv_fwd(X.ptr, self._param("weights").ptr, bias, y.ptr, N, C, H, W, self.num_filters, s,
+                          ws, wsn, runtime.stream())
+        self._x = X
+        return y
+
+    def backward(self, upstream_dx):
+        dY = asarray(upstream_dx)
+        N, C, H, W = self.input_shape
+        _, F, OH, OW = dY.shape
+        s = int(self.stride)
+        w = self._param("weights")
+        st = runtime.stream()
+        ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, max(H, OH * s), max(W, OW * s), F, s))
+        dbias = self._grad("bias").ptr if self.with_bias else None
+        api.dk_pwconv_wgrad(dY.ptr, self._x.ptr, w.ptr, self._grad("weights").ptr, dbias, self._l2_strength(),
+                            N, C, H, W, F, s, ws, wsn, st)
+        # zero-stuffed dx of shape (OH*s, OW*s): for odd H this is NOT the input shape
+        # (pointwise_convolution.py:68-72) -- reproduced on purpose
+        dx = self._buf("dx", (N, C, OH * s, OW * s))
+        api.dk_pwconv_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, OH, OW, F, s, ws, wsn, st)
+        return dx

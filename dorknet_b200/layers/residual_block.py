@@ -1,0 +1,79 @@
+"""ResidualBlock (reference: layers/residual_block.py:12-151)."""
+from .layer import Layer, api, runtime, asarray
+from .activations import ReLu
+from .depthwise_convolution import DepthwiseConvLayer
+
+
+class ResidualBlock(Layer):
+    """out = post_skip_activation(layer_list(X) + skip_projection(X)); skip_projection=None is the
+    identity.  Same constructor and traversal as the reference; the join `X_tmp + skippee` followed
+    by ReLU (residual_block.py:75) is one kernel, and in backward the join `dx + joined_dx`
+    (:93-95) is folded into the first branch layer's backward when that layer supports it."""
+
+    def __init__(self, layer_name, layer_list=None, skip_projection=None, post_skip_activation=None):
+        super().__init__(layer_name)
+        self.layer_list = layer_list
+        self.skip_projection = skip_projection
+        self.post_skip_activation = post_skip_activation
+        if layer_list is None:
+            self.layer_list = []
+
+    def __repr__(self):
+        return "ResidualBlock({}, layer_list={}, skip_projection={}, post_skip_activation={})".format(
+            self.layer_name, self.layer_list, self.skip_projection, self.post_skip_activation)
+
+    def to_gpu(self):
+        if self.is_on_gpu:
+            print("Layer already on GPU, ignoring request")
+            return
+        for layer in self.layer_list:
+            layer.to_gpu()
+        if self.skip_projection is not None:
+            self.skip_projection.to_gpu()
+        if self.post_skip_activation is not None:
+            self.post_skip_activation.to_gpu()
+        self.is_on_gpu = True
+
+    def forward(self, X, test_mode=False):
+        self._ensure_gpu()
+        X = asarray(X)
+        X_tmp = self.layer_list[0].forward(X, test_mode=test_mode)
+        for layer in self.layer_list[1:]:
+            X_tmp = layer.forward(X_tmp, test_mode=test_mode)
+        skippee = self.skip_projection.forward(X, test_mode=test_mode) if self.skip_projection is not None else X
+        act = self.post_skip_activation
+        if type(act) is ReLu:
+            if X_tmp.shape != skippee.shape:
+                raise ValueError("operands could not be broadcast together with shapes {} {}".format(
+                    X_tmp.shape, skippee.shape))
+            y = act._buf("y", X_tmp.shape)
+            api.dk_add_relu_fwd(X_tmp.ptr, skippee.ptr, y.ptr, y.size, runtime.stream())
+            act._y = y  # the reference calls the activation without test_mode, so it always records (:75)
+            return y
+        return act.forward(X_tmp + skippee)
+
+    def regulariser_forward(self):
+        """Sums over layer_list only -- the skip projection's l2 term is not in the loss although its
+        gradient carries strength*W (residual_block.py:78-84)."""
+        regularisation = 0
+        for l in self.layer_list:
+            if hasattr(l, "regulariser_forward"):
+                regularisation += l.regulariser_forward()
+        return regularisation
+
+    def backward(self, upstream_dx):
+        joined_dx = self.post_skip_activation.backward(upstream_dx)
+        dx = self.layer_list[-1].backward(joined_dx)
+        first = self.layer_list[0]
+        for l in self.layer_list[-2:0:-1]:
+            dx = l.backward(dx)
+        if len(self.layer_list) == 1:
+            first_dx_in = None  # already consumed above
+        else:
+            first_dx_in = dx
+        skip_dx = self.skip_projection.backward(joined_dx) if self.skip_projection is not None else joined_dx
+        if first_dx_in is None:
+            return dx + skip_dx
+        if type(first) is DepthwiseConvLayer and tuple(first.input_shape) == tuple(skip_dx.shape):
+            return first.backward(first_dx_in, dx_add=skip_dx)
+        return first.backward(first_dx_in) + skip_dx

@@ -1,0 +1,19 @@
+"""RMSProp (reference: optimisers/RMSProp.py:5-36)."""
+from .. import runtime
+from .._lib import api
+from ._multi import MultiTensorOptimiser, collect_layers
+
+
+class RMSProp(MultiTensorOptimiser):
+    def __init__(self, network, learning_rate, decay_rate):
+        super().__init__(network, learning_rate)
+        self.learnable_layers = collect_layers(network, descend=False)
+        self.decay_rate = decay_rate
+        self.grad_cache = {}
+
+    def update_weights(self):
+        """c = d*c + (1-d)*g^2 ; w -= lr*g/sqrt(c + 1e-5) (RMSProp.py:28-36), one launch."""
+        tab, n, max_n = self._args()
+        if n:
+            api.dk_opt_rmsprop_multi(tab, n, max_n, float(self.learning_rate), float(self.decay_rate),
+                                     float(self.grad_scale), runtime.stream())

@@ -1,0 +1,25 @@
+"""Helpers shared by the -m gpu parity tests (they call the CUDA path through the C ABI via the
+Python mirror and compare with the oracle / the golden vectors)."""
+import numpy as np
+
+
+def err(a, b):
+    """normalised max-abs error max|a-b| / max|b|"""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = np.max(np.abs(a - b)) if a.size else 0.0
+    return float(d / max(np.max(np.abs(b)) if b.size else 1.0, 1e-30))
+
+
+def assert_close(a, b, tol, what=""):
+    e = err(a, b)
+    assert e <= tol, "%s: normalised max-abs error %.3e > %.1e" % (what, e, tol)
+
+
+# Tolerances, stated once:
+FP32 = 1e-5      # fp32 bandwidth kernels vs oracle / golden
+FP32_RED = 2e-5  # long fp32 reductions (BN grads, dW of depthwise)
+GEMM = 2e-3      # TF32 tensor-core GEMMs, fwd / dgrad   (fp32 SIMT backend is held to 1e-5 separately)
+GEMM_W = 5e-3    # TF32 wgrad (reduction over N*OH*OW)
+SIMT = 2e-5

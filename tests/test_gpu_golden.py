@@ -1,0 +1,236 @@
+"""-m gpu: every layer of the CUDA path against the golden vectors made from the live reference."""
+import numpy as np
+import pytest
+
+from gpu_util import FP32, FP32_RED, GEMM, GEMM_W, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import types
+    from dorknet_b200.layers.convolution import ConvLayer
+    from dorknet_b200.layers.depthwise_convolution import DepthwiseConvLayer
+    from dorknet_b200.layers.pointwise_convolution import PointwiseConvLayer
+    from dorknet_b200.layers.batch_norm import BatchNormLayer
+    from dorknet_b200.layers.activations import ReLu
+    from dorknet_b200.layers.pooling import GlobalAveragePoolingLayer, MaxPoolLayer
+    from dorknet_b200.layers.dense_layer import DenseLayer
+    from dorknet_b200.layers.residual_block import ResidualBlock
+    from dorknet_b200.layers.losses import SoftmaxWithCrossEntropy
+    from dorknet_b200.network.feed_forward_network import FeedForwardNetwork
+    from dorknet_b200.optimisers.SGD import SGD
+    from dorknet_b200.optimisers.SGDMomentum import SGDMomentum
+    from dorknet_b200.optimisers.RMSProp import RMSProp
+    from dorknet_b200.regularisers.l2 import l2
+    return types.SimpleNamespace(**{k: v for k, v in locals().items() if k != "types"})
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("name", ["conv_k3s1p1", "conv_k5s2p1_half", "conv_k4s2p1", "conv_k3s1p0"])
+def test_conv(golden, L, name, backend):
+    from dorknet_b200 import api
+    d = golden(name)
+    N, C, H, W, F, k, s, p, bias = [int(v) for v in d["meta"]]
+    api.dk_set_gemm_backend(backend)
+    try:
+        lay = L.ConvLayer(name, (F, C, k, k), stride=s, padding=p, with_bias=bool(bias),
+                          weight_regulariser=L.l2(float(d["l2"])) if float(d["l2"]) else None)
+        lay.learned_params["weights"] = d["W"]
+        if bias:
+            lay.learned_params["bias"] = d["b"]
+        tol_f, tol_w = (GEMM, GEMM_W) if backend == 0 else (FP32, FP32_RED)
+        Y = lay.forward(d["X"])
+        assert np.array_equal(lay.im2col_materialise(d["X"]).get(), d["patches"])  # bit-exact index map
+        assert_close(Y.get(), d["Y"], tol_f, "Y")
+        dX = lay.backward(d["dY"])
+        assert dX.shape == d["dX"].shape
+        assert_close(dX.get(), d["dX"], tol_f, "dX")
+        assert_close(lay.grads["weights"].get(), d["dW"], tol_w, "dW")
+        if bias:
+            assert_close(lay.grads["bias"].get(), d["db"], FP32_RED, "db")
+    finally:
+        api.dk_set_gemm_backend(0)
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("name", ["pw_s1", "pw_s2_even", "pw_s2_odd"])
+def test_pointwise(golden, L, name, backend):
+    from dorknet_b200 import api
+    d = golden(name)
+    N, C, H, W, F, s, bias = [int(v) for v in d["meta"]]
+    api.dk_set_gemm_backend(backend)
+    try:
+        lay = L.PointwiseConvLayer(name, stride=s, filter_block_shape=(F, C), with_bias=bool(bias),
+                                   weight_regulariser=L.l2(float(d["l2"])) if float(d["l2"]) else None)
+        lay.learned_params["weights"] = d["W"]
+        if bias:
+            lay.learned_params["bias"] = d["b"]
+        tol_f, tol_w = (GEMM, GEMM_W) if backend == 0 else (FP32, FP32_RED)
+        assert_close(lay.forward(d["X"]).get(), d["Y"], tol_f, "Y")
+        dX = lay.backward(d["dY"])
+        assert dX.shape == d["dX"].shape  # zero-stuffed (OH*s, OW*s): 8x10 for the 7x9 input
+        assert_close(dX.get(), d["dX"], tol_f, "dX")
+        assert_close(lay.grads["weights"].get(), d["dW"], tol_w, "dW")
+        if bias:
+            assert_close(lay.grads["bias"].get(), d["db"], FP32_RED, "db")
+    finally:
+        api.dk_set_gemm_backend(0)
+
+
+@pytest.mark.parametrize("name", ["dw_k3s1p1", "dw_k3s2p1_half", "dw_k3s2p1_int", "dw_k5s1p2"])
+def test_depthwise(golden, L, name):
+    d = golden(name)
+    N, C, H, W, k, s, p, bias = [int(v) for v in d["meta"]]
+    lay = L.DepthwiseConvLayer(name, (C, k, k), stride=s, padding=p, with_bias=bool(bias))
+    lay.learned_params["weights"] = d["W"]
+    if bias:
+        lay.learned_params["bias"] = d["b"]
+    assert_close(lay.forward(d["X"]).get(), d["Y"], FP32, "Y")
+    dX = lay.backward(d["dY"])
+    assert dX.shape == d["dX"].shape
+    assert_close(dX.get(), d["dX"], FP32, "dX")
+    assert_close(lay.grads["weights"].get(), d["dW"], FP32_RED, "dW")
+    if bias:
+        assert_close(lay.grads["bias"].get(), d["db"], FP32_RED, "db")
+
+
+@pytest.mark.parametrize("name,dim", [("bn_4d", 4), ("bn_2d", 2)])
+def test_batchnorm(golden, L, name, dim):
+    d = golden(name)
+    C = d["X1"].shape[1]
+    lay = L.BatchNormLayer(name, input_dimension=dim, incoming_chans=C)
+    lay.learned_params["gamma"], lay.learned_params["beta"] = d["gamma"], d["beta"]
+    assert_close(lay.forward(d["X1"]).get(), d["Y1"], FP32, "Y1")
+    assert_close(lay.non_learned_params["running_mean"].get(), d["rm1"], FP32, "rm1")
+    assert_close(lay.non_learned_params["running_std"].get(), d["rs1"], FP32, "rs1")
+    assert_close(lay.backward(d["dY1"]).get(), d["dX1"], FP32_RED, "dX1")
+    assert_close(lay.grads["gamma"].get(), d["dgamma1"], FP32_RED, "dgamma")
+    assert_close(lay.grads["beta"].get(), d["dbeta1"], FP32_RED, "dbeta")
+    assert lay.grads["gamma"].shape == d["dgamma1"].shape
+    assert_close(lay.forward(d["X2"]).get(), d["Y2"], FP32, "Y2")
+    assert_close(lay.non_learned_params["running_mean"].get(), d["rm2"], FP32, "rm2")
+    assert_close(lay.non_learned_params["running_std"].get(), d["rs2"], FP32, "rs2")
+    assert_close(lay.forward(d["X1"], test_mode=True).get(), d["Ytest"], FP32, "Ytest")
+
+
+@pytest.mark.parametrize("name", ["relu_4d", "relu_2d"])
+def test_relu_bit_exact(golden, L, name):
+    d = golden(name)
+    lay = L.ReLu(name)
+    assert np.array_equal(lay.forward(d["X"]).get(), d["Y"])
+    assert np.array_equal(lay.positive_locs.get(), d["mask"])
+    assert np.array_equal(lay.backward(d["dY"]).get(), d["dX"])
+    assert np.array_equal(lay.forward(d["X"], test_mode=True).get(), d["Ytest"])
+
+
+def test_gap(golden, L):
+    d = golden("gap")
+    lay = L.GlobalAveragePoolingLayer("gap")
+    assert_close(lay.forward(d["X"]).get(), d["Y"], FP32, "Y")
+    assert_close(lay.backward(d["dY"]).get(), d["dX"], FP32, "dX")
+
+
+@pytest.mark.parametrize("s", [2, 4])
+def test_maxpool_bit_exact(golden, L, s):
+    d = golden("maxpool_s%d" % s)
+    lay = L.MaxPoolLayer("mp", None, stride=s)
+    assert np.array_equal(lay.forward(d["X"]).get(), d["Y"])
+    assert np.array_equal(lay.max_locations.get(), d["mask"])  # argmax one-hot: bit-exact, ties included
+    assert np.array_equal(lay.backward(d["dY"]).get(), d["dX"])
+    assert np.array_equal(lay.forward(d["X"], test_mode=True).get(), d["Ytest"])
+    with pytest.raises(ValueError):
+        L.MaxPoolLayer("bad", None, stride=5).forward(d["X"])
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+def test_dense_loss_l2(golden, L, backend):
+    from dorknet_b200 import api
+    d = golden("dense")
+    api.dk_set_gemm_backend(backend)
+    try:
+        tol_f, tol_w = (GEMM, GEMM_W) if backend == 0 else (FP32, FP32_RED)
+        lay = L.DenseLayer("d", 12, 7, weight_regulariser=L.l2(float(d["l2"])))
+        lay.learned_params["weights"], lay.learned_params["bias"] = d["W"], d["b"]
+        assert_close(lay.forward(d["X"]).get(), d["Y"], tol_f, "Y")
+        assert_close(lay.backward(d["dY"]).get(), d["dX"], tol_f, "dX")
+        assert_close(lay.grads["weights"].get(), d["dW"], tol_w, "dW")
+        assert_close(lay.grads["bias"].get(), d["db"], FP32_RED, "db")
+        assert float(lay.regulariser_forward()) == pytest.approx(float(d["reg"]), rel=1e-5)
+    finally:
+        api.dk_set_gemm_backend(0)
+    for nm in ("softmax_hard", "softmax_soft"):
+        s = golden(nm)
+        sm = L.SoftmaxWithCrossEntropy("s")
+        loss, p = sm.forward(s["X"], s["y"])
+        assert float(loss) == pytest.approx(float(s["loss"]), rel=2e-6)
+        assert_close(p.get(), s["p"], FP32, "p")
+        assert_close(sm.backward().get(), s["dX"], FP32, "dX")
+        z, pt = sm.forward(s["X"], None, test_mode=True)
+        assert z == 0
+        assert_close(pt.get(), s["ptest"], FP32, "ptest")
+
+
+@pytest.mark.parametrize("nm", ["opt_sgd", "opt_sgdm", "opt_rmsprop"])
+def test_optimisers(golden, L, nm):
+    d = golden(nm)
+
+    class Net:
+        pass
+    lay = L.DenseLayer("d", 4, 5)
+    lay.learned_params["weights"], lay.learned_params["bias"] = d["w0"].copy(), d["b0"].copy()
+    net = Net()
+    net.layers = [lay]
+    opt = {"opt_sgd": lambda: L.SGD(net, 0.1), "opt_sgdm": lambda: L.SGDMomentum(net, 0.1, 0.9),
+           "opt_rmsprop": lambda: L.RMSProp(net, 0.01, 0.9)}[nm]()
+    lay.to_gpu()
+    for i in range(3):
+        lay.grads["weights"].set(d["gw%d" % i])
+        lay.grads["bias"].set(d["gb%d" % i])
+        opt.update_weights()
+        assert_close(lay.learned_params["weights"].get(), d["w%d" % (i + 1)], 2e-6, "w step %d" % i)
+        assert_close(lay.learned_params["bias"].get(), d["b%d" % (i + 1)], 2e-6, "b step %d" % i)
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+def test_mini_resnet_three_training_steps(golden, L, backend):
+    """conv s2 - BN - ReLU - pw s2 - BN - ReLU - 2 residual blocks (identity and pw-s2 skip) - GAP -
+    dense - softmax, 3 SGDMomentum steps: losses, first-step gradients and final weights."""
+    import importlib.util
+    import os
+    from dorknet_b200 import api
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_defs", os.path.join(os.path.dirname(__file__), "golden", "net_defs.py"))
+    defs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(defs)
+    d = golden("mini_net")
+    api.dk_set_gemm_backend(backend)
+    try:
+        net = defs.build_small_net(L, seed=123)
+        for l in defs.iter_param_layers(net):
+            for k in list(l.learned_params.keys()):
+                l.learned_params[k] = d["init/%s/%s" % (l.layer_name, k)].copy()
+        opt = L.SGDMomentum(net, 0.02, 0.9)
+        tol = 3e-3 if backend == 0 else 2e-4
+        losses = []
+        for step in range(3):
+            loss, scores = net.forward(d["X"], d["y"])
+            losses.append(float(loss))
+            net.backward()
+            if step == 0:
+                assert_close(scores.get(), d["scores0"], tol, "scores0")
+                for l in defs.iter_param_layers(net):
+                    for k in l.grads.keys():
+                        assert_close(l.grads[k].get(), d["grad0/%s/%s" % (l.layer_name, k)], 10 * tol,
+                                     "grad0 %s/%s" % (l.layer_name, k))
+            opt.update_weights()
+        np.testing.assert_allclose(losses, d["losses"], rtol=tol)
+        for l in defs.iter_param_layers(net):
+            for k in l.learned_params.keys():
+                assert_close(l.learned_params[k].get(), d["final/%s/%s" % (l.layer_name, k)], 10 * tol,
+                             "final %s/%s" % (l.layer_name, k))
+        _, st = net.forward(d["X"], None, test_mode=True)
+        assert_close(st.get(), d["scores_test"], 20 * tol, "scores_test")
+    finally:
+        api.dk_set_gemm_backend(0)
