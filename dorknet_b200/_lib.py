@@ -21,6 +21,8 @@ PROTOS = {
     "dk_init": (I, [I]),
     "dk_destroy": (I, []),
     "dk_sm_count": (I, []),
+    "dk_kernel_launches": (ctypes.c_ulonglong, []),
+    "dk_gemm_call_counts": (None, [P, P]),
     "dk_set_gemm_backend": (I, [I]),
     "dk_get_gemm_backend": (I, []),
     "dk_relu_fwd": (I, [P, P, P, L, P]),
@@ -64,7 +66,7 @@ PROTOS = {
 }
 
 # value-returning (not status) functions
-_NO_CHECK = {"dk_version", "dk_last_error", "dk_sm_count", "dk_get_gemm_backend", "dk_bn_ws_bytes",
+_NO_CHECK = {"dk_version", "dk_last_error", "dk_sm_count", "dk_kernel_launches", "dk_gemm_call_counts", "dk_get_gemm_backend", "dk_bn_ws_bytes",
              "dk_dwconv_ws_bytes", "dk_conv2d_ws_bytes", "dk_pwconv_ws_bytes", "dk_dense_ws_bytes"}
 
 
@@ -79,6 +81,15 @@ class DorknetError(RuntimeError):
 
 _cdll = None
 _launches = 0  # kernels-launching C-ABI calls made by this process (bench.py reports it)
+_timer = None  # optional {name: callback(name, args) -> context} installed by set_call_timer()
+
+
+def set_call_timer(timer):
+    """Install (or clear, with None) a per-call timing hook: `timer` maps C-ABI function names to a
+    callable(name, args) returning an object with .stop().  Only the named calls pay for it; bench.py
+    uses it to bracket the dominant kernel family with CUDA events inside the timed region."""
+    global _timer
+    _timer = timer
 
 
 def load():
@@ -111,7 +122,19 @@ def check(rc, name):
 
 
 def launch_count():
+    """C-ABI calls that launch kernels, made by this process."""
     return _launches
+
+
+def kernel_launches():
+    """CUDA kernels actually launched by the library (counted at every launch site)."""
+    return int(load().dk_kernel_launches())
+
+
+def gemm_call_counts():
+    tc, simt = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    load().dk_gemm_call_counts(ctypes.byref(tc), ctypes.byref(simt))
+    return int(tc.value), int(simt.value)
 
 
 class _Api:
@@ -127,7 +150,12 @@ class _Api:
             def wrapped(*a, _fn=fn, _name=name):
                 global _launches
                 _launches += 1
-                rc = _fn(*a)
+                if _timer is not None and _name in _timer:
+                    tok = _timer[_name](_name, a)
+                    rc = _fn(*a)
+                    tok.stop()
+                else:
+                    rc = _fn(*a)
                 if rc != DK_OK:
                     check(rc, _name)
         setattr(self, name, wrapped)

@@ -155,6 +155,46 @@ def asnumpy(a):
     return np.asarray(a)
 
 
+class _SlotArena:
+    """One small device buffer holding every one-float result slot (loss, l2 terms), so reading a
+    DeviceScalar is ONE device->host copy however many terms it has."""
+
+    SIZE = 4096
+
+    def __init__(self):
+        self.buf = None
+        self.used = 0
+        self.host = None
+
+    def alloc(self):
+        torch = _torch()
+        runtime.ensure_init()
+        if self.buf is None:
+            self.buf = torch.zeros(self.SIZE, dtype=torch.float32, device=runtime.device())
+            self.host = torch.zeros(self.SIZE, dtype=torch.float32).pin_memory()
+        if self.used >= self.SIZE:
+            raise RuntimeError("scalar slot arena exhausted")
+        i = self.used
+        self.used += 1
+        a = DeviceArray(self.buf[i:i + 1], (1,))
+        return a, i
+
+    def read(self):
+        """Synchronous snapshot of all slots (one D2H copy on the current stream)."""
+        torch = _torch()
+        self.host[:max(self.used, 1)].copy_(self.buf[:max(self.used, 1)], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.host.numpy()
+
+
+_arena = _SlotArena()
+
+
+def alloc_scalar_slot():
+    """(DeviceArray one-float slot, arena index)"""
+    return _arena.alloc()
+
+
 class DeviceScalar:
     """A lazily-evaluated float living on the device: sum_i coeff_i * slot_i + const.
 
@@ -168,7 +208,7 @@ class DeviceScalar:
     __array_priority__ = 100.0
 
     def __init__(self, terms=(), const=0.0):
-        self.terms = list(terms)  # [(DeviceArray one-float slot, coeff)]
+        self.terms = list(terms)  # [(slot, coeff)]: slot = arena index (int) or any object with .get()
         self.const = float(const)
 
     def _combine(self, other, sign=1.0):
@@ -192,8 +232,14 @@ class DeviceScalar:
 
     def __float__(self):
         total = np.float64(self.const)
+        snap = None
         for slot, coeff in self.terms:
-            total += coeff * float(slot.get().reshape(-1)[0])
+            if isinstance(slot, int):
+                if snap is None:
+                    snap = _arena.read()
+                total += coeff * float(snap[slot])
+            else:
+                total += coeff * float(slot.get().reshape(-1)[0])
         return float(total)
 
     def get(self):

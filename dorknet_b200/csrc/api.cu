@@ -10,6 +10,7 @@ static thread_local char g_err[512] = "";
 static int g_sm_count = 148;
 static int g_device = -1;
 static int g_backend = 0;
+static unsigned long long g_launches = 0;
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -19,6 +20,7 @@ void set_error(const char *fmt, ...) {
 }
 int sm_count() { return g_sm_count; }
 int gemm_backend() { return g_backend; }
+void count_launch() { ++g_launches; }
 
 int init_gemm_tcgen05();  // gemm_tcgen05.cu: opt-in shared memory sizes
 int init_depthwise();     // depthwise.cu
@@ -54,6 +56,8 @@ int dk_destroy(void) {
 }
 
 int dk_sm_count(void) { return dk::g_sm_count; }
+
+unsigned long long dk_kernel_launches(void) { return dk::g_launches; }
 
 int dk_set_gemm_backend(int backend) {
     if (backend != 0 && backend != 1) {

@@ -12,6 +12,7 @@ namespace dk {
 void set_error(const char *fmt, ...);
 int sm_count();
 int gemm_backend();
+void count_launch();  // every kernel launch site goes through DK_LAUNCH_CHECK, which counts it
 
 #define DK_REQUIRE(cond, ...)                 \
     do {                                      \
@@ -32,6 +33,7 @@ int gemm_backend();
 
 #define DK_LAUNCH_CHECK()                                                                      \
     do {                                                                                       \
+        dk::count_launch();                                                                    \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess) {                                                               \
             dk::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

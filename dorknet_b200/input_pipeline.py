@@ -1,0 +1,88 @@
+"""Host -> device input pipeline: pinned double-buffered host staging, the
+H2D copy of batch i+1 on a side stream while batch i trains, and mixup
+(data_loading/image_data_loader.py:100-112: X = lam*X_b + (1-lam)*X_a, same for the one-hot labels)
+done by one kernel on the device instead of on the host."""
+import numpy as np
+
+from . import runtime
+from ._lib import api
+from .array import DeviceArray, empty
+
+
+class HostBatchUploader:
+    """Double-buffered upload of (X, y_one_hot) host batches.
+
+    submit(X, Y) copies into pinned staging memory and enqueues the H2D copy on a side stream;
+    get() returns DeviceArrays once the compute stream has been made to wait for that copy.  With two
+    slots the upload of the next batch overlaps the training step of the current one."""
+
+    def __init__(self, x_shape, y_shape, slots=2):
+        import torch
+        runtime.ensure_init()
+        self.torch = torch
+        self.stream = torch.cuda.Stream(device=runtime.device())
+        self.slots = []
+        for _ in range(slots):
+            self.slots.append(dict(
+                hx=torch.empty(int(np.prod(x_shape)), dtype=torch.float32).pin_memory(),
+                hy=torch.empty(int(np.prod(y_shape)), dtype=torch.float32).pin_memory(),
+                dx=empty(x_shape), dy=empty(y_shape),
+                ready=torch.cuda.Event(), free=torch.cuda.Event()))
+        self.x_shape, self.y_shape = tuple(x_shape), tuple(y_shape)
+        self.bytes_per_batch = 4 * (int(np.prod(x_shape)) + int(np.prod(y_shape)))
+        self._w = 0
+        self._r = 0
+        self._inflight = 0
+
+    def submit(self, X, Y):
+        torch = self.torch
+        s = self.slots[self._w % len(self.slots)]
+        self._w += 1
+        # the consumer of this slot's previous contents must be done before it is overwritten
+        self.stream.wait_event(s["free"])
+        s["hx"].copy_(torch.from_numpy(np.ascontiguousarray(X, np.float32).reshape(-1)))
+        s["hy"].copy_(torch.from_numpy(np.ascontiguousarray(Y, np.float32).reshape(-1)))
+        with torch.cuda.stream(self.stream):
+            s["dx"].t.copy_(s["hx"], non_blocking=True)
+            s["dy"].t.copy_(s["hy"], non_blocking=True)
+            s["ready"].record(self.stream)
+        self._inflight += 1
+
+    def submit_pinned(self, slot_filler=None):
+        """Like submit() when the producer already wrote the pinned staging tensors in place."""
+        torch = self.torch
+        s = self.slots[self._w % len(self.slots)]
+        self._w += 1
+        self.stream.wait_event(s["free"])
+        if slot_filler is not None:
+            slot_filler(s["hx"].numpy().reshape(self.x_shape), s["hy"].numpy().reshape(self.y_shape))
+        with torch.cuda.stream(self.stream):
+            s["dx"].t.copy_(s["hx"], non_blocking=True)
+            s["dy"].t.copy_(s["hy"], non_blocking=True)
+            s["ready"].record(self.stream)
+        self._inflight += 1
+
+    def get(self):
+        """(X, Y) DeviceArrays of the oldest submitted batch; valid until release()."""
+        if self._inflight <= 0:
+            raise RuntimeError("HostBatchUploader.get() with nothing submitted")
+        s = self.slots[self._r % len(self.slots)]
+        self.torch.cuda.current_stream().wait_event(s["ready"])
+        return s["dx"], s["dy"]
+
+    def release(self):
+        """Mark the oldest batch consumed (call after the step that used it has been enqueued)."""
+        s = self.slots[self._r % len(self.slots)]
+        s["free"].record(self.torch.cuda.current_stream())
+        self._r += 1
+        self._inflight -= 1
+
+
+def mixup(Xa, Xb, lam, out=None):
+    """out = lam*Xb + (1-lam)*Xa on the device (image_data_loader.py:102-110)."""
+    if Xa.shape != Xb.shape:
+        raise ValueError("mixup: shapes differ %s vs %s" % (Xa.shape, Xb.shape))
+    if out is None:
+        out = empty(Xa.shape)
+    api.dk_mixup(Xa.ptr, Xb.ptr, out.ptr, float(lam), Xa.size, runtime.stream())
+    return out

@@ -1,5 +1,6 @@
 """SoftmaxWithCrossEntropy (reference: layers/losses.py:5-41)."""
 from .layer import Layer, api, runtime, asarray, DeviceScalar
+from ..array import alloc_scalar_slot
 
 
 class SoftmaxWithCrossEntropy(Layer):
@@ -26,10 +27,12 @@ class SoftmaxWithCrossEntropy(Layer):
         if self.y_one_hot.shape != (B, K):
             raise ValueError("SoftmaxWithCrossEntropy: labels {} do not match scores {}".format(
                 self.y_one_hot.shape, (B, K)))
-        loss = self._buf("loss", (1,))
+        if getattr(self, "_loss_slot", None) is None:
+            self._loss_slot = alloc_scalar_slot()
+        loss, idx = self._loss_slot
         api.dk_softmax_xent_fwd(X.ptr, self.y_one_hot.ptr, p.ptr, loss.ptr, B, K, runtime.stream())
         self.downstream_x = p
-        return DeviceScalar([(loss, 1.0)]), p
+        return DeviceScalar([(idx, 1.0)]), p
 
     def backward(self, upstream_dx=None):
         """(p - y)/B (losses.py:29-34); upstream_dx is not used."""

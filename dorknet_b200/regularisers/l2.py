@@ -3,7 +3,7 @@ import numpy as np
 
 from .. import runtime
 from .._lib import api
-from ..array import DeviceArray, DeviceScalar, empty
+from ..array import DeviceArray, DeviceScalar, alloc_scalar_slot
 
 
 class l2:
@@ -21,9 +21,9 @@ class l2:
             return 0.5 * self.strength * np.sum(np.power(X, 2))
         slot = self._slots.get(X.ptr)
         if slot is None:
-            slot = self._slots[X.ptr] = empty((1,))
-        api.dk_sumsq(X.ptr, slot.ptr, 1.0, X.size, runtime.stream())
-        return DeviceScalar([(slot, 0.5 * float(self.strength))])
+            slot = self._slots[X.ptr] = alloc_scalar_slot()
+        api.dk_sumsq(X.ptr, slot[0].ptr, 1.0, X.size, runtime.stream())
+        return DeviceScalar([(slot[1], 0.5 * float(self.strength))])
 
     def backward(self, X):
         """strength * X (l2.py:16-17).  The layers fold this term into their wgrad kernels; this

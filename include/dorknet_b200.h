@@ -44,6 +44,10 @@ const char *dk_last_error(void);
 int dk_init(int device);
 int dk_destroy(void);
 int dk_sm_count(void);
+/* Number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches). */
+unsigned long long dk_kernel_launches(void);
+/* How many conv / pointwise / dense GEMM calls went to the tcgen05 and the SIMT backend since load. */
+void dk_gemm_call_counts(unsigned long long *tc, unsigned long long *simt);
 /* GEMM backend for conv / pointwise / dense: 0 = tcgen05+TMEM+TMA (product path, default),
  * 1 = plain SIMT implicit GEMM (GPU-side cross-check used by tests only). */
 int dk_set_gemm_backend(int backend);

@@ -12,9 +12,14 @@ def err(a, b):
     return float(d / max(np.max(np.abs(b)) if b.size else 1.0, 1e-30))
 
 
-def assert_close(a, b, tol, what=""):
-    e = err(a, b)
-    assert e <= tol, "%s: normalised max-abs error %.3e > %.1e" % (what, e, tol)
+def assert_close(a, b, tol, what="", atol=0.0):
+    """max|a-b| <= tol*max|b| + atol.  `atol` is for quantities that are zero in exact arithmetic
+    (e.g. dbeta of a BatchNorm that feeds another BatchNorm), where both sides are rounding noise."""
+    a64, b64 = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a64.shape == b64.shape, (a64.shape, b64.shape)
+    d = float(np.max(np.abs(a64 - b64))) if a64.size else 0.0
+    ref = float(np.max(np.abs(b64))) if b64.size else 1.0
+    assert d <= tol * max(ref, 1e-30) + atol, "%s: max-abs error %.3e > %.1e * %.3e + %.1e" % (what, d, tol, ref, atol)
 
 
 # Tolerances, stated once (SURVEY.md A.12):

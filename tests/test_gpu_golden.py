@@ -222,8 +222,9 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
                 assert_close(scores.get(), d["scores0"], tol, "scores0")
                 for l in defs.iter_param_layers(net):
                     for k in l.grads.keys():
+                        # atol: dbeta/dgamma of a BN feeding another BN are zero in exact arithmetic
                         assert_close(l.grads[k].get(), d["grad0/%s/%s" % (l.layer_name, k)], 10 * tol,
-                                     "grad0 %s/%s" % (l.layer_name, k))
+                                     "grad0 %s/%s" % (l.layer_name, k), atol=2e-8)
             opt.update_weights()
         np.testing.assert_allclose(losses, d["losses"], rtol=tol)
         for l in defs.iter_param_layers(net):
