@@ -23,6 +23,7 @@ PROTOS = {
     "dk_sm_count": (I, []),
     "dk_kernel_launches": (ctypes.c_ulonglong, []),
     "dk_gemm_call_counts": (None, [P, P]),
+    "dk_tc_debug_set": (I, [I, I]),
     "dk_set_gemm_backend": (I, [I]),
     "dk_get_gemm_backend": (I, []),
     "dk_relu_fwd": (I, [P, P, P, L, P]),

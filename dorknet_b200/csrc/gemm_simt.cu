@@ -259,6 +259,10 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, const fl
     }
 }
 
+void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st) {
+    splitk_reduce_kernel<<<stream_grid(mn, 256), 256, 0, st>>>(partial, w, out, l2, mn, Z);
+}
+
 template <class AL, class BL, class ST, bool AK, bool BK_>
 static int launch_gemm(AL al, BL bl, ST st, int64_t M, int Nn, int64_t K, int Z, int64_t k_per_split, cudaStream_t s) {
     dim3 grid((unsigned)ceil_div(M, BM), (unsigned)ceil_div(Nn, BN), (unsigned)Z);

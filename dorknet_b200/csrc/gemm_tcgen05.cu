@@ -1,23 +1,493 @@
-// gemm_tcgen05.cu -- tcgen05 / TMEM / TMA GEMM kernels (placeholder until the first GPU bring-up).
+// gemm_tcgen05.cu -- tensor-core GEMMs for pointwise conv / dense on sm_100a:
+// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared-memory stages -> tcgen05.mma kind::tf32 with the
+// accumulator in TMEM -> tcgen05.ld epilogue with coalesced NCHW stores.
+//
+// One persistent, warp-specialised kernel (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected lane), warps 2-5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).  Three mbarrier rings:
+// full/empty per shared-memory stage (TMA <-> MMA) and full/empty per TMEM accumulator (MMA <-> epilogue; two
+// accumulators, so the epilogue of tile t overlaps the loads and MMAs of tile t+1).
+//
+// The NCHW tensors are used in place -- no NHWC copies as in the reference (pointwise_convolution.py:46-55):
+//   forward  Y[n][F,HW]  = W[F,C] . X[n][C,HW]    M = pixels (A = X[n], MN-major), N = F (B = W, K-major),  K = C
+//   dgrad    dX[n][C,HW] = W^T . dY[n][F,HW]      M = pixels (A = dY[n], MN-major), N = C (B = W, MN-major), K = F
+//   wgrad    dW[F,C]     = sum_n dY[n] . X[n]^T   M = F (A = dY[n], K-major), N = C (B = X[n], K-major), K = (n, hw)
+// Putting the pixels on M makes TMEM lane i <-> pixel i, so for every output channel a warp stores 32 consecutive
+// floats (128 B): the epilogue is coalesced straight from registers.  fp32 MN-major operands use the
+// 128B-swizzle-with-32B-atom layout (the only MN-major layout the tensor core accepts for 32-bit types).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "gemm.cuh"
+#include "tc_ptx.cuh"
 
 namespace dk {
 
-int init_gemm_tcgen05() { return DK_OK; }
+using namespace tc;
 
-int tc_conv_fwd(const float *, const float *, const float *, float *, int, int, int, int, int, int, int, int, int,
-                void *, size_t, cudaStream_t) { return DK_ERR_UNSUPPORTED; }
-int tc_conv_dgrad(const float *, const float *, float *, int, int, int, int, int, int, int, int, int, int, int,
-                  void *, size_t, cudaStream_t) { return DK_ERR_UNSUPPORTED; }
-int tc_conv_wgrad(const float *, const float *, const float *, float *, float, int, int, int, int, int, int, int, int,
-                  int, void *, size_t, cudaStream_t) { return DK_ERR_UNSUPPORTED; }
+constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;                 // MMA M
+constexpr int TC_BK = 32;                  // floats of K per stage (= one 128-byte swizzle span)
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+    int mode;       // 0: tile = (batch, m-block, n-block), K loop over k-blocks.  1: tile = (m-block, n-block, split), K loop over (batch, k-block) items
+    int a_mn, b_mn;  // 1 = operand is MN-major in memory (the GEMM's M / N index is the contiguous one)
+    int b_batched;   // mode 0: does B have a batch coordinate (0 for weights)
+    int M, N, K;     // per-batch GEMM extents (mode 1: K = per-image reduction length)
+    int batches;
+    int bn;          // MMA N (multiple of 32, <= 256)
+    int m_blocks, n_blocks, k_blocks;
+    int splits, items_per_split, total_items;  // mode 1
+    int num_tiles;
+    int stages;
+    int epi;         // 0: out[(b*N + n)*ldo + m] (+bias[n]);  1: out[(split*M + m)*N + n]
+    float *out;
+    const float *bias;
+    long long ldo;
+    uint32_t tmem_cols, acc_stride;
+    // MN-major shared-memory descriptor fields (bytes) -- runtime so a bring-up probe can sweep them
+    uint32_t mn_layout, mn_lbo, mn_sbo, mn_kstep;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: stages first (1024-byte aligned), then barriers
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 4;
+    const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+    const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    // number of K iterations of a tile (same in every role)
+    auto tile_iters = [&](int tile) -> int {
+        if (p.mode == 0) return p.k_blocks;
+        const int split = tile / (p.m_blocks * p.n_blocks);
+        const int beg = split * p.items_per_split;
+        int end = beg + p.items_per_split;
+        if (end > p.total_items) end = p.total_items;
+        return end - beg;
+    };
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int b = 0, m0, n0, item0 = 0;
+                if (p.mode == 0) {
+                    const int per_b = p.m_blocks * p.n_blocks;
+                    b = tile / per_b;
+                    const int r = tile - b * per_b;
+                    m0 = (r / p.n_blocks) * TC_BM;
+                    n0 = (r % p.n_blocks) * p.bn;
+                } else {
+                    const int mn = p.m_blocks * p.n_blocks;
+                    const int split = tile / mn;
+                    const int r = tile - split * mn;
+                    m0 = (r / p.n_blocks) * TC_BM;
+                    n0 = (r % p.n_blocks) * p.bn;
+                    item0 = split * p.items_per_split;
+                }
+                const int iters = tile_iters(tile);
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
+                    const uint32_t fb = full_bar(s);
+                    mbar_expect_tx(fb, stage_bytes);
+                    int kb = it, bb = b;
+                    if (p.mode == 1) {
+                        const int kk = item0 + it;
+                        bb = kk / p.k_blocks;
+                        kb = kk - bb * p.k_blocks;
+                    }
+                    const int k0 = kb * TC_BK;
+                    if (p.a_mn) {
+#pragma unroll
+                        for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(sA + j * 4096u, &tmA, fb, m0 + 32 * j, k0, bb);
+                    } else {
+                        tma_load_3d(sA, &tmA, fb, k0, m0, bb);
+                    }
+                    const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
+                    if (p.b_mn) {
+                        for (int j = 0; j < p.bn / 32; ++j) tma_load_3d(sB + j * 4096u, &tmB, fb, n0 + 32 * j, k0, bbB);
+                    } else {
+                        tma_load_3d(sB, &tmB, fb, k0, n0, bbB);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(TC_BM, p.bn, p.a_mn, p.b_mn);
+            int s = 0;
+            uint32_t ph = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+                const int acc = local & 1;
+                const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+                const int iters = tile_iters(tile);
+                mbar_wait(tempty_bar(acc), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.acc_stride;
+                for (int it = 0; it < iters; ++it) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
+                    int nks = TC_BK / 8;
+                    if (p.mode == 0) {
+                        const int rem = p.K - it * TC_BK;
+                        if (rem < TC_BK) nks = (rem + 7) / 8;
+                    }
+#pragma unroll 1
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint64_t ad = p.a_mn ? smem_desc(sA + ks * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                   : smem_desc(sA + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                        const uint64_t bd = p.b_mn ? smem_desc(sB + ks * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                   : smem_desc(sB + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                        mma_tf32(d_tmem, ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    mma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+                mma_commit(tfull_bar(acc));  // accumulator complete
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 2..5) ========================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            const uint32_t aph = (uint32_t)(local >> 1) & 1u;
+            int b = 0, m0, n0, split = 0;
+            if (p.mode == 0) {
+                const int per_b = p.m_blocks * p.n_blocks;
+                b = tile / per_b;
+                const int r = tile - b * per_b;
+                m0 = (r / p.n_blocks) * TC_BM;
+                n0 = (r % p.n_blocks) * p.bn;
+            } else {
+                const int mn = p.m_blocks * p.n_blocks;
+                split = tile / mn;
+                const int r = tile - split * mn;
+                m0 = (r / p.n_blocks) * TC_BM;
+                n0 = (r % p.n_blocks) * p.bn;
+            }
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const int m = m0 + 32 * q + lane;
+            const bool m_ok = m < p.M;
+            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * p.acc_stride;
+            for (int c = 0; c < p.bn; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_row + (uint32_t)c, v);
+                tmem_ld_wait();
+                const int nb = n0 + c;
+                if (p.epi == 0) {
+                    float *o = p.out + ((long long)b * p.N + nb) * p.ldo + m;
+                    if (m_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (nb + j < p.N) {
+                                float r = __uint_as_float(v[j]);
+                                if (p.bias) r += __ldg(p.bias + nb + j);
+                                o[(long long)j * p.ldo] = r;
+                            }
+                        }
+                    }
+                } else {
+                    if (m_ok) {
+                        float *o = p.out + ((long long)split * p.M + m) * p.N + nb;
+                        if (nb + 32 <= p.N && (p.N & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4 *>(o + j) =
+                                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                __uint_as_float(v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < p.N) o[j] = __uint_as_float(v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static bool g_tc_ready = false;
+static int g_mn_layout = LAYOUT_SW128_BASE32B, g_mn_lbo = 4096, g_mn_sbo = 512, g_mn_kstep = 1024;
+static int g_mn_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+static int g_tc_disable_mask = 0;  // bit0 fwd, bit1 dgrad, bit2 wgrad (bring-up / tests)
+
+int init_gemm_tcgen05() {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        g_tc_ready = false;  // dispatcher falls back to the SIMT kernels
+        return DK_OK;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    DK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
+    g_tc_ready = true;
+    return DK_OK;
+}
+
+struct MapKey {
+    const void *ptr;
+    uint64_t d0, d1, d2;
+    uint32_t b0, b1, sw;
+    bool operator==(const MapKey &o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && sw == o.sw;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey &k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.b0); mix(k.b1); mix(k.sw);
+        return h;
+    }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
+// 3-D fp32 tensor map: dims (d0 fastest, d1, d2) with dense strides, box (b0, b1, 1).
+static int make_map(CUtensorMap *out, const float *ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                    CUtensorMapSwizzle sw) {
+    MapKey key{ptr, d0, d1, d2, b0, b1, (uint32_t)sw};
+    {
+        std::lock_guard<std::mutex> g(g_maps_mu);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) {
+            *out = it->second;
+            return DK_OK;
+        }
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for dims (%llu,%llu,%llu) box (%u,%u)", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1);
+        return DK_ERR_CUDA;
+    }
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = *out;
+    return DK_OK;
+}
+
+static bool tma_ok(const void *p, int64_t inner) { return aligned16(p) && (inner % 4) == 0; }
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static void fill_common(TcParams &p) {
+    p.bn = p.N >= 256 ? 256 : round_up(p.N, 32);
+    p.m_blocks = (int)ceil_div(p.M, TC_BM);
+    p.n_blocks = (int)ceil_div(p.N, p.bn);
+    p.k_blocks = (int)ceil_div(p.K, TC_BK);
+    p.acc_stride = p.bn <= 32 ? 32 : p.bn <= 64 ? 64 : p.bn <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * p.acc_stride;
+    const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 4;
+    int st = TC_SMEM_BUDGET / stage_bytes;
+    if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
+    p.stages = st;
+    p.mn_layout = (uint32_t)g_mn_layout;
+    p.mn_lbo = (uint32_t)g_mn_lbo;
+    p.mn_sbo = (uint32_t)g_mn_sbo;
+    p.mn_kstep = (uint32_t)g_mn_kstep;
+}
+
+static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t st) {
+    const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 4;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * TC_MAX_STAGES + 8);
+    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(ta, tb, p);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
+// split plan for wgrad: enough CTAs to fill the machine, but partial sums must stay small next to the inputs
+static void wgrad_plan(int F, int C, int64_t total_items, int64_t in_bytes, int *splits, int *per) {
+    const int tiles = (int)(ceil_div(F, TC_BM) * ceil_div(C, C >= 256 ? 256 : round_up(C, 32)));
+    int64_t s = sm_count() / tiles;
+    const int64_t out_bytes = (int64_t)F * C * 4;
+    const int64_t cap = in_bytes / (4 * out_bytes);
+    if (s > cap) s = cap;
+    if (s > total_items) s = total_items;
+    if (s < 1) s = 1;
+    *per = (int)ceil_div(total_items, s);
+    *splits = (int)ceil_div(total_items, *per);
+}
+
+void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st);
+
+size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p) {
+    if (kh != 1 || kw != 1 || p != 0) return 0;
+    const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
+    const int64_t HW = (int64_t)OH * OW;
+    int splits, per;
+    wgrad_plan(F, C, (int64_t)N * ceil_div(HW, TC_BK), (int64_t)N * HW * (F + C) * 4, &splits, &per);
+    return (size_t)splits * F * C * sizeof(float);
+}
+
+int tc_conv_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
+                int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
+    (void)ws; (void)ws_bytes;
+    if (!g_tc_ready || (g_tc_disable_mask & 1)) return DK_ERR_UNSUPPORTED;
+    if (kh != 1 || kw != 1 || s != 1 || p != 0) return DK_ERR_UNSUPPORTED;  // pointwise, stride 1 (v1)
+    const int64_t HW = (int64_t)H * W;
+    if (!tma_ok(x, HW) || !tma_ok(w, C) || !aligned16(y) || HW > (1 << 30)) return DK_ERR_UNSUPPORTED;
+    TcParams q = {};
+    q.mode = 0; q.a_mn = 1; q.b_mn = 0; q.b_batched = 0;
+    q.M = (int)HW; q.N = F; q.K = C; q.batches = N;
+    fill_common(q);
+    q.num_tiles = N * q.m_blocks * q.n_blocks;
+    q.epi = 0; q.out = y; q.bias = bias; q.ldo = HW;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, x, HW, C, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+    if (rc) return rc;
+    rc = make_map(&tb, w, C, F, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    return tc_launch(ta, tb, q, st);
+}
+
+int tc_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int s,
+                  int p, int OH, int OW, void *ws, size_t ws_bytes, cudaStream_t st) {
+    (void)ws; (void)ws_bytes;
+    if (!g_tc_ready || (g_tc_disable_mask & 2)) return DK_ERR_UNSUPPORTED;
+    if (kh != 1 || kw != 1 || s != 1 || p != 0 || OH != H || OW != W) return DK_ERR_UNSUPPORTED;
+    const int64_t HW = (int64_t)H * W;
+    if (!tma_ok(dy, HW) || !tma_ok(w, C) || !aligned16(dx) || HW > (1 << 30)) return DK_ERR_UNSUPPORTED;
+    TcParams q = {};
+    q.mode = 0; q.a_mn = 1; q.b_mn = 1; q.b_batched = 0;
+    q.M = (int)HW; q.N = C; q.K = F; q.batches = N;
+    fill_common(q);
+    q.num_tiles = N * q.m_blocks * q.n_blocks;
+    q.epi = 0; q.out = dx; q.bias = nullptr; q.ldo = HW;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, dy, HW, F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+    if (rc) return rc;
+    rc = make_map(&tb, w, C, F, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);  // B(k=f, n=c) = W[f][c]: n contiguous
+    if (rc) return rc;
+    return tc_launch(ta, tb, q, st);
+}
+
+int tc_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
+                  int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!g_tc_ready || (g_tc_disable_mask & 4)) return DK_ERR_UNSUPPORTED;
+    if (kh != 1 || kw != 1 || s != 1 || p != 0) return DK_ERR_UNSUPPORTED;
+    const int64_t HW = (int64_t)H * W;
+    if (!tma_ok(dy, HW) || !tma_ok(x, HW) || HW > (1 << 30)) return DK_ERR_UNSUPPORTED;
+    TcParams q = {};
+    q.mode = 1; q.a_mn = 0; q.b_mn = 0; q.b_batched = 1;
+    q.M = F; q.N = C; q.K = (int)HW; q.batches = N;
+    fill_common(q);
+    q.total_items = N * q.k_blocks;
+    wgrad_plan(F, C, q.total_items, (int64_t)N * HW * (F + C) * 4, &q.splits, &q.items_per_split);
+    q.num_tiles = q.m_blocks * q.n_blocks * q.splits;
+    const size_t need = (size_t)q.splits * F * C * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("pointwise wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+        return DK_ERR_WORKSPACE;
+    }
+    q.epi = 1; q.out = reinterpret_cast<float *>(ws); q.bias = nullptr; q.ldo = 0;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, dy, HW, F, N, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_map(&tb, x, HW, C, N, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = tc_launch(ta, tb, q, st);
+    if (rc) return rc;
+    splitk_reduce_launch(q.out, w, dw, l2, (int64_t)F * C, q.splits, st);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
 int tc_dense_fwd(const float *, const float *, const float *, float *, int, int, int, void *, size_t, cudaStream_t) {
     return DK_ERR_UNSUPPORTED;
 }
 int tc_dense_bwd(const float *, const float *, const float *, float *, float *, float, int, int, int, void *, size_t,
                  cudaStream_t) { return DK_ERR_UNSUPPORTED; }
-size_t tc_conv_ws_bytes(int, int, int, int, int, int, int, int, int) { return 0; }
 size_t tc_dense_ws_bytes(int, int, int) { return 0; }
 
 }  // namespace dk
+
+extern "C" {
+/* Bring-up / test knobs for the tensor-core path (not part of the reference-facing ABI):
+ * key 0: disable mask (bit0 fwd, bit1 dgrad, bit2 wgrad); 1: MN-major layout type; 2: LBO bytes; 3: SBO bytes;
+ * 4: bytes per 8-deep K step; 5: TMA swizzle enum for MN-major operands. */
+int dk_tc_debug_set(int key, int value) {
+    switch (key) {
+        case 0: dk::g_tc_disable_mask = value; break;
+        case 1: dk::g_mn_layout = value; break;
+        case 2: dk::g_mn_lbo = value; break;
+        case 3: dk::g_mn_sbo = value; break;
+        case 4: dk::g_mn_kstep = value; break;
+        case 5: dk::g_mn_swizzle = value; break;
+        default: dk::set_error("dk_tc_debug_set: unknown key %d", key); return DK_ERR_INVALID;
+    }
+    {
+        std::lock_guard<std::mutex> g(dk::g_maps_mu);
+        dk::g_maps.clear();
+    }
+    return DK_OK;
+}
+}

@@ -48,6 +48,10 @@ int dk_sm_count(void);
 unsigned long long dk_kernel_launches(void);
 /* How many conv / pointwise / dense GEMM calls went to the tcgen05 and the SIMT backend since load. */
 void dk_gemm_call_counts(unsigned long long *tc, unsigned long long *simt);
+/* Diagnostics for the tensor-core path (bring-up and tests; not a reference call site): key 0 = disable mask
+ * (bit0 fwd, bit1 dgrad, bit2 wgrad -> those calls use the SIMT kernels); keys 1-5 override the MN-major
+ * shared-memory descriptor fields / TMA swizzle mode. */
+int dk_tc_debug_set(int key, int value);
 /* GEMM backend for conv / pointwise / dense: 0 = tcgen05+TMEM+TMA (product path, default),
  * 1 = plain SIMT implicit GEMM (GPU-side cross-check used by tests only). */
 int dk_set_gemm_backend(int backend);
