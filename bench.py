@@ -206,8 +206,9 @@ def cpu_baseline_subprocess(a, spec):
 class CallTimer:
     """CUDA-event brackets around selected C-ABI calls on the launching (current) stream."""
 
-    def __init__(self, torch, bytes_fn):
+    def __init__(self, torch, bytes_fn, by_shape=False):
         self.torch = torch
+        self.by_shape = by_shape
         self.bytes_fn = bytes_fn  # name -> fn(args) -> algorithmic bytes
         self.records = []  # (name, start_event, end_event, bytes)
 
@@ -221,7 +222,8 @@ class CallTimer:
 
     def __call__(self, name, args):
         tok = CallTimer._Tok()
-        tok.timer, tok.name = self, name
+        tok.timer = self
+        tok.name = name if not self.by_shape else name + str(tuple(x for x in args if isinstance(x, int) and 0 < x < 10**6))
         tok.nbytes = self.bytes_fn[name](args)
         tok.e0 = self.torch.cuda.Event(enable_timing=True)
         tok.e0.record()
@@ -370,12 +372,20 @@ def run_ours(a, spec):
     _lib.set_call_timer(None)
     table = full.summary()
     dominant = max(table.items(), key=lambda kv: kv[1][1])[0]
+    if a.per_kernel:
+        shp = CallTimer(torch, BYTES_FN, by_shape=True)
+        _lib.set_call_timer({k: shp for k in BYTES_FN})
+        train_step(*ring[0][2:])
+        torch.cuda.synchronize()
+        _lib.set_call_timer(None)
+        by_shape = shp.summary()
     if a.per_kernel and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(a.per_kernel)), exist_ok=True)
         with open(a.per_kernel, "w") as f:
-            json.dump({k: {"calls": v[0], "ms": v[1], "alg_bytes": v[2],
-                           "GBps": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else None} for k, v in
-                       sorted(table.items(), key=lambda kv: -kv[1][1])}, f, indent=1)
+            fmt = lambda t: {k: {"calls": v[0], "ms": round(v[1], 4), "alg_bytes": v[2],  # noqa: E731
+                                 "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None}
+                             for k, v in sorted(t.items(), key=lambda kv: -kv[1][1])}
+            json.dump({"by_family": fmt(table), "by_call_shape": fmt(by_shape)}, f, indent=1)
 
     # ---- timed region: K steps, inputs resident in HBM, only the dominant family carries event brackets ----
     dom = CallTimer(torch, BYTES_FN)

@@ -117,6 +117,41 @@ class DeviceArray:
     __radd__ = __add__
 
 
+class LazyDeviceArray(DeviceArray):
+    """A DeviceArray whose contents are produced on first use.
+
+    ConvLayer.backward returns its input gradient this way: the reference's container computes the first
+    layer's dX only to drop it (feed_forward_network.py:69-70), so the dgrad kernel -- the most expensive
+    launch of conv0 -- runs only if somebody actually reads the result (`.ptr`, `.t`, `.get()`, `+`).  Like
+    every buffer a layer hands out, it must be consumed before that layer's next backward()."""
+
+    __slots__ = ("_thunk", "_buf")
+
+    def __init__(self, buf, thunk):
+        self._buf = buf
+        self._thunk = thunk
+        self.shape = buf.shape
+        self.dtype = buf.dtype
+
+    def materialise(self):
+        if self._thunk is not None:
+            thunk, self._thunk = self._thunk, None
+            thunk()
+        return self._buf
+
+    @property
+    def t(self):
+        return self.materialise().t
+
+    @t.setter
+    def t(self, value):  # DeviceArray.__init__ is bypassed; nothing assigns t
+        raise AttributeError("LazyDeviceArray.t is read-only")
+
+    @property
+    def is_materialised(self):
+        return self._thunk is None
+
+
 def empty(shape, dtype=np.float32):
     torch = _torch()
     runtime.ensure_init()

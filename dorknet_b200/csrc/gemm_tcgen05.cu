@@ -45,17 +45,205 @@ struct TcParams {
     int splits, items_per_split, total_items;  // mode 1
     int num_tiles;
     int stages;
-    int epi;         // 0: out[(b*N + n)*ldo + m] (+bias[n]);  1: out[(split*M + m)*N + n]
+    int epi;         // 0: out[(b*N + n)*ldo + m] (+bias[n]);  1: out[(split*M + m)*N + n];  2: zero-stuffed strided scatter
     float *out;
     const float *bias;
     long long ldo;
+    int epi_ow, epi_s;  // epi 2: output-pixel row length and the stride of the zero-stuffed scatter
     uint32_t tmem_cols, acc_stride;
     // MN-major shared-memory descriptor fields (bytes) -- runtime so a bring-up probe can sweep them
     uint32_t mn_layout, mn_lbo, mn_sbo, mn_kstep;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+// ---- software-gather operand loaders ---------------------------------------------------------------------
+// Operands TMA cannot describe (stride-2 subsampling, 7x7 planes whose row pitch is not a multiple of 16 bytes,
+// im2col patches) are written into the SAME swizzled stage layout by four loader warps (warps 6-9), which then
+// fence.proxy.async and arrive on the stage's full barrier next to the TMA transaction count.
+//   MN-major functor:  Row row(int b, int m) const;   float load(const Row &, int k) const;
+//   K-major functor:   KCol kcol(int b, int k) const; float load(int r, const KCol &) const;
+struct NoGather {
+    static constexpr bool kGather = false;
+    static constexpr bool kMN = false;
+};
+
+// byte offset of element (m, k) inside an MN-major stage tile (128B swizzle, 32B atom; 32-wide MN blocks of 4 KB)
+__device__ __forceinline__ uint32_t mn_tile_off(int m, int k) {
+    return (uint32_t)(m >> 5) * 4096u + (uint32_t)k * 128u + ((((uint32_t)(m & 31) >> 3) ^ ((uint32_t)k & 3u)) << 5) +
+           ((uint32_t)(m & 7) << 2);
+}
+// byte offset of element (r, k) inside a K-major stage tile (128B swizzle, 16B atom; rows of 128 B)
+__device__ __forceinline__ uint32_t km_tile_off(int r, int k) {
+    return (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// pixels of a [B, K, SH, SW] tensor subsampled by s: element (b, m = oh*OW + ow, k) = src[b][k][oh*s][ow*s]
+struct PixelGatherMN {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = true;
+    const float *src;
+    int K, SH, SW, OW, M, s;
+    struct Row { long long off; bool ok; };
+    __device__ __forceinline__ Row row(int b, int m) const {
+        Row r;
+        r.ok = m < M;
+        const int oh = m / OW, ow = m - oh * OW;
+        r.off = ((long long)b * K * SH + (long long)oh * s) * SW + (long long)ow * s;
+        return r;
+    }
+    __device__ __forceinline__ float load(const Row &r, int k) const {
+        return (r.ok && k < K) ? __ldg(src + r.off + (long long)k * SH * SW) : 0.0f;
+    }
+};
+// same tensor as a K-major operand: rows r = channel, k = pixel index inside image b
+struct PixelGatherKM {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = false;
+    const float *src;
+    int R, SH, SW, OW, P, s;  // R channels, P = OH*OW pixels per image
+    struct KCol { long long off; bool ok; };
+    __device__ __forceinline__ KCol kcol(int b, int k) const {
+        KCol c;
+        c.ok = k < P;
+        const int oh = k / OW, ow = k - oh * OW;
+        c.off = ((long long)b * R * SH + (long long)oh * s) * SW + (long long)ow * s;
+        return c;
+    }
+    __device__ __forceinline__ float load(int r, const KCol &c) const {
+        return (c.ok && r < R) ? __ldg(src + c.off + (long long)r * SH * SW) : 0.0f;
+    }
+};
+
+struct ConvGeom {
+    int C, H, W, F, kh, kw, s, p, OH, OW;
+};
+// im2col patches as the MN-major A of the forward GEMM: (b, m = oh*OW+ow, k = (c*kh+i)*kw+j) (im2col.pyx:33-34)
+struct ConvPatchMN {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = true;
+    const float *x;
+    ConvGeom g;
+    struct Row { long long base; int ih0, iw0; bool ok; };
+    __device__ __forceinline__ Row row(int b, int m) const {
+        Row r;
+        r.ok = m < g.OH * g.OW;
+        const int oh = m / g.OW, ow = m - oh * g.OW;
+        r.base = (long long)b * g.C * g.H * g.W;
+        r.ih0 = oh * g.s - g.p;
+        r.iw0 = ow * g.s - g.p;
+        return r;
+    }
+    __device__ __forceinline__ float load(const Row &r, int k) const {
+        const int kk = g.kh * g.kw;
+        const int c = k / kk, t = k - c * kk;
+        const int i = t / g.kw, j = t - i * g.kw;
+        const int ih = r.ih0 + i, iw = r.iw0 + j;
+        if (!r.ok || c >= g.C || ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0.0f;
+        return __ldg(x + r.base + ((long long)c * g.H + ih) * g.W + iw);
+    }
+};
+// the same patches as the K-major B of the wgrad GEMM: rows r = (c,i,j), k = output pixel of image b
+struct ConvPatchKM {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = false;
+    const float *x;
+    ConvGeom g;
+    struct KCol { long long base; int ih0, iw0; bool ok; };
+    __device__ __forceinline__ KCol kcol(int b, int k) const {
+        KCol c;
+        c.ok = k < g.OH * g.OW;
+        const int oh = k / g.OW, ow = k - oh * g.OW;
+        c.base = (long long)b * g.C * g.H * g.W;
+        c.ih0 = oh * g.s - g.p;
+        c.iw0 = ow * g.s - g.p;
+        return c;
+    }
+    __device__ __forceinline__ float load(int r, const KCol &kc) const {
+        const int kk = g.kh * g.kw;
+        const int c = r / kk, t = r - c * kk;
+        const int i = t / g.kw, j = t - i * g.kw;
+        const int ih = kc.ih0 + i, iw = kc.iw0 + j;
+        if (!kc.ok || c >= g.C || ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0.0f;
+        return __ldg(x + kc.base + ((long long)c * g.H + ih) * g.W + iw);
+    }
+};
+// a dense row-major matrix [R][K] as a K-major operand (filters W[F][C*kh*kw] whose pitch TMA cannot take)
+struct MatrixKM {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = false;
+    const float *w;
+    int R, K;
+    struct KCol { int k; bool ok; };
+    __device__ __forceinline__ KCol kcol(int, int k) const { return KCol{k, k < K}; }
+    __device__ __forceinline__ float load(int r, const KCol &c) const {
+        return (c.ok && r < R) ? __ldg(w + (long long)r * K + c.k) : 0.0f;
+    }
+};
+// dgrad of a general convolution, gather form of col2im (im2col.pyx:209-234): A(b, m = input pixel, k = (f,i,j))
+struct ConvDgradMN {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = true;
+    const float *dy;
+    ConvGeom g;
+    struct Row { long long base; int hp, wp; bool ok; };
+    __device__ __forceinline__ Row row(int b, int m) const {
+        Row r;
+        r.ok = m < g.H * g.W;
+        const int h = m / g.W, w = m - h * g.W;
+        r.base = (long long)b * g.F * g.OH * g.OW;
+        r.hp = h + g.p;
+        r.wp = w + g.p;
+        return r;
+    }
+    __device__ __forceinline__ float load(const Row &r, int k) const {
+        const int kk = g.kh * g.kw;
+        const int f = k / kk, t = k - f * kk;
+        const int i = t / g.kw, j = t - i * g.kw;
+        const int ti = r.hp - i, tj = r.wp - j;
+        if (!r.ok || f >= g.F || ti < 0 || tj < 0 || (ti % g.s) != 0 || (tj % g.s) != 0) return 0.0f;
+        const int oh = ti / g.s, ow = tj / g.s;
+        if (oh >= g.OH || ow >= g.OW) return 0.0f;
+        return __ldg(dy + r.base + ((long long)f * g.OH + oh) * g.OW + ow);
+    }
+};
+// ... and its B(n = c, k = (f,i,j)) = W[f][c][i][j] as a K-major operand
+struct ConvDgradWKM {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = false;
+    const float *w;
+    ConvGeom g;
+    struct KCol { long long off; bool ok; };
+    __device__ __forceinline__ KCol kcol(int, int k) const {
+        const int kk = g.kh * g.kw;
+        const int f = k / kk, t = k - f * kk;
+        return KCol{(long long)f * g.C * kk + t, f < g.F};
+    }
+    __device__ __forceinline__ float load(int r, const KCol &c) const {
+        return (c.ok && r < g.C) ? __ldg(w + c.off + (long long)r * g.kh * g.kw) : 0.0f;
+    }
+};
+
+// W[F][C] read as the K-major operand B(n = c, k = f) of the pointwise dgrad when C is not TMA-friendly
+struct MatrixTransposedKM {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = false;
+    const float *w;
+    int R, K;  // R = C (rows of the operand), K = F; element (r, k) = w[k*R + r]
+    struct KCol { long long off; bool ok; };
+    __device__ __forceinline__ KCol kcol(int, int k) const { return KCol{(long long)k * R, k < K}; }
+    __device__ __forceinline__ float load(int r, const KCol &c) const { return (c.ok && r < R) ? __ldg(w + c.off + r) : 0.0f; }
+};
+
+constexpr int TC_GATHER_THREADS = TC_THREADS + 128;
+
+template <class AG, class BG>
+__global__ void __launch_bounds__((AG::kGather || BG::kGather) ? TC_GATHER_THREADS : TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+               const AG ag, const BG bg) {
+    constexpr bool kAnyGather = AG::kGather || BG::kGather;
+    constexpr bool kAnyTma = !AG::kGather || !BG::kGather;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: stages first (1024-byte aligned), then barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -71,10 +259,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
+        if (!AG::kGather) tma_prefetch_desc(&tmA);
+        if (!BG::kGather) tma_prefetch_desc(&tmB);
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), (kAnyTma ? 1u : 0u) + (kAnyGather ? 4u : 0u));
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -105,7 +293,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        if (kAnyTma && lane == 0) {
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -129,7 +317,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
                     const uint32_t fb = full_bar(s);
-                    mbar_expect_tx(fb, stage_bytes);
+                    mbar_expect_tx(fb, (AG::kGather ? 0u : (uint32_t)TC_A_BYTES) + (BG::kGather ? 0u : b_bytes));
                     int kb = it, bb = b;
                     if (p.mode == 1) {
                         const int kk = item0 + it;
@@ -137,17 +325,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         kb = kk - bb * p.k_blocks;
                     }
                     const int k0 = kb * TC_BK;
-                    if (p.a_mn) {
+                    if (!AG::kGather) {
+                        if (p.a_mn) {
 #pragma unroll
-                        for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(sA + j * 4096u, &tmA, fb, m0 + 32 * j, k0, bb);
-                    } else {
-                        tma_load_3d(sA, &tmA, fb, k0, m0, bb);
+                            for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(sA + j * 4096u, &tmA, fb, m0 + 32 * j, k0, bb);
+                        } else {
+                            tma_load_3d(sA, &tmA, fb, k0, m0, bb);
+                        }
                     }
-                    const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
-                    if (p.b_mn) {
-                        for (int j = 0; j < p.bn / 32; ++j) tma_load_3d(sB + j * 4096u, &tmB, fb, n0 + 32 * j, k0, bbB);
-                    } else {
-                        tma_load_3d(sB, &tmB, fb, k0, n0, bbB);
+                    if (!BG::kGather) {
+                        const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
+                        if (p.b_mn) {
+                            for (int j = 0; j < p.bn / 32; ++j) tma_load_3d(sB + j * 4096u, &tmB, fb, n0 + 32 * j, k0, bbB);
+                        } else {
+                            tma_load_3d(sB, &tmB, fb, k0, n0, bbB);
+                        }
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
@@ -190,6 +382,77 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mma_commit(tfull_bar(acc));  // accumulator complete
             }
         }
+    } else if (warp >= 6) {
+        // ================================ gather loaders (warps 6..9) ===================
+        if constexpr (kAnyGather) {
+            const int lw = warp - 6;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int b = 0, m0, n0, item0 = 0;
+                if (p.mode == 0) {
+                    const int per_b = p.m_blocks * p.n_blocks;
+                    b = tile / per_b;
+                    const int r = tile - b * per_b;
+                    m0 = (r / p.n_blocks) * TC_BM;
+                    n0 = (r % p.n_blocks) * p.bn;
+                } else {
+                    const int mn = p.m_blocks * p.n_blocks;
+                    const int split = tile / mn;
+                    const int r = tile - split * mn;
+                    m0 = (r / p.n_blocks) * TC_BM;
+                    n0 = (r % p.n_blocks) * p.bn;
+                    item0 = split * p.items_per_split;
+                }
+                const int iters = tile_iters(tile);
+                for (int it = 0; it < iters; ++it) {
+                    int kb = it, bb = b;
+                    if (p.mode == 1) {
+                        const int kk = item0 + it;
+                        bb = kk / p.k_blocks;
+                        kb = kk - bb * p.k_blocks;
+                    }
+                    const int k0 = kb * TC_BK;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
+                    if constexpr (AG::kGather) {
+                        if constexpr (AG::kMN) {
+                            // lanes along m (coalesced pixels), this warp owns k = lw*8 .. lw*8+7
+                            typename AG::Row rows[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) rows[j] = ag.row(bb, m0 + 32 * j + lane);
+#pragma unroll 2
+                            for (int kk = 0; kk < 8; ++kk) {
+                                const int k = lw * 8 + kk;
+                                float v[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[j] = ag.load(rows[j], k0 + k);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) st_shared_f32(sA + mn_tile_off(32 * j + lane, k), v[j]);
+                            }
+                        } else {
+                            // lanes along k, this warp owns rows lw, lw+4, ...
+                            const auto kc = ag.kcol(bb, k0 + lane);
+#pragma unroll 4
+                            for (int r = lw; r < TC_BM; r += 4)
+                                st_shared_f32(sA + km_tile_off(r, lane), ag.load(m0 + r, kc));
+                        }
+                    }
+                    if constexpr (BG::kGather) {
+                        static_assert(!BG::kMN, "gathered B operands are K-major");
+                        const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
+                        const auto kc = bg.kcol(bbB, k0 + lane);
+#pragma unroll 4
+                        for (int r = lw; r < p.bn; r += 4)
+                            st_shared_f32(sB + km_tile_off(r, lane), bg.load(n0 + r, kc));
+                    }
+                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar(s));
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
     } else {
         // ================================ epilogue (warps 2..5) ========================
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
@@ -230,6 +493,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 float r = __uint_as_float(v[j]);
                                 if (p.bias) r += __ldg(p.bias + nb + j);
                                 o[(long long)j * p.ldo] = r;
+                            }
+                        }
+                    }
+                } else if (p.epi == 2) {
+                    // pointwise dgrad with stride s: zero-stuffed dX[b][n][oh*s + di][ow*s + dj] (pointwise_convolution.py:68-72)
+                    if (m_ok) {
+                        const int oh = m / p.epi_ow, ow = m - oh * p.epi_ow;
+                        const int st2 = p.epi_s;
+                        const long long plane = (long long)p.epi_ow * st2 * ((long long)(p.M / p.epi_ow) * st2);
+                        float *o = p.out + ((long long)b * p.N + nb) * plane + ((long long)oh * st2) * (p.epi_ow * st2) + ow * st2;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (nb + j < p.N) {
+                                float *oj = o + (long long)j * plane;
+                                for (int di = 0; di < st2; ++di)
+                                    for (int dj = 0; dj < st2; ++dj)
+                                        oj[(long long)di * (p.epi_ow * st2) + dj] = (di | dj) ? 0.0f : __uint_as_float(v[j]);
                             }
                         }
                     }
@@ -280,7 +560,6 @@ int init_gemm_tcgen05() {
         return DK_OK;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    DK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
     g_tc_ready = true;
     return DK_OK;
 }
@@ -355,20 +634,31 @@ static void fill_common(TcParams &p) {
     p.mn_kstep = (uint32_t)g_mn_kstep;
 }
 
-static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, cudaStream_t st) {
+template <class AG, class BG>
+static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, const AG &ag, const BG &bg,
+                     cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        DK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<AG, BG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_BUDGET + 2048));
+        attr_set = true;
+    }
     const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 4;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * TC_MAX_STAGES + 8);
-    int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-    tc_gemm_kernel<<<grid, TC_THREADS, smem, st>>>(ta, tb, p);
+    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    const int threads = (AG::kGather || BG::kGather) ? TC_GATHER_THREADS : TC_THREADS;
+    tc_gemm_kernel<AG, BG><<<grid, threads, smem, st>>>(ta, tb, p, ag, bg);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }
 
-// split plan for wgrad: enough CTAs to fill the machine, but partial sums must stay small next to the inputs
-static void wgrad_plan(int F, int C, int64_t total_items, int64_t in_bytes, int *splits, int *per) {
-    const int tiles = (int)(ceil_div(F, TC_BM) * ceil_div(C, C >= 256 ? 256 : round_up(C, 32)));
+// split plan for wgrad-type GEMMs (output [M][N], reduction over `total_items` k-blocks): enough CTAs to fill the
+// machine, but the partial sums must stay small next to the inputs
+static void split_plan(int M, int N, int64_t total_items, int64_t in_bytes, int *splits, int *per) {
+    const int bn = N >= 256 ? 256 : round_up(N, 32);
+    const int tiles = (int)(ceil_div(M, TC_BM) * ceil_div(N, bn));
     int64_t s = sm_count() / tiles;
-    const int64_t out_bytes = (int64_t)F * C * 4;
+    const int64_t out_bytes = (int64_t)M * N * 4;
     const int64_t cap = in_bytes / (4 * out_bytes);
     if (s > cap) s = cap;
     if (s > total_items) s = total_items;
@@ -379,69 +669,77 @@ static void wgrad_plan(int F, int C, int64_t total_items, int64_t in_bytes, int 
 
 void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st);
 
-size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p) {
-    if (kh != 1 || kw != 1 || p != 0) return 0;
-    const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
-    const int64_t HW = (int64_t)OH * OW;
-    int splits, per;
-    wgrad_plan(F, C, (int64_t)N * ceil_div(HW, TC_BK), (int64_t)N * HW * (F + C) * 4, &splits, &per);
-    return (size_t)splits * F * C * sizeof(float);
+static ConvGeom mk_geom(int C, int H, int W, int F, int kh, int kw, int s, int p) {
+    ConvGeom g{C, H, W, F, kh, kw, s, p, (H + 2 * p - kh) / s + 1, (W + 2 * p - kw) / s + 1};
+    return g;
 }
 
-int tc_conv_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
-                int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
-    (void)ws; (void)ws_bytes;
-    if (!g_tc_ready || (g_tc_disable_mask & 1)) return DK_ERR_UNSUPPORTED;
-    if (kh != 1 || kw != 1 || s != 1 || p != 0) return DK_ERR_UNSUPPORTED;  // pointwise, stride 1 (v1)
-    const int64_t HW = (int64_t)H * W;
-    if (!tma_ok(x, HW) || !tma_ok(w, C) || !aligned16(y) || HW > (1 << 30)) return DK_ERR_UNSUPPORTED;
+size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p) {
+    const ConvGeom g = mk_geom(C, H, W, F, kh, kw, s, p);
+    const int64_t P = (int64_t)g.OH * g.OW;
+    const int Kf = C * kh * kw;
+    int splits, per;
+    split_plan(F, Kf, (int64_t)N * ceil_div(P, TC_BK), (int64_t)N * P * (F + Kf) * 4, &splits, &per);
+    return (size_t)splits * F * Kf * sizeof(float);
+}
+
+static bool dims_ok(int64_t a, int64_t b) { return a > 0 && b > 0 && a < (1 << 30) && b < (1 << 30); }
+
+// ---- pointwise (1x1, pad 0, stride s) ------------------------------------------------------------------------
+static int pw_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int s,
+                  cudaStream_t st) {
+    const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
+    const int64_t P = (int64_t)OH * OW;
+    if (!tma_ok(w, C) || !dims_ok(P, (int64_t)H * W)) return DK_ERR_UNSUPPORTED;
     TcParams q = {};
     q.mode = 0; q.a_mn = 1; q.b_mn = 0; q.b_batched = 0;
-    q.M = (int)HW; q.N = F; q.K = C; q.batches = N;
+    q.M = (int)P; q.N = F; q.K = C; q.batches = N;
     fill_common(q);
     q.num_tiles = N * q.m_blocks * q.n_blocks;
-    q.epi = 0; q.out = y; q.bias = bias; q.ldo = HW;
-    CUtensorMap ta, tb;
-    int rc = make_map(&ta, x, HW, C, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+    q.epi = 0; q.out = y; q.bias = bias; q.ldo = P;
+    CUtensorMap ta = {}, tb;
+    int rc = make_map(&tb, w, C, F, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map(&tb, w, C, F, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
-    return tc_launch(ta, tb, q, st);
+    if (s == 1 && tma_ok(x, P)) {
+        rc = make_map(&ta, x, P, C, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+        if (rc) return rc;
+        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+    }
+    return tc_launch(ta, tb, q, PixelGatherMN{x, C, H, W, OW, (int)P, s}, NoGather{}, st);
 }
 
-int tc_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int s,
-                  int p, int OH, int OW, void *ws, size_t ws_bytes, cudaStream_t st) {
-    (void)ws; (void)ws_bytes;
-    if (!g_tc_ready || (g_tc_disable_mask & 2)) return DK_ERR_UNSUPPORTED;
-    if (kh != 1 || kw != 1 || s != 1 || p != 0 || OH != H || OW != W) return DK_ERR_UNSUPPORTED;
-    const int64_t HW = (int64_t)H * W;
-    if (!tma_ok(dy, HW) || !tma_ok(w, C) || !aligned16(dx) || HW > (1 << 30)) return DK_ERR_UNSUPPORTED;
+static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, int OH, int OW, int F, int s, cudaStream_t st) {
+    const int64_t P = (int64_t)OH * OW;
+    if (!tma_ok(w, C) || !dims_ok(P, P * s * s)) return DK_ERR_UNSUPPORTED;
     TcParams q = {};
     q.mode = 0; q.a_mn = 1; q.b_mn = 1; q.b_batched = 0;
-    q.M = (int)HW; q.N = C; q.K = F; q.batches = N;
+    q.M = (int)P; q.N = C; q.K = F; q.batches = N;
     fill_common(q);
     q.num_tiles = N * q.m_blocks * q.n_blocks;
-    q.epi = 0; q.out = dx; q.bias = nullptr; q.ldo = HW;
-    CUtensorMap ta, tb;
-    int rc = make_map(&ta, dy, HW, F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+    q.out = dx; q.bias = nullptr; q.ldo = P;
+    q.epi = s == 1 ? 0 : 2; q.epi_ow = OW; q.epi_s = s;
+    CUtensorMap ta = {}, tb;
+    int rc = make_map(&tb, w, C, F, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);  // B(k=f, n=c) = W[f][c]: n contiguous
     if (rc) return rc;
-    rc = make_map(&tb, w, C, F, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);  // B(k=f, n=c) = W[f][c]: n contiguous
-    if (rc) return rc;
-    return tc_launch(ta, tb, q, st);
+    if (tma_ok(dy, P)) {
+        rc = make_map(&ta, dy, P, F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+        if (rc) return rc;
+        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+    }
+    return tc_launch(ta, tb, q, PixelGatherMN{dy, F, OH, OW, OW, (int)P, 1}, NoGather{}, st);
 }
 
-int tc_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
-                  int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
-    if (!g_tc_ready || (g_tc_disable_mask & 4)) return DK_ERR_UNSUPPORTED;
-    if (kh != 1 || kw != 1 || s != 1 || p != 0) return DK_ERR_UNSUPPORTED;
-    const int64_t HW = (int64_t)H * W;
-    if (!tma_ok(dy, HW) || !tma_ok(x, HW) || HW > (1 << 30)) return DK_ERR_UNSUPPORTED;
+static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
+                    int s, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
+    const int64_t P = (int64_t)OH * OW;
+    if (!dims_ok(P, (int64_t)H * W)) return DK_ERR_UNSUPPORTED;
     TcParams q = {};
     q.mode = 1; q.a_mn = 0; q.b_mn = 0; q.b_batched = 1;
-    q.M = F; q.N = C; q.K = (int)HW; q.batches = N;
+    q.M = F; q.N = C; q.K = (int)P; q.batches = N;
     fill_common(q);
     q.total_items = N * q.k_blocks;
-    wgrad_plan(F, C, q.total_items, (int64_t)N * HW * (F + C) * 4, &q.splits, &q.items_per_split);
+    split_plan(F, C, q.total_items, (int64_t)N * P * (F + C) * 4, &q.splits, &q.items_per_split);
     q.num_tiles = q.m_blocks * q.n_blocks * q.splits;
     const size_t need = (size_t)q.splits * F * C * sizeof(float);
     if (ws == nullptr || ws_bytes < need) {
@@ -449,16 +747,118 @@ int tc_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, fl
         return DK_ERR_WORKSPACE;
     }
     q.epi = 1; q.out = reinterpret_cast<float *>(ws); q.bias = nullptr; q.ldo = 0;
-    CUtensorMap ta, tb;
-    int rc = make_map(&ta, dy, HW, F, N, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap ta = {}, tb = {};
+    const bool a_tma = tma_ok(dy, P), b_tma = (s == 1) && tma_ok(x, P);
+    int rc = DK_OK;
+    if (a_tma) rc = make_map(&ta, dy, P, F, N, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_map(&tb, x, HW, C, N, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (b_tma) rc = make_map(&tb, x, P, C, N, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = tc_launch(ta, tb, q, st);
+    const PixelGatherKM ga{dy, F, OH, OW, OW, (int)P, 1}, gb{x, C, H, W, OW, (int)P, s};
+    if (a_tma && b_tma) rc = tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+    else if (a_tma) rc = tc_launch(ta, tb, q, NoGather{}, gb, st);
+    else rc = tc_launch(ta, tb, q, ga, gb, st);
     if (rc) return rc;
     splitk_reduce_launch(q.out, w, dw, l2, (int64_t)F * C, q.splits, st);
     DK_LAUNCH_CHECK();
     return DK_OK;
+}
+
+// ---- general convolution as an implicit GEMM (patches gathered by the loader warps) -------------------------------
+static int cv_fwd(const float *x, const float *w, const float *bias, float *y, int N, const ConvGeom &g, cudaStream_t st) {
+    const int64_t P = (int64_t)g.OH * g.OW;
+    const int Kf = g.C * g.kh * g.kw;
+    if (!dims_ok(P, (int64_t)g.H * g.W)) return DK_ERR_UNSUPPORTED;
+    TcParams q = {};
+    q.mode = 0; q.a_mn = 1; q.b_mn = 0; q.b_batched = 0;
+    q.M = (int)P; q.N = g.F; q.K = Kf; q.batches = N;
+    fill_common(q);
+    q.num_tiles = N * q.m_blocks * q.n_blocks;
+    q.epi = 0; q.out = y; q.bias = bias; q.ldo = P;
+    CUtensorMap ta = {}, tb = {};
+    const ConvPatchMN ga{x, g};
+    if (tma_ok(w, Kf)) {
+        int rc = make_map(&tb, w, Kf, g.F, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        return tc_launch(ta, tb, q, ga, NoGather{}, st);
+    }
+    return tc_launch(ta, tb, q, ga, MatrixKM{w, g.F, Kf}, st);
+}
+
+static int cv_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, const ConvGeom &g, void *ws,
+                    size_t ws_bytes, cudaStream_t st) {
+    const int64_t P = (int64_t)g.OH * g.OW;
+    const int Kf = g.C * g.kh * g.kw;
+    if (!dims_ok(P, (int64_t)g.H * g.W)) return DK_ERR_UNSUPPORTED;
+    TcParams q = {};
+    q.mode = 1; q.a_mn = 0; q.b_mn = 0; q.b_batched = 1;
+    q.M = g.F; q.N = Kf; q.K = (int)P; q.batches = N;
+    fill_common(q);
+    q.total_items = N * q.k_blocks;
+    split_plan(g.F, Kf, q.total_items, (int64_t)N * P * (g.F + Kf) * 4, &q.splits, &q.items_per_split);
+    q.num_tiles = q.m_blocks * q.n_blocks * q.splits;
+    const size_t need = (size_t)q.splits * g.F * Kf * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("conv wgrad: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+        return DK_ERR_WORKSPACE;
+    }
+    q.epi = 1; q.out = reinterpret_cast<float *>(ws); q.bias = nullptr; q.ldo = 0;
+    CUtensorMap ta = {}, tb = {};
+    const ConvPatchKM gb{x, g};
+    int rc;
+    if (tma_ok(dy, P)) {
+        rc = make_map(&ta, dy, P, g.F, N, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = tc_launch(ta, tb, q, NoGather{}, gb, st);
+    } else {
+        rc = tc_launch(ta, tb, q, PixelGatherKM{dy, g.F, g.OH, g.OW, g.OW, (int)P, 1}, gb, st);
+    }
+    if (rc) return rc;
+    splitk_reduce_launch(q.out, w, dw, l2, (int64_t)g.F * Kf, q.splits, st);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
+static int cv_dgrad(const float *dy, const float *w, float *dx, int N, const ConvGeom &g, cudaStream_t st) {
+    const int64_t HW = (int64_t)g.H * g.W;
+    if (!dims_ok(HW, (int64_t)g.OH * g.OW)) return DK_ERR_UNSUPPORTED;
+    TcParams q = {};
+    q.mode = 0; q.a_mn = 1; q.b_mn = 0; q.b_batched = 0;
+    q.M = (int)HW; q.N = g.C; q.K = g.F * g.kh * g.kw; q.batches = N;
+    fill_common(q);
+    q.num_tiles = N * q.m_blocks * q.n_blocks;
+    q.epi = 0; q.out = dx; q.bias = nullptr; q.ldo = HW;
+    CUtensorMap ta = {}, tb = {};
+    return tc_launch(ta, tb, q, ConvDgradMN{dy, g}, ConvDgradWKM{w, g}, st);
+}
+
+int tc_conv_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
+                int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
+    (void)ws; (void)ws_bytes;
+    if (!g_tc_ready || (g_tc_disable_mask & 1)) return DK_ERR_UNSUPPORTED;
+    if (kh == 1 && kw == 1 && p == 0) return pw_fwd(x, w, bias, y, N, C, H, W, F, s, st);
+    if (g_tc_disable_mask & 8) return DK_ERR_UNSUPPORTED;
+    return cv_fwd(x, w, bias, y, N, mk_geom(C, H, W, F, kh, kw, s, p), st);
+}
+
+int tc_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int s,
+                  int p, int OH, int OW, void *ws, size_t ws_bytes, cudaStream_t st) {
+    (void)ws; (void)ws_bytes;
+    if (!g_tc_ready || (g_tc_disable_mask & 2)) return DK_ERR_UNSUPPORTED;
+    if (kh == 1 && kw == 1 && p == 0) {
+        if (H != OH * s || W != OW * s) return DK_ERR_UNSUPPORTED;
+        return pw_dgrad(dy, w, dx, N, C, OH, OW, F, s, st);
+    }
+    if (g_tc_disable_mask & 8) return DK_ERR_UNSUPPORTED;
+    return cv_dgrad(dy, w, dx, N, mk_geom(C, H, W, F, kh, kw, s, p), st);
+}
+
+int tc_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
+                  int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!g_tc_ready || (g_tc_disable_mask & 4)) return DK_ERR_UNSUPPORTED;
+    if (kh == 1 && kw == 1 && p == 0) return pw_wgrad(dy, x, w, dw, l2, N, C, H, W, F, s, ws, ws_bytes, st);
+    if (g_tc_disable_mask & 8) return DK_ERR_UNSUPPORTED;
+    return cv_wgrad(dy, x, w, dw, l2, N, mk_geom(C, H, W, F, kh, kw, s, p), ws, ws_bytes, st);
 }
 
 int tc_dense_fwd(const float *, const float *, const float *, float *, int, int, int, void *, size_t, cudaStream_t) {
@@ -472,8 +872,8 @@ size_t tc_dense_ws_bytes(int, int, int) { return 0; }
 
 extern "C" {
 /* Bring-up / test knobs for the tensor-core path (not part of the reference-facing ABI):
- * key 0: disable mask (bit0 fwd, bit1 dgrad, bit2 wgrad); 1: MN-major layout type; 2: LBO bytes; 3: SBO bytes;
- * 4: bytes per 8-deep K step; 5: TMA swizzle enum for MN-major operands. */
+ * key 0: disable mask (bit0 fwd, bit1 dgrad, bit2 wgrad, bit3 non-pointwise convs); 1: MN-major layout type;
+ * 2: LBO bytes; 3: SBO bytes; 4: bytes per 8-deep K step; 5: TMA swizzle enum for MN-major operands. */
 int dk_tc_debug_set(int key, int value) {
     switch (key) {
         case 0: dk::g_tc_disable_mask = value; break;

@@ -2,6 +2,7 @@
 import numpy as np
 
 from .layer import Layer, api, runtime, asarray
+from ..array import LazyDeviceArray
 
 
 class ConvLayer(Layer):
@@ -17,7 +18,9 @@ class ConvLayer(Layer):
         self.weight_regulariser = weight_regulariser
         self.weight_initialiser = weight_initialiser
         self.with_bias = with_bias
-        self.needs_input_grad = True  # set False on a first layer to skip the (discarded) dgrad
+        # "lazy": dX is computed when first read (a first layer's dX is dropped by the container, so its dgrad
+        # never runs); True: always compute; False: return None
+        self.needs_input_grad = "lazy"
         if filter_block_shape:
             self.num_filters, self.filter_chans, self.f_rows, self.f_cols = filter_block_shape
             if self.weight_initialiser == "glorot_uniform":
@@ -88,8 +91,14 @@ class ConvLayer(Layer):
         if not self.needs_input_grad:
             return None
         dx = self._buf("dx", self.input_shape)
-        api.dk_conv2d_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, H, W, self.num_filters, self.f_rows, self.f_cols,
-                            self.stride, self.padding, ws, wsn, st)
+
+        def dgrad():
+            ws2, wsn2 = self._scratch(N, C, H, W)
+            api.dk_conv2d_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, H, W, self.num_filters, self.f_rows, self.f_cols,
+                                self.stride, self.padding, ws2, wsn2, runtime.stream())
+        if self.needs_input_grad == "lazy":
+            return LazyDeviceArray(dx, dgrad)
+        dgrad()
         return dx
 
     def im2col_materialise(self, X):

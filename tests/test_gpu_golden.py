@@ -213,6 +213,10 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
                 l.learned_params[k] = d["init/%s/%s" % (l.layer_name, k)].copy()
         opt = L.SGDMomentum(net, 0.02, 0.9)
         tol = 3e-3 if backend == 0 else 2e-4
+        # TF32 (backend 0) noise floor for gradients that are small because they cancel (BN gamma/beta in front of
+        # another BN): measured against the largest gradient of the whole net, not against the tensor's own maximum
+        gscale = max(float(np.max(np.abs(d[k]))) for k in d.files if k.startswith("grad0/"))
+        floor = 2e-3 * gscale if backend == 0 else 2e-8
         losses = []
         for step in range(3):
             loss, scores = net.forward(d["X"], d["y"])
@@ -224,7 +228,7 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
                     for k in l.grads.keys():
                         # atol: dbeta/dgamma of a BN feeding another BN are zero in exact arithmetic
                         assert_close(l.grads[k].get(), d["grad0/%s/%s" % (l.layer_name, k)], 10 * tol,
-                                     "grad0 %s/%s" % (l.layer_name, k), atol=2e-8)
+                                     "grad0 %s/%s" % (l.layer_name, k), atol=floor)
             opt.update_weights()
         np.testing.assert_allclose(losses, d["losses"], rtol=tol)
         for l in defs.iter_param_layers(net):
