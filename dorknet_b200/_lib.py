@@ -24,6 +24,7 @@ PROTOS = {
     "dk_kernel_launches": (ctypes.c_ulonglong, []),
     "dk_gemm_call_counts": (None, [P, P]),
     "dk_tc_debug_set": (I, [I, I]),
+    "dk_dw_debug_set": (I, [I]),
     "dk_set_gemm_backend": (I, [I]),
     "dk_get_gemm_backend": (I, []),
     "dk_relu_fwd": (I, [P, P, P, L, P]),
@@ -60,9 +61,9 @@ PROTOS = {
     "dk_softmax_xent_fwd": (I, [P, P, P, P, I, I, P]),
     "dk_softmax_xent_bwd": (I, [P, P, P, I, I, P]),
     "dk_sumsq": (I, [P, P, F, L, P]),
-    "dk_opt_sgd_multi": (I, [P, I, L, F, F, P]),
-    "dk_opt_sgdm_multi": (I, [P, I, L, F, F, F, P]),
-    "dk_opt_rmsprop_multi": (I, [P, I, L, F, F, F, P]),
+    "dk_opt_sgd_multi": (I, [P, I, L, F, F, P, P]),
+    "dk_opt_sgdm_multi": (I, [P, I, L, F, F, F, P, P]),
+    "dk_opt_rmsprop_multi": (I, [P, I, L, F, F, F, P, P]),
     "dk_mixup": (I, [P, P, P, F, L, P]),
 }
 

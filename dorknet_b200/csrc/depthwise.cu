@@ -450,6 +450,15 @@ static int dw_geom(DwGeom &g, int N, int C, int H, int W, int kh, int kw, int s,
     return DK_OK;
 }
 
+// register-window fast path for 3x3 / stride 1 / pad 1 (depthwise_rows.cu)
+size_t dw_rows_ws_bytes(int N, int C, int H, int W, int kh, int kw, int s, int p);
+int dw_rows_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int kh, int kw,
+                int s, int p, cudaStream_t st);
+int dw_rows_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
+                float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, void *ws, size_t ws_bytes,
+                cudaStream_t st);
+static int g_dw_rows_enabled = 1;
+
 int init_depthwise() {
     // budgets are within the 48 KB default for forward; backward may slightly exceed with the filter stash
     return DK_OK;
@@ -489,7 +498,9 @@ extern "C" {
 size_t dk_dwconv_ws_bytes(int N, int C, int H, int W, int kh, int kw, int stride, int pad) {
     DwGeom g;
     if (dw_geom(g, N, C, H, W, kh, kw, stride, pad, true, "dk_dwconv_ws_bytes")) return 0;
-    return (size_t)g.planes * g.bands * (kh * kw + 1) * sizeof(float);
+    const size_t tiles = (size_t)g.planes * g.bands * (kh * kw + 1) * sizeof(float);
+    const size_t rows = dw_rows_ws_bytes(N, C, H, W, kh, kw, stride, pad);
+    return tiles > rows ? tiles : rows;
 }
 
 int dk_dwconv_fwd(const float *x, const float *w, const float *bias, float *y, const float *in_scale,
@@ -501,6 +512,10 @@ int dk_dwconv_fwd(const float *x, const float *w, const float *bias, float *y, c
     DK_REQUIRE(x && w && y, "dk_dwconv_fwd: NULL pointer");
     DK_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "dk_dwconv_fwd: in_scale/in_shift must come together");
     cudaStream_t st = as_stream(stream);
+    if (g_dw_rows_enabled && in_scale == nullptr) {
+        rc = dw_rows_fwd(x, w, bias, y, N, C, H, W, kh, kw, stride, pad, st);
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     if (kh == 3 && kw == 3 && stride == 1) return dw_launch_fwd<3, 3, 1>(x, w, bias, y, in_scale, in_shift, in_relu, g, st);
     if (kh == 3 && kw == 3 && stride == 2) return dw_launch_fwd<3, 3, 2>(x, w, bias, y, in_scale, in_shift, in_relu, g, st);
     return dw_launch_fwd<0, 0, 0>(x, w, bias, y, in_scale, in_shift, in_relu, g, st);
@@ -515,6 +530,10 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
     if (rc) return rc;
     DK_REQUIRE(dy && x && w && dx && dw, "dk_dwconv_bwd: NULL pointer");
     DK_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "dk_dwconv_bwd: in_scale/in_shift must come together");
+    if (g_dw_rows_enabled && in_scale == nullptr) {
+        rc = dw_rows_bwd(dy, x, w, dx, dw, dbias, dx_add, l2, N, C, H, W, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream));
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     const size_t need = (size_t)g.planes * g.bands * (kh * kw + 1) * sizeof(float);
     if (ws == nullptr || ws_bytes < need) {
         set_error("dk_dwconv_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, need);
@@ -528,6 +547,12 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
     if (rc) return rc;
     dw_reduce_kernel<<<C, 128, 0, st>>>(partial, w, dw, dbias, l2, N, C, g.bands, kh * kw);
     DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
+/* test hook: 0 = always use the shared-memory tile kernels, 1 = register-window fast path where it applies */
+int dk_dw_debug_set(int enable_rows) {
+    g_dw_rows_enabled = enable_rows;
     return DK_OK;
 }
 

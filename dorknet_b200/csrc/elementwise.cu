@@ -194,7 +194,13 @@ enum { OPT_SGD = 0, OPT_SGDM = 1, OPT_RMSPROP = 2 };
 
 template <int KIND>
 __global__ void __launch_bounds__(OPT_THREADS)
-opt_multi_kernel(const dk_opt_tensor *__restrict__ table, float lr, float hp, float grad_scale) {
+opt_multi_kernel(const dk_opt_tensor *__restrict__ table, float lr, float hp, float grad_scale,
+                 const float *__restrict__ hyper) {
+    if (hyper) {  // hyper-parameters live in device memory: a captured CUDA graph sees later changes
+        lr = hyper[0];
+        hp = hyper[1];
+        grad_scale = hyper[2];
+    }
     const dk_opt_tensor t = table[blockIdx.y];
     const int64_t start = (int64_t)blockIdx.x * OPT_CHUNK;
     if (start >= t.n) return;
@@ -219,12 +225,12 @@ opt_multi_kernel(const dk_opt_tensor *__restrict__ table, float lr, float hp, fl
 
 template <int KIND>
 static int launch_opt(const dk_opt_tensor *table, int num_tensors, int64_t max_n, float lr, float hp,
-                      float grad_scale, cudaStream_t st) {
+                      float grad_scale, const float *hyper, cudaStream_t st) {
     if (num_tensors <= 0 || max_n <= 0) return DK_OK;
     DK_REQUIRE(table != nullptr, "optimiser: NULL tensor table");
     DK_REQUIRE(num_tensors <= 65535, "optimiser: too many tensors (%d)", num_tensors);
     dim3 grid((unsigned)ceil_div(max_n, OPT_CHUNK), (unsigned)num_tensors);
-    opt_multi_kernel<KIND><<<grid, OPT_THREADS, 0, st>>>(table, lr, hp, grad_scale);
+    opt_multi_kernel<KIND><<<grid, OPT_THREADS, 0, st>>>(table, lr, hp, grad_scale, hyper);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }
@@ -343,16 +349,16 @@ int dk_sumsq(const float *w, float *out, float scale, int64_t n, dk_stream_t str
 }
 
 int dk_opt_sgd_multi(const dk_opt_tensor *table, int num_tensors, int64_t max_n, float lr, float grad_scale,
-                     dk_stream_t stream) {
-    return launch_opt<OPT_SGD>(table, num_tensors, max_n, lr, 0.0f, grad_scale, as_stream(stream));
+                     const float *hyper, dk_stream_t stream) {
+    return launch_opt<OPT_SGD>(table, num_tensors, max_n, lr, 0.0f, grad_scale, hyper, as_stream(stream));
 }
 int dk_opt_sgdm_multi(const dk_opt_tensor *table, int num_tensors, int64_t max_n, float lr, float momentum,
-                      float grad_scale, dk_stream_t stream) {
-    return launch_opt<OPT_SGDM>(table, num_tensors, max_n, lr, momentum, grad_scale, as_stream(stream));
+                      float grad_scale, const float *hyper, dk_stream_t stream) {
+    return launch_opt<OPT_SGDM>(table, num_tensors, max_n, lr, momentum, grad_scale, hyper, as_stream(stream));
 }
 int dk_opt_rmsprop_multi(const dk_opt_tensor *table, int num_tensors, int64_t max_n, float lr, float decay,
-                         float grad_scale, dk_stream_t stream) {
-    return launch_opt<OPT_RMSPROP>(table, num_tensors, max_n, lr, decay, grad_scale, as_stream(stream));
+                         float grad_scale, const float *hyper, dk_stream_t stream) {
+    return launch_opt<OPT_RMSPROP>(table, num_tensors, max_n, lr, decay, grad_scale, hyper, as_stream(stream));
 }
 
 }  // extern "C"

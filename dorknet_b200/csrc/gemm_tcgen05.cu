@@ -48,7 +48,7 @@ struct TcParams {
     int epi;         // 0: out[(b*N + n)*ldo + m] (+bias[n]);  1: out[(split*M + m)*N + n];  2: zero-stuffed strided scatter
     float *out;
     const float *bias;
-    long long ldo;
+    int ldo;
     int epi_ow, epi_s;  // epi 2: output-pixel row length and the stride of the zero-stuffed scatter
     uint32_t tmem_cols, acc_stride;
     // MN-major shared-memory descriptor fields (bytes) -- runtime so a bring-up probe can sweep them
@@ -421,7 +421,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             typename AG::Row rows[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) rows[j] = ag.row(bb, m0 + 32 * j + lane);
-#pragma unroll 2
+#pragma unroll 4
                             for (int kk = 0; kk < 8; ++kk) {
                                 const int k = lw * 8 + kk;
                                 float v[4];
@@ -433,7 +433,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         } else {
                             // lanes along k, this warp owns rows lw, lw+4, ...
                             const auto kc = ag.kcol(bb, k0 + lane);
-#pragma unroll 4
+#pragma unroll 16
                             for (int r = lw; r < TC_BM; r += 4)
                                 st_shared_f32(sA + km_tile_off(r, lane), ag.load(m0 + r, kc));
                         }
@@ -442,7 +442,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         static_assert(!BG::kMN, "gathered B operands are K-major");
                         const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
                         const auto kc = bg.kcol(bbB, k0 + lane);
-#pragma unroll 4
+#pragma unroll 16
                         for (int r = lw; r < p.bn; r += 4)
                             st_shared_f32(sB + km_tile_off(r, lane), bg.load(n0 + r, kc));
                     }
@@ -485,14 +485,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld_wait();
                 const int nb = n0 + c;
                 if (p.epi == 0) {
+                    // lane <-> pixel: for every output channel the warp stores 32 consecutive floats (one 128 B line)
                     float *o = p.out + ((long long)b * p.N + nb) * p.ldo + m;
                     if (m_ok) {
+                        if (nb + 32 <= p.N && p.bias == nullptr) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (nb + j < p.N) {
-                                float r = __uint_as_float(v[j]);
-                                if (p.bias) r += __ldg(p.bias + nb + j);
-                                o[(long long)j * p.ldo] = r;
+                            for (int j = 0; j < 32; ++j) o[(long long)j * p.ldo] = __uint_as_float(v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (nb + j < p.N) {
+                                    float r = __uint_as_float(v[j]);
+                                    if (p.bias) r += __ldg(p.bias + nb + j);
+                                    o[(long long)j * p.ldo] = r;
+                                }
                             }
                         }
                     }
@@ -548,6 +554,7 @@ static EncodeTiledFn g_encode = nullptr;
 static bool g_tc_ready = false;
 static int g_mn_layout = LAYOUT_SW128_BASE32B, g_mn_lbo = 4096, g_mn_sbo = 512, g_mn_kstep = 1024;
 static int g_mn_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+static int g_l2_promo = (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
 static int g_tc_disable_mask = 0;  // bit0 fwd, bit1 dgrad, bit2 wgrad (bring-up / tests)
 
 int init_gemm_tcgen05() {
@@ -600,7 +607,7 @@ static int make_map(CUtensorMap *out, const float *ptr, uint64_t d0, uint64_t d1
     cuuint32_t box[3] = {b0, b1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, (CUtensorMapL2promotion)g_l2_promo,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for dims (%llu,%llu,%llu) box (%u,%u)", (int)r,
@@ -659,7 +666,11 @@ static void split_plan(int M, int N, int64_t total_items, int64_t in_bytes, int 
     const int tiles = (int)(ceil_div(M, TC_BM) * ceil_div(N, bn));
     int64_t s = sm_count() / tiles;
     const int64_t out_bytes = (int64_t)M * N * 4;
-    const int64_t cap = in_bytes / (4 * out_bytes);
+    // partial sums are written once and read once: keep them under ~1/4 of the input bytes, but never refuse the
+    // first 32 MB of them (tiny layers would otherwise run on a handful of SMs)
+    int64_t cap = in_bytes / (4 * out_bytes);
+    const int64_t cap_abs = (32ll << 20) / out_bytes;
+    if (cap < cap_abs) cap = cap_abs;
     if (s > cap) s = cap;
     if (s > total_items) s = total_items;
     if (s < 1) s = 1;
@@ -696,7 +707,7 @@ static int pw_fwd(const float *x, const float *w, const float *bias, float *y, i
     q.M = (int)P; q.N = F; q.K = C; q.batches = N;
     fill_common(q);
     q.num_tiles = N * q.m_blocks * q.n_blocks;
-    q.epi = 0; q.out = y; q.bias = bias; q.ldo = P;
+    q.epi = 0; q.out = y; q.bias = bias; q.ldo = (int)P;
     CUtensorMap ta = {}, tb;
     int rc = make_map(&tb, w, C, F, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -716,7 +727,7 @@ static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     q.M = (int)P; q.N = C; q.K = F; q.batches = N;
     fill_common(q);
     q.num_tiles = N * q.m_blocks * q.n_blocks;
-    q.out = dx; q.bias = nullptr; q.ldo = P;
+    q.out = dx; q.bias = nullptr; q.ldo = (int)P;
     q.epi = s == 1 ? 0 : 2; q.epi_ow = OW; q.epi_s = s;
     CUtensorMap ta = {}, tb;
     int rc = make_map(&tb, w, C, F, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);  // B(k=f, n=c) = W[f][c]: n contiguous
@@ -774,7 +785,7 @@ static int cv_fwd(const float *x, const float *w, const float *bias, float *y, i
     q.M = (int)P; q.N = g.F; q.K = Kf; q.batches = N;
     fill_common(q);
     q.num_tiles = N * q.m_blocks * q.n_blocks;
-    q.epi = 0; q.out = y; q.bias = bias; q.ldo = P;
+    q.epi = 0; q.out = y; q.bias = bias; q.ldo = (int)P;
     CUtensorMap ta = {}, tb = {};
     const ConvPatchMN ga{x, g};
     if (tma_ok(w, Kf)) {
@@ -827,7 +838,7 @@ static int cv_dgrad(const float *dy, const float *w, float *dx, int N, const Con
     q.M = (int)HW; q.N = g.C; q.K = g.F * g.kh * g.kw; q.batches = N;
     fill_common(q);
     q.num_tiles = N * q.m_blocks * q.n_blocks;
-    q.epi = 0; q.out = dx; q.bias = nullptr; q.ldo = HW;
+    q.epi = 0; q.out = dx; q.bias = nullptr; q.ldo = (int)HW;
     CUtensorMap ta = {}, tb = {};
     return tc_launch(ta, tb, q, ConvDgradMN{dy, g}, ConvDgradWKM{w, g}, st);
 }
@@ -882,6 +893,7 @@ int dk_tc_debug_set(int key, int value) {
         case 3: dk::g_mn_sbo = value; break;
         case 4: dk::g_mn_kstep = value; break;
         case 5: dk::g_mn_swizzle = value; break;
+        case 6: dk::g_l2_promo = value; break;  // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
         default: dk::set_error("dk_tc_debug_set: unknown key %d", key); return DK_ERR_INVALID;
     }
     {

@@ -11,9 +11,12 @@ class RMSProp(MultiTensorOptimiser):
         self.decay_rate = decay_rate
         self.grad_cache = {}
 
+    def _second_hyper(self):
+        return self.decay_rate
+
     def update_weights(self):
         """c = d*c + (1-d)*g^2 ; w -= lr*g/sqrt(c + 1e-5) (RMSProp.py:28-36), one launch."""
         tab, n, max_n = self._args()
         if n:
             api.dk_opt_rmsprop_multi(tab, n, max_n, float(self.learning_rate), float(self.decay_rate),
-                                     float(self.grad_scale), runtime.stream())
+                                     float(self.grad_scale), self.push_hyper(), runtime.stream())

@@ -15,4 +15,5 @@ class SGD(MultiTensorOptimiser):
         """w += -lr * g for every tensor of the update set, one launch."""
         tab, n, max_n = self._args()
         if n:
-            api.dk_opt_sgd_multi(tab, n, max_n, float(self.learning_rate), float(self.grad_scale), runtime.stream())
+            api.dk_opt_sgd_multi(tab, n, max_n, float(self.learning_rate), float(self.grad_scale), self.push_hyper(),
+                                 runtime.stream())

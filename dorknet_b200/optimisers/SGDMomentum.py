@@ -11,9 +11,12 @@ class SGDMomentum(MultiTensorOptimiser):
         self.momentum = momentum
         self.grad_cache = {}  # layer -> {param name -> DeviceArray velocity}; allocated on first update
 
+    def _second_hyper(self):
+        return self.momentum
+
     def update_weights(self):
         """v = -lr*g + momentum*v ; w += v (SGDMomentum.py:31-39), one launch."""
         tab, n, max_n = self._args()
         if n:
             api.dk_opt_sgdm_multi(tab, n, max_n, float(self.learning_rate), float(self.momentum),
-                                  float(self.grad_scale), runtime.stream())
+                                  float(self.grad_scale), self.push_hyper(), runtime.stream())

@@ -44,6 +44,9 @@ class MultiTensorOptimiser:
         self.grad_scale = 1.0  # set to 1/world_size by the data-parallel wrapper
         self._table = None
         self._sig = None
+        self._hyper = None       # device {lr, momentum/decay, grad_scale}
+        self._hyper_host = None  # pinned staging
+        self._hyper_vals = None
 
     def set_learning_rate(self, new_lr):
         self.learning_rate = new_lr
@@ -84,3 +87,20 @@ class MultiTensorOptimiser:
     def _args(self):
         self._build_table()
         return self._table.data_ptr(), self._n, self._max_n
+
+    def _second_hyper(self):
+        return 0.0
+
+    def push_hyper(self):
+        """Mirror (lr, momentum/decay, grad_scale) into device memory; returns the device pointer.  The kernel
+        reads them from there, so a CUDA-graph replay of update_weights() follows set_learning_rate()."""
+        import torch
+        vals = (float(self.learning_rate), float(self._second_hyper()), float(self.grad_scale))
+        if self._hyper is None:
+            self._hyper = torch.zeros(4, dtype=torch.float32, device=runtime.device())
+            self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        if vals != self._hyper_vals:
+            self._hyper_host[0], self._hyper_host[1], self._hyper_host[2] = vals
+            self._hyper.copy_(self._hyper_host, non_blocking=True)
+            self._hyper_vals = vals
+        return self._hyper.data_ptr()

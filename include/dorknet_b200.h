@@ -52,6 +52,8 @@ void dk_gemm_call_counts(unsigned long long *tc, unsigned long long *simt);
  * (bit0 fwd, bit1 dgrad, bit2 wgrad -> those calls use the SIMT kernels); keys 1-5 override the MN-major
  * shared-memory descriptor fields / TMA swizzle mode. */
 int dk_tc_debug_set(int key, int value);
+/* Depthwise: 1 (default) = register-window kernels for 3x3 / stride 1 / pad 1, 0 = shared-memory tile kernels only. */
+int dk_dw_debug_set(int enable_rows);
 /* GEMM backend for conv / pointwise / dense: 0 = tcgen05+TMEM+TMA (product path, default),
  * 1 = plain SIMT implicit GEMM (GPU-side cross-check used by tests only). */
 int dk_set_gemm_backend(int backend);
@@ -184,7 +186,9 @@ int dk_sumsq(const float *w, float *out, float scale, int64_t n, dk_stream_t str
 
 /* ---- optimisers: optimisers/SGD.py:20-24, SGDMomentum.py:31-39, RMSProp.py:28-36 ----------- */
 /* One fused multi-tensor launch.  `table` is a DEVICE array of num_tensors descriptors;
- * grad_scale multiplies every gradient first (1/world_size after a data-parallel all-reduce). */
+ * grad_scale multiplies every gradient first (1/world_size after a data-parallel all-reduce).
+ * `hyper` (nullable) is a DEVICE array {lr, momentum-or-decay, grad_scale}: when given it overrides the scalar
+ * arguments, so a training step captured in a CUDA graph follows later set_learning_rate() calls. */
 typedef struct {
     float *param;
     const float *grad;
@@ -192,13 +196,13 @@ typedef struct {
     int64_t n;
 } dk_opt_tensor;
 int dk_opt_sgd_multi(const dk_opt_tensor *table, int num_tensors, int64_t max_n,
-                     float lr, float grad_scale, dk_stream_t stream);
+                     float lr, float grad_scale, const float *hyper, dk_stream_t stream);
 /* v = -lr*g + momentum*v ; w += v */
 int dk_opt_sgdm_multi(const dk_opt_tensor *table, int num_tensors, int64_t max_n,
-                      float lr, float momentum, float grad_scale, dk_stream_t stream);
+                      float lr, float momentum, float grad_scale, const float *hyper, dk_stream_t stream);
 /* c = decay*c + (1-decay)*g^2 ; w -= lr*g/sqrt(c + 1e-5) */
 int dk_opt_rmsprop_multi(const dk_opt_tensor *table, int num_tensors, int64_t max_n,
-                         float lr, float decay, float grad_scale, dk_stream_t stream);
+                         float lr, float decay, float grad_scale, const float *hyper, dk_stream_t stream);
 
 /* ---- input pipeline (next row): data_loading/image_data_loader.py:100-112 ---- */
 /* out = lam*xb + (1-lam)*xa  (mixup of two batches / label sets) */

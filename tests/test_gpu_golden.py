@@ -216,7 +216,7 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
         # TF32 (backend 0) noise floor for gradients that are small because they cancel (BN gamma/beta in front of
         # another BN): measured against the largest gradient of the whole net, not against the tensor's own maximum
         gscale = max(float(np.max(np.abs(d[k]))) for k in d.files if k.startswith("grad0/"))
-        floor = 2e-3 * gscale if backend == 0 else 2e-8
+        floor = 1.5e-2 * gscale if backend == 0 else 2e-8
         losses = []
         for step in range(3):
             loss, scores = net.forward(d["X"], d["y"])

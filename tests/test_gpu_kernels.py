@@ -1,0 +1,175 @@
+"""-m gpu: the CUDA kernels against the oracle (oracle/oracle.py) on seeded inputs, at shapes chosen to hit every
+kernel variant: register-window vs tile depthwise (vector widths 4/2/1, row bands, stride 2), TMA vs software-gather
+tcgen05 GEMM operands (stride 2, 7x7 planes, odd channel counts), implicit-GEMM convolutions, split-K plans.
+All calls go through the C ABI via the layer classes."""
+import numpy as np
+import pytest
+
+from gpu_util import FP32, FP32_RED, GEMM, GEMM_W, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+DW_CASES = [
+    # N, C, H, W, k, s, p, bias
+    (3, 8, 56, 56, 3, 1, 1, False),   # vec 4, bands
+    (2, 16, 28, 28, 3, 1, 1, True),   # vec 4
+    (2, 24, 14, 14, 3, 1, 1, False),  # vec 2
+    (3, 40, 7, 7, 3, 1, 1, True),     # vec 1
+    (1, 5, 9, 112, 3, 1, 1, False),   # 28 strips/row
+    (1, 3, 12, 224, 3, 1, 1, False),  # a row spans two warps (56 strips)
+    (2, 8, 11, 13, 3, 1, 1, False),   # odd sizes -> scalar strips
+    (2, 8, 56, 56, 3, 2, 1, False),   # stride 2 (x.5 patch count): tile kernel
+    (2, 6, 15, 15, 5, 1, 2, True),    # 5x5: generic tile kernel
+]
+
+
+@pytest.mark.parametrize("rows", [1, 0])
+@pytest.mark.parametrize("case", DW_CASES)
+def test_depthwise_vs_oracle(O, case, rows):
+    from dorknet_b200 import api
+    from dorknet_b200.layers.depthwise_convolution import DepthwiseConvLayer
+    N, C, H, W, k, s, p, bias = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    Wt = rng.standard_normal((C, k, k)).astype(np.float32)
+    b = rng.standard_normal(C).astype(np.float32) if bias else None
+    api.dk_dw_debug_set(rows)
+    try:
+        lay = DepthwiseConvLayer("dw", (C, k, k), stride=s, padding=p, with_bias=bias)
+        lay.learned_params["weights"] = Wt
+        if bias:
+            lay.learned_params["bias"] = b
+        Y = lay.forward(X)
+        Yo, cache = O.depthwise_fwd(X, Wt, b, s, p)
+        assert Y.shape == Yo.shape
+        assert_close(Y.get(), Yo, FP32, "Y")
+        dY = rng.standard_normal(Yo.shape).astype(np.float32)
+        dXo, g = O.depthwise_bwd(dY, Wt, cache, s, p, 0.0, bias)
+        dX = lay.backward(dY)
+        assert_close(dX.get(), dXo, FP32, "dX")
+        assert_close(lay.grads["weights"].get(), g["weights"], 5 * FP32_RED, "dW")
+        if bias:
+            assert_close(lay.grads["bias"].get(), g["bias"], 5 * FP32_RED, "db")
+        # residual join folded into the backward
+        add = rng.standard_normal(X.shape).astype(np.float32)
+        from dorknet_b200.array import asarray
+        dX2 = lay.backward(dY, dx_add=asarray(add))
+        assert_close(dX2.get(), dXo + add, FP32, "dX + skip")
+    finally:
+        api.dk_dw_debug_set(1)
+
+
+def test_depthwise_backward_is_deterministic():
+    from dorknet_b200.layers.depthwise_convolution import DepthwiseConvLayer
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((4, 32, 56, 56)).astype(np.float32)
+    dY = rng.standard_normal((4, 32, 56, 56)).astype(np.float32)
+    lay = DepthwiseConvLayer("dw", (32, 3, 3), stride=1, padding=1, with_bias=True)
+    lay.forward(X)
+    lay.backward(dY)
+    a = lay.grads["weights"].get().copy(), lay.grads["bias"].get().copy()
+    for _ in range(3):
+        lay.backward(dY)
+        assert np.array_equal(lay.grads["weights"].get(), a[0]) and np.array_equal(lay.grads["bias"].get(), a[1])
+
+
+PW_CASES = [
+    # N, C, F, H, W, s
+    (2, 64, 64, 8, 16, 1), (3, 64, 128, 28, 28, 1), (2, 256, 256, 14, 14, 1), (2, 40, 48, 10, 10, 1),
+    (2, 64, 64, 14, 14, 2), (2, 64, 128, 15, 15, 2), (2, 256, 512, 7, 7, 1), (3, 512, 512, 7, 7, 1),
+    (2, 64, 64, 112, 112, 2), (2, 24, 40, 9, 7, 3), (2, 6, 10, 5, 5, 1),
+]
+
+
+@pytest.mark.parametrize("case", PW_CASES)
+def test_pointwise_tcgen05_vs_oracle(O, case):
+    from dorknet_b200 import _lib
+    from dorknet_b200.layers.pointwise_convolution import PointwiseConvLayer
+    from dorknet_b200.regularisers.l2 import l2
+    N, C, F, H, W, s = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    Wt = (rng.standard_normal((F, C)) / np.sqrt(C)).astype(np.float32)
+    b = rng.standard_normal(F).astype(np.float32)
+    lay = PointwiseConvLayer("p", stride=s, filter_block_shape=(F, C), with_bias=True, weight_regulariser=l2(1e-2))
+    lay.learned_params["weights"], lay.learned_params["bias"] = Wt, b
+    tc0, _ = _lib.gemm_call_counts()
+    Y = lay.forward(X)
+    Yo, cache = O.pointwise_fwd(X, Wt, b, s)
+    assert_close(Y.get(), Yo, GEMM, "Y")
+    dY = rng.standard_normal(Yo.shape).astype(np.float32)
+    dXo, g = O.pointwise_bwd(dY, Wt, cache, s, 1e-2, True)
+    dX = lay.backward(dY)
+    assert dX.shape == dXo.shape
+    assert_close(dX.get(), dXo, GEMM, "dX")
+    assert_close(lay.grads["weights"].get(), g["weights"], GEMM_W, "dW")
+    assert_close(lay.grads["bias"].get(), g["bias"], FP32_RED, "db")
+    tc1, _ = _lib.gemm_call_counts()
+    if C % 4 == 0:
+        assert tc1 - tc0 == 3, "expected fwd, dgrad and wgrad on the tcgen05 path"
+
+
+CONV_CASES = [
+    # N, C, H, W, F, k, s, p
+    (2, 3, 33, 33, 8, 5, 2, 1), (2, 3, 65, 65, 64, 5, 2, 1), (2, 32, 14, 14, 64, 4, 2, 1), (2, 64, 16, 16, 64, 3, 1, 1),
+    (2, 1, 28, 28, 32, 3, 1, 1), (2, 5, 10, 10, 7, 3, 2, 1), (1, 16, 9, 9, 300, 3, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tcgen05_vs_oracle(O, case):
+    from dorknet_b200.layers.convolution import ConvLayer
+    N, C, H, W, F, k, s, p = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    Wt = (rng.standard_normal((F, C, k, k)) / np.sqrt(C * k * k)).astype(np.float32)
+    lay = ConvLayer("c", (F, C, k, k), stride=s, padding=p, with_bias=False)
+    lay.learned_params["weights"] = Wt
+    Y = lay.forward(X)
+    Yo, cache = O.conv_fwd(X, Wt, None, s, p)
+    assert np.array_equal(lay.im2col_materialise(X).get(), cache["P"])  # bit-exact im2col index map
+    assert_close(Y.get(), Yo, GEMM, "Y")
+    dY = rng.standard_normal(Yo.shape).astype(np.float32)
+    dXo, g = O.conv_bwd(dY, Wt, cache, s, p)
+    dX = lay.backward(dY)  # lazy: computed on first read
+    assert not dX.is_materialised
+    assert_close(dX.get(), dXo, GEMM, "dX")
+    assert dX.is_materialised
+    assert_close(lay.grads["weights"].get(), g["weights"], GEMM_W, "dW")
+
+
+def test_full_size_properties_resnet_shapes():
+    """BASELINE full sizes (batch 64): size-independent properties instead of an oracle run --
+    linearity of the pointwise GEMM, dX of depthwise against a finite-difference probe along one direction,
+    BN output statistics (zero mean / unit variance per channel)."""
+    from dorknet_b200.layers.pointwise_convolution import PointwiseConvLayer
+    from dorknet_b200.layers.batch_norm import BatchNormLayer
+    from dorknet_b200.layers.depthwise_convolution import DepthwiseConvLayer
+    rng = np.random.default_rng(11)
+    N, C, H, W = 64, 64, 56, 56
+    X1 = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    X2 = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    pw = PointwiseConvLayer("p", filter_block_shape=(64, 64), with_bias=False)
+    y1 = pw.forward(X1).get().copy()
+    y2 = pw.forward(X2).get().copy()
+    y12 = pw.forward(X1 + 2 * X2).get()
+    assert_close(y12, y1 + 2 * y2, 3 * GEMM, "pointwise linearity")
+    bn = BatchNormLayer("bn", input_dimension=4, incoming_chans=C)
+    yb = bn.forward(3.0 * X1 + 1.5).get()
+    m, v = yb.mean(axis=(0, 2, 3)), yb.var(axis=(0, 2, 3))
+    assert np.max(np.abs(m)) < 1e-4 and np.max(np.abs(v - 1.0)) < 1e-3
+    dw = DepthwiseConvLayer("d", (C, 3, 3), stride=1, padding=1, with_bias=False)
+    ya = dw.forward(X1).get().copy()
+    dY = rng.standard_normal(ya.shape).astype(np.float32)
+    dX = dw.backward(dY).get()
+    yb2 = dw.forward(X1 + 1e-2 * X2).get()
+    lhs = float(np.sum((yb2.astype(np.float64) - ya) * dY))  # <J dx, dY>
+    rhs = float(np.sum(1e-2 * X2.astype(np.float64) * dX))    # <dx, J^T dY>
+    assert abs(lhs - rhs) <= 2e-3 * abs(rhs)
