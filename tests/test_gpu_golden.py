@@ -233,8 +233,9 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
         np.testing.assert_allclose(losses, d["losses"], rtol=tol)
         for l in defs.iter_param_layers(net):
             for k in l.learned_params.keys():
+                # atol: parameters whose gradient is zero in exact arithmetic only ever hold rounding noise
                 assert_close(l.learned_params[k].get(), d["final/%s/%s" % (l.layer_name, k)], 10 * tol,
-                             "final %s/%s" % (l.layer_name, k))
+                             "final %s/%s" % (l.layer_name, k), atol=0.1 * floor)
         _, st = net.forward(d["X"], None, test_mode=True)
         assert_close(st.get(), d["scores_test"], 20 * tol, "scores_test")
     finally:
