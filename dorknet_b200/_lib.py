@@ -61,6 +61,7 @@ PROTOS = {
     "dk_softmax_xent_fwd": (I, [P, P, P, P, I, I, P]),
     "dk_softmax_xent_bwd": (I, [P, P, P, I, I, P]),
     "dk_sumsq": (I, [P, P, F, L, P]),
+    "dk_sumsq_multi": (I, [P, I, P]),
     "dk_opt_sgd_multi": (I, [P, I, L, F, F, P, P]),
     "dk_opt_sgdm_multi": (I, [P, I, L, F, F, F, P, P]),
     "dk_opt_rmsprop_multi": (I, [P, I, L, F, F, F, P, P]),
@@ -75,6 +76,11 @@ _NO_CHECK = {"dk_version", "dk_last_error", "dk_sm_count", "dk_kernel_launches",
 class OptTensor(ctypes.Structure):
     """mirror of dk_opt_tensor"""
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("state", c_void_p), ("n", c_int64)]
+
+
+class SumsqTask(ctypes.Structure):
+    """mirror of dk_sumsq_task"""
+    _fields_ = [("w", c_void_p), ("out", c_void_p), ("n", c_int64), ("scale", c_float), ("pad_", c_int)]
 
 
 class DorknetError(RuntimeError):

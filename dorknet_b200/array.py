@@ -266,6 +266,8 @@ class DeviceScalar:
     __rmul__ = __mul__
 
     def __float__(self):
+        from .regularisers.l2 import flush_pending
+        flush_pending()
         total = np.float64(self.const)
         snap = None
         for slot, coeff in self.terms:

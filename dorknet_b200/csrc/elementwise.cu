@@ -185,6 +185,16 @@ __global__ void __launch_bounds__(1024) sumsq_kernel(const float *__restrict__ w
     if (threadIdx.x == 0) out[0] = scale * s;
 }
 
+// all l2 terms of a step in one launch: block b reduces tensor b (fixed order) into its own result slot
+__global__ void __launch_bounds__(512) sumsq_multi_kernel(const dk_sumsq_task *__restrict__ tasks) {
+    __shared__ float red[33];
+    const dk_sumsq_task t = tasks[blockIdx.x];
+    float s = 0.0f;
+    for (int64_t i = threadIdx.x; i < t.n; i += blockDim.x) s += t.w[i] * t.w[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) t.out[0] = t.scale * s;
+}
+
 // ---- fused multi-tensor optimisers -----------------------------------------------------------------
 // grid = (chunks of the largest tensor, num_tensors); blocks past a tensor's end exit at once.
 constexpr int OPT_THREADS = 256;
@@ -344,6 +354,14 @@ int dk_softmax_xent_bwd(const float *probs, const float *y_one_hot, float *dx, i
 int dk_sumsq(const float *w, float *out, float scale, int64_t n, dk_stream_t stream) {
     DK_REQUIRE(n >= 0 && out && (n == 0 || w), "dk_sumsq: bad arguments");
     sumsq_kernel<<<1, 1024, 0, as_stream(stream)>>>(w, out, scale, n);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
+int dk_sumsq_multi(const dk_sumsq_task *tasks, int num_tasks, dk_stream_t stream) {
+    if (num_tasks <= 0) return DK_OK;
+    DK_REQUIRE(tasks != nullptr && num_tasks <= 65535, "dk_sumsq_multi: bad arguments");
+    sumsq_multi_kernel<<<num_tasks, 512, 0, as_stream(stream)>>>(tasks);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }

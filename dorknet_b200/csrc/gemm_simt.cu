@@ -259,8 +259,39 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, const fl
     }
 }
 
+// Same reduction with the Z partials spread over 8 thread rows (fixed combination order -> deterministic): the
+// split-K GEMMs leave up to 148 partials of a small [M][N] matrix, which a one-thread-per-output loop reads as a
+// serial chain of dependent-latency loads.
+constexpr int SKR_X = 32, SKR_Y = 8;
+__global__ void __launch_bounds__(SKR_X * SKR_Y)
+splitk_reduce2_kernel(const float *__restrict__ partial, const float *__restrict__ w, float *__restrict__ out, float l2,
+                      int64_t mn, int Z) {
+    __shared__ float red[SKR_Y][SKR_X + 1];
+    const int tx = threadIdx.x % SKR_X, ty = threadIdx.x / SKR_X;
+    const int64_t i = (int64_t)blockIdx.x * SKR_X + tx;
+    float s = 0.0f;
+    if (i < mn) {
+        int z = ty;
+        for (; z + 3 * SKR_Y < Z; z += 4 * SKR_Y) {
+            const float a = partial[(int64_t)z * mn + i], b = partial[(int64_t)(z + SKR_Y) * mn + i];
+            const float c = partial[(int64_t)(z + 2 * SKR_Y) * mn + i], d = partial[(int64_t)(z + 3 * SKR_Y) * mn + i];
+            s += (a + b) + (c + d);
+        }
+        for (; z < Z; z += SKR_Y) s += partial[(int64_t)z * mn + i];
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < mn) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int y = 1; y < SKR_Y; ++y) t += red[y][tx];
+        out[i] = t + (l2 != 0.0f ? l2 * w[i] : 0.0f);
+    }
+}
+
 void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st) {
-    splitk_reduce_kernel<<<stream_grid(mn, 256), 256, 0, st>>>(partial, w, out, l2, mn, Z);
+    if (Z >= 16) splitk_reduce2_kernel<<<(unsigned)ceil_div(mn, SKR_X), SKR_X * SKR_Y, 0, st>>>(partial, w, out, l2, mn, Z);
+    else splitk_reduce_kernel<<<stream_grid(mn, 256), 256, 0, st>>>(partial, w, out, l2, mn, Z);
 }
 
 template <class AL, class BL, class ST, bool AK, bool BK_>

@@ -78,6 +78,21 @@ __device__ __forceinline__ uint32_t km_tile_off(int r, int k) {
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// asynchronous 4-byte global -> shared copy (LDGSTS); src == nullptr writes a zero (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async_f32(uint32_t dst, const float *src, const float *safe) {
+    const uint32_t n = src ? 4u : 0u;
+    const float *q = src ? src : safe;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {  // wait until at most n groups are still in flight
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
 
 // pixels of a [B, K, SH, SW] tensor subsampled by s: element (b, m = oh*OW + ow, k) = src[b][k][oh*s][ow*s]
 struct PixelGatherMN {
@@ -93,8 +108,8 @@ struct PixelGatherMN {
         r.off = ((long long)b * K * SH + (long long)oh * s) * SW + (long long)ow * s;
         return r;
     }
-    __device__ __forceinline__ float load(const Row &r, int k) const {
-        return (r.ok && k < K) ? __ldg(src + r.off + (long long)k * SH * SW) : 0.0f;
+    __device__ __forceinline__ const float *ptr(const Row &r, int k) const {
+        return (r.ok && k < K) ? src + r.off + (long long)k * SH * SW : nullptr;
     }
 };
 // same tensor as a K-major operand: rows r = channel, k = pixel index inside image b
@@ -111,8 +126,8 @@ struct PixelGatherKM {
         c.off = ((long long)b * R * SH + (long long)oh * s) * SW + (long long)ow * s;
         return c;
     }
-    __device__ __forceinline__ float load(int r, const KCol &c) const {
-        return (c.ok && r < R) ? __ldg(src + c.off + (long long)r * SH * SW) : 0.0f;
+    __device__ __forceinline__ const float *ptr(int r, const KCol &c) const {
+        return (c.ok && r < R) ? src + c.off + (long long)r * SH * SW : nullptr;
     }
 };
 
@@ -135,13 +150,13 @@ struct ConvPatchMN {
         r.iw0 = ow * g.s - g.p;
         return r;
     }
-    __device__ __forceinline__ float load(const Row &r, int k) const {
+    __device__ __forceinline__ const float *ptr(const Row &r, int k) const {
         const int kk = g.kh * g.kw;
         const int c = k / kk, t = k - c * kk;
         const int i = t / g.kw, j = t - i * g.kw;
         const int ih = r.ih0 + i, iw = r.iw0 + j;
-        if (!r.ok || c >= g.C || ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0.0f;
-        return __ldg(x + r.base + ((long long)c * g.H + ih) * g.W + iw);
+        if (!r.ok || c >= g.C || ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return nullptr;
+        return x + r.base + ((long long)c * g.H + ih) * g.W + iw;
     }
 };
 // the same patches as the K-major B of the wgrad GEMM: rows r = (c,i,j), k = output pixel of image b
@@ -160,13 +175,13 @@ struct ConvPatchKM {
         c.iw0 = ow * g.s - g.p;
         return c;
     }
-    __device__ __forceinline__ float load(int r, const KCol &kc) const {
+    __device__ __forceinline__ const float *ptr(int r, const KCol &kc) const {
         const int kk = g.kh * g.kw;
         const int c = r / kk, t = r - c * kk;
         const int i = t / g.kw, j = t - i * g.kw;
         const int ih = kc.ih0 + i, iw = kc.iw0 + j;
-        if (!kc.ok || c >= g.C || ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0.0f;
-        return __ldg(x + kc.base + ((long long)c * g.H + ih) * g.W + iw);
+        if (!kc.ok || c >= g.C || ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return nullptr;
+        return x + kc.base + ((long long)c * g.H + ih) * g.W + iw;
     }
 };
 // a dense row-major matrix [R][K] as a K-major operand (filters W[F][C*kh*kw] whose pitch TMA cannot take)
@@ -177,8 +192,8 @@ struct MatrixKM {
     int R, K;
     struct KCol { int k; bool ok; };
     __device__ __forceinline__ KCol kcol(int, int k) const { return KCol{k, k < K}; }
-    __device__ __forceinline__ float load(int r, const KCol &c) const {
-        return (c.ok && r < R) ? __ldg(w + (long long)r * K + c.k) : 0.0f;
+    __device__ __forceinline__ const float *ptr(int r, const KCol &c) const {
+        return (c.ok && r < R) ? w + (long long)r * K + c.k : nullptr;
     }
 };
 // dgrad of a general convolution, gather form of col2im (im2col.pyx:209-234): A(b, m = input pixel, k = (f,i,j))
@@ -197,15 +212,15 @@ struct ConvDgradMN {
         r.wp = w + g.p;
         return r;
     }
-    __device__ __forceinline__ float load(const Row &r, int k) const {
+    __device__ __forceinline__ const float *ptr(const Row &r, int k) const {
         const int kk = g.kh * g.kw;
         const int f = k / kk, t = k - f * kk;
         const int i = t / g.kw, j = t - i * g.kw;
         const int ti = r.hp - i, tj = r.wp - j;
-        if (!r.ok || f >= g.F || ti < 0 || tj < 0 || (ti % g.s) != 0 || (tj % g.s) != 0) return 0.0f;
+        if (!r.ok || f >= g.F || ti < 0 || tj < 0 || (ti % g.s) != 0 || (tj % g.s) != 0) return nullptr;
         const int oh = ti / g.s, ow = tj / g.s;
-        if (oh >= g.OH || ow >= g.OW) return 0.0f;
-        return __ldg(dy + r.base + ((long long)f * g.OH + oh) * g.OW + ow);
+        if (oh >= g.OH || ow >= g.OW) return nullptr;
+        return dy + r.base + ((long long)f * g.OH + oh) * g.OW + ow;
     }
 };
 // ... and its B(n = c, k = (f,i,j)) = W[f][c][i][j] as a K-major operand
@@ -220,8 +235,8 @@ struct ConvDgradWKM {
         const int f = k / kk, t = k - f * kk;
         return KCol{(long long)f * g.C * kk + t, f < g.F};
     }
-    __device__ __forceinline__ float load(int r, const KCol &c) const {
-        return (c.ok && r < g.C) ? __ldg(w + c.off + (long long)r * g.kh * g.kw) : 0.0f;
+    __device__ __forceinline__ const float *ptr(int r, const KCol &c) const {
+        return (c.ok && r < g.C) ? w + c.off + (long long)r * g.kh * g.kw : nullptr;
     }
 };
 
@@ -233,7 +248,7 @@ struct MatrixTransposedKM {
     int R, K;  // R = C (rows of the operand), K = F; element (r, k) = w[k*R + r]
     struct KCol { long long off; bool ok; };
     __device__ __forceinline__ KCol kcol(int, int k) const { return KCol{(long long)k * R, k < K}; }
-    __device__ __forceinline__ float load(int r, const KCol &c) const { return (c.ok && r < R) ? __ldg(w + c.off + r) : 0.0f; }
+    __device__ __forceinline__ const float *ptr(int r, const KCol &c) const { return (c.ok && r < R) ? w + c.off + r : nullptr; }
 };
 
 constexpr int TC_GATHER_THREADS = TC_THREADS + 128;
@@ -385,8 +400,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= 6) {
         // ================================ gather loaders (warps 6..9) ===================
         if constexpr (kAnyGather) {
+            // The copies are asynchronous (cp.async): a warp issues the whole stage, commits the group and moves on
+            // to the next stage; a stage is published (fence.proxy.async + arrive on its full barrier) once its
+            // group has landed, `depth` stages later -- so up to depth+1 stages of gathers are in flight per warp.
             const int lw = warp - 6;
-            int s = 0;
+            const int depth = p.stages > 3 ? 3 : p.stages - 1;
+            const float *safe = p.out;  // any mapped address: never dereferenced (src-size 0)
+            int s = 0, sa = 0, inflight = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int b = 0, m0, n0, item0 = 0;
@@ -421,36 +441,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             typename AG::Row rows[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) rows[j] = ag.row(bb, m0 + 32 * j + lane);
-#pragma unroll 4
+#pragma unroll 2
                             for (int kk = 0; kk < 8; ++kk) {
                                 const int k = lw * 8 + kk;
-                                float v[4];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) v[j] = ag.load(rows[j], k0 + k);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) st_shared_f32(sA + mn_tile_off(32 * j + lane, k), v[j]);
+                                for (int j = 0; j < 4; ++j)
+                                    cp_async_f32(sA + mn_tile_off(32 * j + lane, k), ag.ptr(rows[j], k0 + k), safe);
                             }
                         } else {
                             // lanes along k, this warp owns rows lw, lw+4, ...
                             const auto kc = ag.kcol(bb, k0 + lane);
-#pragma unroll 16
+#pragma unroll 4
                             for (int r = lw; r < TC_BM; r += 4)
-                                st_shared_f32(sA + km_tile_off(r, lane), ag.load(m0 + r, kc));
+                                cp_async_f32(sA + km_tile_off(r, lane), ag.ptr(m0 + r, kc), safe);
                         }
                     }
                     if constexpr (BG::kGather) {
                         static_assert(!BG::kMN, "gathered B operands are K-major");
                         const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
                         const auto kc = bg.kcol(bbB, k0 + lane);
-#pragma unroll 16
+#pragma unroll 4
                         for (int r = lw; r < p.bn; r += 4)
-                            st_shared_f32(sB + km_tile_off(r, lane), bg.load(n0 + r, kc));
+                            cp_async_f32(sB + km_tile_off(r, lane), bg.ptr(n0 + r, kc), safe);
                     }
-                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(full_bar(s));
+                    cp_async_commit();
+                    ++inflight;
+                    if (inflight > depth) {
+                        cp_async_wait_pending(depth);
+                        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_bar(sa));
+                        if (++sa == p.stages) sa = 0;
+                        --inflight;
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
+            }
+            cp_async_wait_pending(0);
+            fence_proxy_async();
+            __syncwarp();
+            while (inflight > 0) {
+                if (lane == 0) mbar_arrive(full_bar(sa));
+                if (++sa == p.stages) sa = 0;
+                --inflight;
             }
         }
     } else {

@@ -1,6 +1,7 @@
 """SoftmaxWithCrossEntropy (reference: layers/losses.py:5-41)."""
 from .layer import Layer, api, runtime, asarray, DeviceScalar
 from ..array import alloc_scalar_slot
+from ..regularisers.l2 import flush_pending
 
 
 class SoftmaxWithCrossEntropy(Layer):
@@ -17,6 +18,7 @@ class SoftmaxWithCrossEntropy(Layer):
         `loss` is a DeviceScalar: adding the regularisation terms to it costs no kernel and float()
         is the only synchronisation point."""
         self._ensure_gpu()
+        flush_pending()  # every layer's l2 term of this step, one launch
         X = asarray(X)
         B, K = X.shape
         p = self._buf("p", (B, K))

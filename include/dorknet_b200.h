@@ -183,6 +183,16 @@ int dk_softmax_xent_fwd(const float *logits, const float *y_one_hot, float *prob
 int dk_softmax_xent_bwd(const float *probs, const float *y_one_hot, float *dx, int B, int K, dk_stream_t stream);
 /* out[0] = scale * sum(w^2)   (l2.forward with scale = 0.5*strength) */
 int dk_sumsq(const float *w, float *out, float scale, int64_t n, dk_stream_t stream);
+/* The same for many tensors in ONE launch (`tasks` is a DEVICE array): every layer's regulariser_forward()
+ * (layers/layer.py:42-46) of a step, flushed by the loss layer. */
+typedef struct {
+    const float *w;
+    float *out;
+    int64_t n;
+    float scale;
+    int32_t pad_;
+} dk_sumsq_task;
+int dk_sumsq_multi(const dk_sumsq_task *tasks, int num_tasks, dk_stream_t stream);
 
 /* ---- optimisers: optimisers/SGD.py:20-24, SGDMomentum.py:31-39, RMSProp.py:28-36 ----------- */
 /* One fused multi-tensor launch.  `table` is a DEVICE array of num_tensors descriptors;

@@ -207,9 +207,57 @@ def optimiser_cases():
 from net_defs import build_small_net, iter_param_layers  # noqa: E402
 
 
-def net_case():
+def _tf32(a, mode):
+    """fp32 -> TF32 (10-bit mantissa) as the tensor core sees its operands: "rz" drops the 13 low mantissa bits,
+    "rn" rounds to nearest (ties away from zero)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    if mode == "rn":
+        u = u + np.uint32(0x1000)
+    return (u & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+class _Tf32Numpy:
+    """numpy / cupy-stub stand-in whose dot() feeds TF32-rounded operands to the fp32 GEMM: patched into the
+    reference's convolution / pointwise modules to model the sm_100a tensor-core path (kind::tf32)."""
+
+    def __init__(self, mode):
+        self._mode = mode
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    def dot(self, a, b):
+        return np.dot(_tf32(a, self._mode), _tf32(b, self._mode))
+
+    def get_array_module(self, *a):
+        return self
+
+    def asarray(self, a, *k, **kw):
+        return np.asarray(a, *k, **kw)
+
+
+def net_case(tf32_mode=None):
     """3 SGDMomentum steps on the miniature net at 33x33 (the reference's odd-size geometry:
-    33 -(5x5 s2 p1)-> 16 -(pw s2)-> 8 -> 8 -(dw s2)-> 4)."""
+    33 -(5x5 s2 p1)-> 16 -(pw s2)-> 8 -> 8 -(dw s2)-> 4).  With tf32_mode the reference's conv / pointwise GEMMs
+    (and only those: cp.dot / np.dot / xp.dot in layers/convolution.py:75-120, pointwise_convolution.py:51-65) see
+    TF32-rounded operands -- the arithmetic model of the tcgen05 kind::tf32 path."""
+    import importlib
+    patched = []
+    if tf32_mode:
+        proxy = _Tf32Numpy(tf32_mode)
+        for mn in ("layers.convolution", "layers.pointwise_convolution"):
+            mod = importlib.import_module(mn)
+            patched.append((mod, mod.cp, mod.np))
+            mod.cp = proxy
+            mod.np = proxy
+    try:
+        _net_case_body("mini_net" if not tf32_mode else "mini_net_tf32" + tf32_mode)
+    finally:
+        for mod, cp_, np_ in patched:
+            mod.cp, mod.np = cp_, np_
+
+
+def _net_case_body(name):
     g = rng(70)
     net = build_small_net(R, seed=123)
     out = {}
@@ -239,7 +287,7 @@ def net_case():
     out["scores_test"] = f32(st)
     _, lt = net.forward(X, None, test_mode=True, terminal_layer_name="dense1")
     out["logits_test"] = f32(lt)
-    save("mini_net", **out)
+    save(name, **out)
 
 
 def main():
@@ -262,6 +310,8 @@ def main():
     dense_loss_cases()
     optimiser_cases()
     net_case()
+    net_case("rz")
+    net_case("rn")
 
 
 if __name__ == "__main__":
