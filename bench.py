@@ -244,7 +244,12 @@ class CallTimer:
 # Argument positions follow include/dorknet_b200.h.
 def _bn_fwd_bytes(a):
     N, C, HW = a[14], a[15], a[16]
-    return 4 * 3 * N * C * HW  # read for stats, read for apply, write
+    return 4 * (3 if a[1] else 1) * N * C * HW  # read for stats (+ read for apply, write, unless y is deferred)
+
+
+def _bn_apply_bytes(a):
+    N, C, HW = a[5], a[6], a[7]
+    return 4 * 2 * N * C * HW
 
 
 def _bn_bwd_bytes(a):
@@ -300,7 +305,7 @@ def _conv_dgrad_bytes(a):
 
 
 BYTES_FN = {
-    "dk_bn_fwd_train": _bn_fwd_bytes, "dk_bn_bwd": _bn_bwd_bytes,
+    "dk_bn_fwd_train": _bn_fwd_bytes, "dk_bn_bwd": _bn_bwd_bytes, "dk_bn_apply": _bn_apply_bytes,
     "dk_dwconv_fwd": _dw_fwd_bytes, "dk_dwconv_bwd": _dw_bwd_bytes,
     "dk_pwconv_fwd": _pw_fwd_bytes, "dk_pwconv_dgrad": _pw_dgrad_bytes, "dk_pwconv_wgrad": _pw_wgrad_bytes,
     "dk_conv2d_fwd": _conv_fwd_bytes, "dk_conv2d_wgrad": _conv_wgrad_bytes, "dk_conv2d_dgrad": _conv_dgrad_bytes,

@@ -152,6 +152,23 @@ class LazyDeviceArray(DeviceArray):
         return self._thunk is None
 
 
+class LazyBNOutput(LazyDeviceArray):
+    """Output of a training-mode BatchNormLayer.forward whose normalisation pass has not run yet: the statistics
+    kernel has, and `scale` / `shift` per channel are on the device.  A ReLu that receives it launches ONE fused
+    apply+ReLU pass instead of two (and tells the BatchNorm to mask its backward); any other consumer materialises
+    the plain y = x*scale + shift on first use."""
+
+    __slots__ = ("bn",)
+
+    def __init__(self, buf, thunk, bn):
+        super().__init__(buf, thunk)
+        self.bn = bn
+
+    def consume(self):
+        """Mark as consumed by a fused kernel: the plain y will never be produced."""
+        self._thunk = None
+
+
 def empty(shape, dtype=np.float32):
     torch = _torch()
     runtime.ensure_init()

@@ -75,8 +75,28 @@ bn_stats_kernel(const float *__restrict__ x, int N, int C, int HW, int S, int64_
     float shift = 0.0f, sum = 0.0f, sq = 0.0f, cnt = 0.0f;
     bool have = false;
     if (VEC) {
-        for (int64_t v = v0 + 4 * (int64_t)threadIdx.x; v < v1; v += 4 * BN_THREADS) {
-            const int64_t n = v / HW, off = v - n * HW;  // HW % 4 == 0: a float4 never straddles planes
+        // four independent 128-bit loads in flight per thread before any arithmetic
+        constexpr int U = 4;
+        int64_t v = v0 + 4 * (int64_t)threadIdx.x;
+        for (; v + (U - 1) * 4 * BN_THREADS < v1; v += U * 4 * BN_THREADS) {
+            float4 t[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t vv = v + (int64_t)u * 4 * BN_THREADS;
+                const uint32_t n = (uint32_t)vv / (uint32_t)HW, off = (uint32_t)vv - n * (uint32_t)HW;  // N*HW < 2^31 (host check)  // HW % 4 == 0: a float4 never straddles planes
+                t[u] = ld_stream4(x + n * cstride + (int64_t)c * HW + off);
+            }
+            if (!have) { shift = t[0].x; have = true; }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float d0 = t[u].x - shift, d1 = t[u].y - shift, d2 = t[u].z - shift, d3 = t[u].w - shift;
+                sum += (d0 + d1) + (d2 + d3);
+                sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+            cnt += 4.0f * U;
+        }
+        for (; v < v1; v += 4 * BN_THREADS) {
+            const uint32_t n = (uint32_t)v / (uint32_t)HW, off = (uint32_t)v - n * (uint32_t)HW;
             const float4 t = ld_stream4(x + n * cstride + (int64_t)c * HW + off);
             if (!have) { shift = t.x; have = true; }
             const float d0 = t.x - shift, d1 = t.y - shift, d2 = t.z - shift, d3 = t.w - shift;
@@ -86,7 +106,7 @@ bn_stats_kernel(const float *__restrict__ x, int N, int C, int HW, int S, int64_
         }
     } else {
         for (int64_t v = v0 + threadIdx.x; v < v1; v += BN_THREADS) {
-            const int64_t n = v / HW, off = v - n * HW;
+            const uint32_t n = (uint32_t)v / (uint32_t)HW, off = (uint32_t)v - n * (uint32_t)HW;
             const float t = x[n * cstride + (int64_t)c * HW + off];
             if (!have) { shift = t; have = true; }
             const float d = t - shift;
@@ -220,8 +240,33 @@ bn_bwd_reduce_kernel(const float *__restrict__ dy, const float *__restrict__ x, 
     const float sc = RELU ? save_scale[c] : 0.f, sh = RELU ? save_shift[c] : 0.f;
     float sg = 0.0f, sgx = 0.0f;
     if (VEC) {
-        for (int64_t v = v0 + 4 * (int64_t)threadIdx.x; v < v1; v += 4 * BN_THREADS) {
-            const int64_t n = v / HW, off = v - n * HW;
+        constexpr int U = 2;  // 2 x (dY, X) 128-bit loads in flight per thread
+        int64_t v = v0 + 4 * (int64_t)threadIdx.x;
+        for (; v + (U - 1) * 4 * BN_THREADS < v1; v += U * 4 * BN_THREADS) {
+            float4 gq[U], tq[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t vv = v + (int64_t)u * 4 * BN_THREADS;
+                const uint32_t n = (uint32_t)vv / (uint32_t)HW, off = (uint32_t)vv - n * (uint32_t)HW;  // N*HW < 2^31 (host check)
+                const int64_t idx = n * cstride + (int64_t)c * HW + off;
+                gq[u] = ld_stream4(dy + idx);
+                tq[u] = ld_stream4(x + idx);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float4 g = gq[u];
+                const float4 t = tq[u];
+                if (RELU) {
+                    g.x = fmaf(t.x, sc, sh) > 0.f ? g.x : 0.f; g.y = fmaf(t.y, sc, sh) > 0.f ? g.y : 0.f;
+                    g.z = fmaf(t.z, sc, sh) > 0.f ? g.z : 0.f; g.w = fmaf(t.w, sc, sh) > 0.f ? g.w : 0.f;
+                }
+                sg += (g.x + g.y) + (g.z + g.w);
+                sgx += (g.x * ((t.x - mean) * invstd) + g.y * ((t.y - mean) * invstd)) +
+                       (g.z * ((t.z - mean) * invstd) + g.w * ((t.w - mean) * invstd));
+            }
+        }
+        for (; v < v1; v += 4 * BN_THREADS) {
+            const uint32_t n = (uint32_t)v / (uint32_t)HW, off = (uint32_t)v - n * (uint32_t)HW;
             const int64_t idx = n * cstride + (int64_t)c * HW + off;
             float4 g = ld_stream4(dy + idx);
             const float4 t = ld_stream4(x + idx);
@@ -235,7 +280,7 @@ bn_bwd_reduce_kernel(const float *__restrict__ dy, const float *__restrict__ x, 
         }
     } else {
         for (int64_t v = v0 + threadIdx.x; v < v1; v += BN_THREADS) {
-            const int64_t n = v / HW, off = v - n * HW;
+            const uint32_t n = (uint32_t)v / (uint32_t)HW, off = (uint32_t)v - n * (uint32_t)HW;
             const int64_t idx = n * cstride + (int64_t)c * HW + off;
             float g = dy[idx];
             const float t = x[idx];
@@ -337,8 +382,8 @@ static BnWs bn_ws_carve(void *ws, int C) {
 // choose the number of splits per channel: ~4 CTAs per SM in total, each split a multiple of 4 elements
 static void bn_plan(int N, int C, int HW, int *S, int64_t *per_split) {
     const int64_t total = (int64_t)N * HW;
-    int64_t want = ceil_div((int64_t)sm_count() * 4, C);
-    const int64_t max_by_work = ceil_div(total, 4 * BN_THREADS);  // at least one float4 per thread
+    int64_t want = ceil_div((int64_t)sm_count() * 8, C);  // 8 resident CTAs of 256 threads per SM
+    const int64_t max_by_work = ceil_div(total, 16 * BN_THREADS);  // at least four float4 per thread
     if (want > max_by_work) want = max_by_work;
     if (want > BN_MAX_SPLITS) want = BN_MAX_SPLITS;
     if (want < 1) want = 1;
@@ -350,7 +395,7 @@ static void bn_plan(int N, int C, int HW, int *S, int64_t *per_split) {
 
 static int bn_check(const char *who, int N, int C, int HW, const void *ws, size_t ws_bytes) {
     DK_REQUIRE(N > 0 && C > 0 && HW > 0, "%s: bad shape N=%d C=%d HW=%d", who, N, C, HW);
-    DK_REQUIRE((int64_t)N * C * HW < ((int64_t)1 << 40), "%s: tensor too large", who);
+    DK_REQUIRE((int64_t)N * C * HW < ((int64_t)1 << 40) && (int64_t)N * HW < ((int64_t)1 << 31), "%s: tensor too large", who);
     if (ws_bytes < bn_ws_bytes(C) || ws == nullptr) {
         set_error("%s: workspace too small (%zu < %zu bytes)", who, ws_bytes, bn_ws_bytes(C));
         return DK_ERR_WORKSPACE;
@@ -496,7 +541,7 @@ bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ dbias, int N,
     const int64_t total = (int64_t)N * HW;
     float s = 0.0f;
     for (int64_t v = threadIdx.x; v < total; v += blockDim.x) {
-        const int64_t n = v / HW, off = v - n * HW;
+        const uint32_t n = (uint32_t)v / (uint32_t)HW, off = (uint32_t)v - n * (uint32_t)HW;
         s += dy[(n * F + f) * (int64_t)HW + off];
     }
     s = block_sum(s, red);

@@ -1,5 +1,6 @@
 """ReLu (reference: layers/activations.py:6-53, layers/relu_cy.pyx)."""
 from .layer import Layer, api, runtime, asarray
+from ..array import LazyBNOutput
 
 
 class ReLu(Layer):
@@ -7,6 +8,7 @@ class ReLu(Layer):
     def __init__(self, layer_name):
         super().__init__(layer_name)
         self._y = None
+        self._fused_bn = None
 
     def __repr__(self):
         return "ReLu({})".format(self.layer_name)
@@ -18,6 +20,14 @@ class ReLu(Layer):
         self._ensure_gpu()
         X = asarray(X)
         y = self._buf("y", X.shape)
+        self._fused_bn = None
+        if isinstance(X, LazyBNOutput) and not X.is_materialised and not test_mode:
+            # BatchNorm -> ReLU: one pass y = relu(x*scale + shift); backward: the BatchNorm masks dY itself
+            X.bn.fused_relu_apply(y)
+            X.consume()
+            self._fused_bn = X.bn
+            self._y = y
+            return y
         api.dk_relu_fwd(X.ptr, y.ptr, None, X.size, runtime.stream())
         if not test_mode:
             self._y = y
@@ -35,6 +45,8 @@ class ReLu(Layer):
     def backward(self, upstream_dx):
         """dY * mask (activations.py:44-47)"""
         upstream_dx = asarray(upstream_dx)
+        if self._fused_bn is not None:
+            return upstream_dx  # the fused BatchNorm's backward applies the (x_hat*gamma+beta > 0) mask
         dx = self._buf("dx", upstream_dx.shape)
         api.dk_relu_bwd(upstream_dx.ptr, self._y.ptr, dx.ptr, upstream_dx.size, runtime.stream())
         return dx

@@ -2,6 +2,7 @@
 import numpy as np
 
 from .layer import Layer, api, runtime, asarray, empty
+from ..array import LazyBNOutput
 
 
 class BatchNormLayer(Layer):
@@ -29,6 +30,16 @@ class BatchNormLayer(Layer):
             self.learned_params = {}
             self.grads = {}
         self._x = None
+        self._relu_fused = False
+        self.defer_apply = True  # return a lazy output so that a following ReLu can fuse (False: always apply now)
+
+    def fused_relu_apply(self, y):
+        """y = relu(x*scale + shift) in one pass (called by the ReLu that consumes our lazy output); the mask is
+        re-derived from x in backward, so this layer's backward must start with it."""
+        N, C, HW = self._dims(self.input_shape)
+        base = self._bufs["saved"].ptr
+        api.dk_bn_apply(self._x.ptr, y.ptr, base + 8 * C, base + 12 * C, 1, N, C, HW, runtime.stream())
+        self._relu_fused = True
 
     def __repr__(self):
         return "BatchNormLayer({}, input_dimension={}, incoming_chans={}, run_momentum={})".format(
@@ -67,10 +78,20 @@ class BatchNormLayer(Layer):
             sv = self._buf("saved", (4, C))  # mean, invstd, scale, shift
             ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
             base = sv.ptr
+            self._x = X
+            self._relu_fused = False
+            if self.defer_apply:
+                # statistics now, normalisation when the consumer is known (a ReLu fuses it with its own pass)
+                api.dk_bn_fwd_train(X.ptr, None, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first),
+                                    float(self.run_momentum), float(self.eps),
+                                    base, base + 4 * C, base + 8 * C, base + 12 * C, 0, N, C, HW, ws, wsn, st)
+
+                def apply():
+                    api.dk_bn_apply(X.ptr, y.ptr, base + 8 * C, base + 12 * C, 0, N, C, HW, runtime.stream())
+                return LazyBNOutput(y, apply, self)
             api.dk_bn_fwd_train(X.ptr, y.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first),
                                 float(self.run_momentum), float(self.eps),
                                 base, base + 4 * C, base + 8 * C, base + 12 * C, 0, N, C, HW, ws, wsn, st)
-            self._x = X
         else:
             rm, rs = self.non_learned_params["running_mean"], self.non_learned_params["running_std"]
             if rm is None:
@@ -89,7 +110,7 @@ class BatchNormLayer(Layer):
         dg, db = self._grad("gamma"), self._grad("beta")
         ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
         api.dk_bn_bwd(dY.ptr, self._x.ptr, self._param("gamma").ptr, base, base + 4 * C, base + 8 * C, base + 12 * C,
-                      dx.ptr, dg.ptr, db.ptr, 0, N, C, HW, ws, wsn, runtime.stream())
+                      dx.ptr, dg.ptr, db.ptr, 1 if self._relu_fused else 0, N, C, HW, ws, wsn, runtime.stream())
         return dx
 
     # the reference exposes these pieces separately (batch_norm.py:124-174)

@@ -196,7 +196,13 @@ def test_optimisers(golden, L, nm):
 @pytest.mark.parametrize("backend", [0, 1])
 def test_mini_resnet_three_training_steps(golden, L, backend):
     """conv s2 - BN - ReLU - pw s2 - BN - ReLU - 2 residual blocks (identity and pw-s2 skip) - GAP -
-    dense - softmax, 3 SGDMomentum steps: losses, first-step gradients and final weights."""
+    dense - softmax, 3 SGDMomentum steps: losses, first-step gradients and final weights.
+
+    backend 1 (fp32 SIMT GEMMs) is held to the live reference's fp32 run.  backend 0 (tcgen05 kind::tf32) is held,
+    just as tightly, to the reference run whose conv / pointwise GEMM operands were truncated to TF32
+    (tests/golden/make_golden.py net_case("rz")): that is exactly what the tensor core does with fp32 operands, and
+    this miniature net is ill-conditioned enough (BatchNorm over 8x2x2 samples) that the truncation alone moves
+    some gradients of the fp32 reference by ~10 % -- so the fp32 golden is only used for the loss there."""
     import importlib.util
     import os
     from dorknet_b200 import api
@@ -204,7 +210,8 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
         "make_golden_defs", os.path.join(os.path.dirname(__file__), "golden", "net_defs.py"))
     defs = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(defs)
-    d = golden("mini_net")
+    d = golden("mini_net_tf32rz" if backend == 0 else "mini_net")
+    d32 = golden("mini_net")
     api.dk_set_gemm_backend(backend)
     try:
         net = defs.build_small_net(L, seed=123)
@@ -212,11 +219,11 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
             for k in list(l.learned_params.keys()):
                 l.learned_params[k] = d["init/%s/%s" % (l.layer_name, k)].copy()
         opt = L.SGDMomentum(net, 0.02, 0.9)
-        tol = 3e-3 if backend == 0 else 2e-4
-        # TF32 (backend 0) noise floor for gradients that are small because they cancel (BN gamma/beta in front of
-        # another BN): measured against the largest gradient of the whole net, not against the tensor's own maximum
+        tol = 3e-4 if backend == 0 else 2e-4
+        # absolute floor for gradients that are small because they cancel (zero in exact arithmetic for a BN that
+        # feeds another BN), relative to the largest gradient of the whole net
         gscale = max(float(np.max(np.abs(d[k]))) for k in d.files if k.startswith("grad0/"))
-        floor = 1.5e-2 * gscale if backend == 0 else 2e-8
+        floor = (1e-3 if backend == 0 else 1e-6) * gscale
         losses = []
         for step in range(3):
             loss, scores = net.forward(d["X"], d["y"])
@@ -226,16 +233,15 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
                 assert_close(scores.get(), d["scores0"], tol, "scores0")
                 for l in defs.iter_param_layers(net):
                     for k in l.grads.keys():
-                        # atol: dbeta/dgamma of a BN feeding another BN are zero in exact arithmetic
                         assert_close(l.grads[k].get(), d["grad0/%s/%s" % (l.layer_name, k)], 10 * tol,
                                      "grad0 %s/%s" % (l.layer_name, k), atol=floor)
             opt.update_weights()
         np.testing.assert_allclose(losses, d["losses"], rtol=tol)
+        np.testing.assert_allclose(losses, d32["losses"], rtol=5e-4)  # TF32 vs the fp32 reference: loss level
         for l in defs.iter_param_layers(net):
             for k in l.learned_params.keys():
-                # atol: parameters whose gradient is zero in exact arithmetic only ever hold rounding noise
                 assert_close(l.learned_params[k].get(), d["final/%s/%s" % (l.layer_name, k)], 10 * tol,
-                             "final %s/%s" % (l.layer_name, k), atol=0.1 * floor)
+                             "final %s/%s" % (l.layer_name, k), atol=0.1 * floor + 1e-9)
         _, st = net.forward(d["X"], None, test_mode=True)
         assert_close(st.get(), d["scores_test"], 20 * tol, "scores_test")
     finally:
