@@ -335,7 +335,11 @@ def run_ours(a, spec):
     M = W.ours()
     net, opt = build_net(M, spec, seed=0)
     net.to_gpu()
-    dp = DataParallel(net, opt, num_buckets=3, overlap=True) if world > 1 else None
+    # eager mode: bucketed all-reduce overlapped with backward; graph mode: one all-reduce of the flat gradient
+    # buffer between the forward+backward graph and the optimiser graph
+    dp = None
+    if world > 1:
+        dp = DataParallel(net, opt, num_buckets=3 if a.no_graph else 1, overlap=bool(a.no_graph))
     if dp is not None:
         dp.broadcast_parameters(0)
     B = spec["batch"]

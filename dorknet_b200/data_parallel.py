@@ -69,7 +69,7 @@ def flat_layout(sizes, align=32):
 
 
 class DataParallel:
-    def __init__(self, network, optimiser=None, num_buckets=3, overlap=True, process_group=None):
+    def __init__(self, network, optimiser=None, num_buckets=3, overlap=True, process_group=None, device=None):
         import torch.distributed as dist
         self.dist = dist
         self.network = network
@@ -78,13 +78,16 @@ class DataParallel:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap
         self._pending = []
+        self.device = device  # None: the process's B200; tests pass torch.device("cpu") with the gloo backend
         # parameter layers in REVERSE execution order = the order backward produces gradients
         layers = list(iter_param_layers(network, include_skip=True))
         self.entries = []  # (layer, key)
         for layer in reversed(layers):
-            layer._ensure_gpu()
+            if hasattr(layer, "_ensure_gpu") and device is None:
+                layer._ensure_gpu()
             for k in layer.learned_params.keys():
-                layer._param(k)
+                if hasattr(layer, "_param") and device is None:
+                    layer._param(k)
                 self.entries.append((layer, k))
         sizes = [int(np.prod(l.learned_params[k].shape)) for l, k in self.entries]
         self.offsets, self.total = flat_layout(sizes)
@@ -104,7 +107,8 @@ class DataParallel:
     # -- flat gradient storage ---------------------------------------------------------------------
     def _flatten_grads(self):
         import torch
-        self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=runtime.device())
+        dev = self.device if self.device is not None else runtime.device()
+        self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=dev)
         for (layer, k), off, n in zip(self.entries, self.offsets, self.sizes):
             shape = layer.learned_params[k].shape
             layer.grads[k] = DeviceArray(self.flat[off:off + n], shape)
