@@ -74,56 +74,71 @@ def build_net(M, spec, seed=0):
 
 # ------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the timed region, through NVML in a thread of this process
+    (an `nvidia-smi -lms` child polling a multi-GPU box stalls NCCL traffic, so it is only the fallback)."""
 
-    def __init__(self, index):
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, index, period=0.05):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.period = period
+        self.samples = []
+        self._stop = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                ids = [v for v in visible.split(",") if v.strip()]
+                if idx < len(ids) and ids[idx].strip().isdigit():
+                    idx = int(ids[idx])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+        n = self.nvml
+        calls = os.environ.get("BENCH_CLOCK_CALLS", "clock,power,reasons").split(",")
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM) if "clock" in calls else 0
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if "power" in calls else 0.0
+                rs = 0
+                if "reasons" in calls:
+                    try:
+                        rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:  # noqa: BLE001
+                        rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.time(), sm, pw, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        rows = [l for t, l in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
-        for l in rows:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                power.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self.thread.join(timeout=2)
+        rows = [r for r in self.samples if t0 - 0.02 <= r[0] <= t1 + 0.02] or self.samples
+        sm = sorted(r[1] for r in rows)
+        reasons = set()
+        for r in rows:
+            for nm, bit in self.REASONS:
+                if r[3] & bit:
                     reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.max_sm),
+                "power_w_max": max(r[2] for r in rows) if rows else None, "samples": len(rows),
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------- reference arm
@@ -404,16 +419,20 @@ def run_ours(a, spec):
             json.dump({"by_family": fmt(table), "by_call_shape": fmt(by_shape)}, f, indent=1)
 
     # ---- timed region: K steps, inputs resident in HBM (one CUDA-graph replay per step) -----------------------
-    clocks = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    clocks = ClockSampler(torch.cuda.current_device(), period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.05"))) if (
+        rank == 0 and os.environ.get("BENCH_NO_CLOCKS") != "1") else None
     barrier()
     if clocks:
         clocks.start()
-        time.sleep(0.25)
+        time.sleep(float(os.environ.get("BENCH_CLOCK_SLEEP", "0")))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
+    dbg_sync = os.environ.get("BENCH_SYNC_EVERY") == "1"  # diagnostics only
     for i in range(a.steps):
         loss = train_step(*ring[i % nring][2:])
+        if dbg_sync:
+            torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -506,6 +525,8 @@ def run_ours(a, spec):
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        del os.environ["NCCL_DEBUG"]  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     a = parse_args()
     spec = workload_spec(a)
     if a.impl == "reference":
