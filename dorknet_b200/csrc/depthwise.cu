@@ -458,6 +458,7 @@ int dw_rows_bwd(const float *dy, const float *x, const float *w, float *dx, floa
                 float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, void *ws, size_t ws_bytes,
                 cudaStream_t st);
 static int g_dw_rows_enabled = 1;
+extern int g_dwr_bwd_rb, g_dwr_bwd_vec_cap;
 
 int init_depthwise() {
     // budgets are within the 48 KB default for forward; backward may slightly exceed with the filter stash
@@ -552,7 +553,9 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
 
 /* test hook: 0 = always use the shared-memory tile kernels, 1 = register-window fast path where it applies */
 int dk_dw_debug_set(int enable_rows) {
-    g_dw_rows_enabled = enable_rows;
+    if (enable_rows >= 20) g_dwr_bwd_vec_cap = enable_rows - 20;  // 21 / 22 / 24
+    else if (enable_rows >= 10) g_dwr_bwd_rb = enable_rows - 10;  // 12 / 14: rows per iteration of the backward kernel
+    else g_dw_rows_enabled = enable_rows;
     return DK_OK;
 }
 

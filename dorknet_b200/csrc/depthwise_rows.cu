@@ -44,27 +44,52 @@ __device__ __forceinline__ void st_vec(float *p, const float (&v)[VEC]) {
 }
 
 // One input row of a strip with its halo columns: r[0] = left neighbour, r[1..VEC] = own columns, r[VEC+1] = right.
-// All 32 lanes execute the shuffles; `ok` masks the global accesses only.
+// Loading is split in two so that the global loads of the NEXT row group are in flight while the current one is
+// being computed: issue_row() only issues the loads (own columns + the two halo scalars that cannot come from a
+// neighbouring lane), finish_row() does the shuffles.  All 32 lanes execute the shuffles; `ok` masks the loads.
+template <int VEC>
+struct RawRow {
+    float v[VEC];
+    float hl, hr;  // halo values for lane 0 / lane 31 (neighbour strip lives in another warp)
+    bool in;
+};
+
+template <int VEC>
+__device__ __forceinline__ void issue_row(const float *__restrict__ src, bool ok, int row, int H, int W, int strip,
+                                          int SP, int lane, RawRow<VEC> &q) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) q.v[i] = 0.0f;
+    q.hl = 0.0f;
+    q.hr = 0.0f;
+    q.in = ok && row >= 0 && row < H;
+    const float *p = src + (long long)row * W + strip * VEC;
+    if (q.in) {
+        ld_vec<VEC>(p, q.v);
+        if (lane == 0 && strip > 0) q.hl = __ldg(p - 1);
+        if (lane == 31 && strip < SP - 1) q.hr = __ldg(p + VEC);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void finish_row(const RawRow<VEC> &q, int strip, int SP, int lane, float (&r)[VEC + 2]) {
+    float left = __shfl_up_sync(0xffffffffu, q.v[VEC - 1], 1);
+    float right = __shfl_down_sync(0xffffffffu, q.v[0], 1);
+    if (lane == 0) left = q.hl;
+    if (lane == 31) right = q.hr;
+    if (strip == 0 || !q.in) left = 0.0f;
+    if (strip == SP - 1 || !q.in) right = 0.0f;
+    r[0] = left;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r[1 + i] = q.v[i];
+    r[VEC + 1] = right;
+}
+
 template <int VEC>
 __device__ __forceinline__ void load_row(const float *__restrict__ src, bool ok, int row, int H, int W, int strip,
                                          int SP, int lane, float (&r)[VEC + 2]) {
-    float v[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) v[i] = 0.0f;
-    const bool in = ok && row >= 0 && row < H;
-    const float *p = src + (long long)row * W + strip * VEC;
-    if (in) ld_vec<VEC>(p, v);
-    float left = __shfl_up_sync(0xffffffffu, v[VEC - 1], 1);
-    float right = __shfl_down_sync(0xffffffffu, v[0], 1);
-    if (strip == 0) left = 0.0f;
-    else if (lane == 0 && in) left = __ldg(p - 1);        // neighbour strip lives in the previous warp
-    if (strip == SP - 1) right = 0.0f;
-    else if (lane == 31 && in) right = __ldg(p + VEC);    // ... or in the next one
-    if (!in) { left = 0.0f; right = 0.0f; }
-    r[0] = left;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) r[1 + i] = v[i];
-    r[VEC + 1] = right;
+    RawRow<VEC> q;
+    issue_row<VEC>(src, ok, row, H, W, strip, SP, lane, q);
+    finish_row<VEC>(q, strip, SP, lane, r);
 }
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -95,9 +120,16 @@ dw3x3_rows_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, 
     float win[DWR_RB + 2][VEC + 2];
     load_row<VEC>(xp, ok, h0 - 1, H, W, strip, SP, lane, win[0]);
     load_row<VEC>(xp, ok, h0, H, W, strip, SP, lane, win[1]);
+    RawRow<VEC> nxt[DWR_RB];
+#pragma unroll
+    for (int r = 0; r < DWR_RB; ++r) issue_row<VEC>(xp, ok && (r < rows), h0 + r + 1, H, W, strip, SP, lane, nxt[r]);
     for (int hb = 0; hb < rows; hb += DWR_RB) {
 #pragma unroll
-        for (int r = 0; r < DWR_RB; ++r) load_row<VEC>(xp, ok && (hb + r < rows), h0 + hb + r + 1, H, W, strip, SP, lane, win[2 + r]);
+        for (int r = 0; r < DWR_RB; ++r) finish_row<VEC>(nxt[r], strip, SP, lane, win[2 + r]);
+        // loads of the next row group fly while this one is computed
+#pragma unroll
+        for (int r = 0; r < DWR_RB; ++r)
+            issue_row<VEC>(xp, ok && (hb + DWR_RB + r < rows), h0 + hb + DWR_RB + r + 1, H, W, strip, SP, lane, nxt[r]);
 #pragma unroll
         for (int r = 0; r < DWR_RB; ++r) {
             float o[VEC];
@@ -122,7 +154,7 @@ dw3x3_rows_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, 
 
 // --------------------------------------------------------------------------------------------- backward
 // dX[h][w] = sum_{i,j} dY[h+1-i][w+1-j] w[i][j];  dW[i][j] += dY[h][w] X[h+i-1][w+j-1];  db += dY[h][w]
-template <int VEC>
+template <int VEC, int RB>
 __global__ void __launch_bounds__(DWR_THREADS)
 dw3x3_rows_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ w,
                       float *__restrict__ dx, float *__restrict__ partial, const float *__restrict__ dx_add,
@@ -151,19 +183,32 @@ dw3x3_rows_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x,
     float acc[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = 0.0f;
-    float gw[DWR_RB + 2][VEC + 2], xw[DWR_RB + 2][VEC + 2];
+    float gw[RB + 2][VEC + 2], xw[RB + 2][VEC + 2];
     load_row<VEC>(gp, ok, h0 - 1, H, W, strip, SP, lane, gw[0]);
     load_row<VEC>(gp, ok, h0, H, W, strip, SP, lane, gw[1]);
     load_row<VEC>(xp, ok, h0 - 1, H, W, strip, SP, lane, xw[0]);
     load_row<VEC>(xp, ok, h0, H, W, strip, SP, lane, xw[1]);
-    for (int hb = 0; hb < rows; hb += DWR_RB) {
+    RawRow<VEC> ng[RB], nx[RB];
 #pragma unroll
-        for (int r = 0; r < DWR_RB; ++r) {
-            load_row<VEC>(gp, ok && (hb + r < rows), h0 + hb + r + 1, H, W, strip, SP, lane, gw[2 + r]);
-            load_row<VEC>(xp, ok && (hb + r < rows), h0 + hb + r + 1, H, W, strip, SP, lane, xw[2 + r]);
+    for (int r = 0; r < RB; ++r) {
+        issue_row<VEC>(gp, ok && (r < rows), h0 + r + 1, H, W, strip, SP, lane, ng[r]);
+        issue_row<VEC>(xp, ok && (r < rows), h0 + r + 1, H, W, strip, SP, lane, nx[r]);
+    }
+    for (int hb = 0; hb < rows; hb += RB) {
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            finish_row<VEC>(ng[r], strip, SP, lane, gw[2 + r]);
+            finish_row<VEC>(nx[r], strip, SP, lane, xw[2 + r]);
+        }
+        // loads of the next row group fly while this one is computed
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const bool more = ok && (hb + RB + r < rows);
+            issue_row<VEC>(gp, more, h0 + hb + RB + r + 1, H, W, strip, SP, lane, ng[r]);
+            issue_row<VEC>(xp, more, h0 + hb + RB + r + 1, H, W, strip, SP, lane, nx[r]);
         }
 #pragma unroll
-        for (int r = 0; r < DWR_RB; ++r) {
+        for (int r = 0; r < RB; ++r) {
             const bool live = ok && hb + r < rows;
             float o[VEC];
 #pragma unroll
@@ -195,8 +240,8 @@ dw3x3_rows_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x,
         }
 #pragma unroll
         for (int v = 0; v < VEC + 2; ++v) {
-            gw[0][v] = gw[DWR_RB][v]; gw[1][v] = gw[DWR_RB + 1][v];
-            xw[0][v] = xw[DWR_RB][v]; xw[1][v] = xw[DWR_RB + 1][v];
+            gw[0][v] = gw[RB][v]; gw[1][v] = gw[RB + 1][v];
+            xw[0][v] = xw[RB][v]; xw[1][v] = xw[RB + 1][v];
         }
     }
     // Reduce the 10 accumulators over the strips of this (plane, band).  The strips of one (plane, band) are
@@ -231,26 +276,34 @@ dw3x3_rows_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x,
     }
 }
 
-// partial rows that no piece wrote must read as zero: the workspace region is cleared by this kernel first
-__global__ void dw_rows_clear_kernel(float *__restrict__ p, long long n) {
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) p[i] = 0.0f;
-}
-
-// dw[c][t] = sum over (n, band, piece) partial + l2*w ; dbias[c]
+// dw[c][t] = sum over (n, band, piece) partial + l2*w ; dbias[c].  Only the pieces a (plane, band) segment really
+// has are read (a segment of SP consecutive threads starting at thread seg*SP spans a known number of warps), so the
+// workspace needs no clearing.  One pass: every thread accumulates all 10 sums, then 10 block reductions.
 __global__ void __launch_bounds__(128)
 dw_rows_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ w, float *__restrict__ dw,
-                      float *__restrict__ dbias, float l2, int N, int C, int per_plane) {
+                      float *__restrict__ dbias, float l2, int N, int C, int bands, int pieces_max, int SP) {
     __shared__ float red[33];
     const int c = blockIdx.x;
+    const int per_plane = bands * pieces_max;
     const int total = N * per_plane;
-    for (int t = 0; t < 10; ++t) {
-        float s = 0.0f;
-        for (int k = threadIdx.x; k < total; k += blockDim.x) {
-            const int n = k / per_plane, q = k - n * per_plane;
-            s += partial[(((long long)n * C + c) * per_plane + q) * 10 + t];
+    float acc[10];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[t] = 0.0f;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+        const int n = k / per_plane, q = k - n * per_plane;
+        const int band = q / pieces_max, piece = q - band * pieces_max;
+        const long long seg = ((long long)n * C + c) * bands + band;  // (plane, band) id
+        const long long first = seg * SP, last = first + SP - 1;
+        const int npieces = (int)((last >> 5) - (first >> 5)) + 1;
+        if (piece < npieces) {
+            const float *src = partial + (seg * pieces_max + piece) * 10;
+#pragma unroll
+            for (int t = 0; t < 10; ++t) acc[t] += src[t];
         }
-        s = block_sum(s, red);
+    }
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+        const float s = block_sum(acc[t], red);
         if (threadIdx.x == 0) {
             if (t < 9) dw[c * 9 + t] = s + (l2 != 0.0f ? l2 * w[c * 9 + t] : 0.0f);
             else if (dbias) dbias[c] = s;
@@ -259,6 +312,9 @@ dw_rows_reduce_kernel(const float *__restrict__ partial, const float *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------------- host
+int g_dwr_bwd_vec_cap = 4;  // test knob: cap the vector width of the backward kernel
+int g_dwr_bwd_rb = 2;  // rows per iteration of the vec-4 backward kernel (2: 4 CTAs/SM, 4: 2 CTAs/SM)
+
 struct DwRowsPlan {
     int vec, bands, sp, pieces_max;
     long long planes, total;
@@ -319,20 +375,25 @@ int dw_rows_bwd(const float *dy, const float *x, const float *w, float *dx, floa
                 cudaStream_t st) {
     DwRowsPlan pl;
     if (!dw_rows_plan(pl, dy, x, dx, dx_add, N, C, H, W, kh, kw, s, p)) return DK_ERR_UNSUPPORTED;
+    if (pl.vec > g_dwr_bwd_vec_cap) {
+        pl.vec = g_dwr_bwd_vec_cap;
+        pl.sp = W / pl.vec;
+        pl.bands = dw_rows_bands(pl.planes, pl.sp, H);
+        pl.total = pl.planes * pl.bands * pl.sp;
+        pl.pieces_max = (pl.sp + 30) / 32 + 1;
+    }
     const int per_plane = pl.bands * pl.pieces_max;
     const long long nfloats = pl.planes * per_plane * 10;
     if (ws == nullptr || ws_bytes < (size_t)nfloats * sizeof(float)) return DK_ERR_UNSUPPORTED;  // caller falls back
     float *partial = reinterpret_cast<float *>(ws);
-    if (pl.pieces_max > 1) {
-        dw_rows_clear_kernel<<<stream_grid(nfloats, 1024), 256, 0, st>>>(partial, nfloats);
-        DK_LAUNCH_CHECK();
-    }
     const unsigned grid = (unsigned)ceil_div(pl.total, DWR_THREADS);
-    if (pl.vec == 4) dw3x3_rows_bwd_kernel<4><<<grid, DWR_THREADS, 0, st>>>(dy, x, w, dx, partial, dx_add, pl.planes, C, H, W, pl.bands);
-    else if (pl.vec == 2) dw3x3_rows_bwd_kernel<2><<<grid, DWR_THREADS, 0, st>>>(dy, x, w, dx, partial, dx_add, pl.planes, C, H, W, pl.bands);
-    else dw3x3_rows_bwd_kernel<1><<<grid, DWR_THREADS, 0, st>>>(dy, x, w, dx, partial, dx_add, pl.planes, C, H, W, pl.bands);
+    if (pl.vec == 4) {
+        if (g_dwr_bwd_rb == 4) dw3x3_rows_bwd_kernel<4, 4><<<grid, DWR_THREADS, 0, st>>>(dy, x, w, dx, partial, dx_add, pl.planes, C, H, W, pl.bands);
+        else dw3x3_rows_bwd_kernel<4, 2><<<grid, DWR_THREADS, 0, st>>>(dy, x, w, dx, partial, dx_add, pl.planes, C, H, W, pl.bands);
+    } else if (pl.vec == 2) dw3x3_rows_bwd_kernel<2, 4><<<grid, DWR_THREADS, 0, st>>>(dy, x, w, dx, partial, dx_add, pl.planes, C, H, W, pl.bands);
+    else dw3x3_rows_bwd_kernel<1, 4><<<grid, DWR_THREADS, 0, st>>>(dy, x, w, dx, partial, dx_add, pl.planes, C, H, W, pl.bands);
     DK_LAUNCH_CHECK();
-    dw_rows_reduce_kernel<<<C, 128, 0, st>>>(partial, w, dw, dbias, l2, N, C, per_plane);
+    dw_rows_reduce_kernel<<<C, 128, 0, st>>>(partial, w, dw, dbias, l2, N, C, pl.bands, pl.pieces_max, pl.sp);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--once", action="store_true")
     ap.add_argument("--out", default="")
     ap.add_argument("--knobs", default="", help="comma list key=value for dk_tc_debug_set")
+    ap.add_argument("--dw", type=int, default=-1, help="dk_dw_debug_set value")
     a = ap.parse_args()
     import torch
     from dorknet_b200 import api, runtime
@@ -38,6 +39,8 @@ def main():
     for kv in [x for x in a.knobs.split(",") if x]:
         k, v = kv.split("=")
         api.dk_tc_debug_set(int(k), int(v))
+    if a.dw >= 0:
+        api.dk_dw_debug_set(a.dw)
     st = runtime.stream
     N, C, H, W = a.batch, a.chans, a.hw, a.hw
     F = a.filters or C
