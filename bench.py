@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "train images/sec (ResNet-18-depsep, fwd+bwd+SGDMomentum)"
+METRIC = "train images/sec (ResNet-18-depsep, fwd+bwd+SGDMomentum)"  # the BASELINE.json metric (default workload)
 UNIT = "images/s"
 
 
@@ -525,10 +525,13 @@ def run_ours(a, spec):
 
 
 def main():
+    global METRIC
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         del os.environ["NCCL_DEBUG"]  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     a = parse_args()
     spec = workload_spec(a)
+    if a.workload != "resnet18":
+        METRIC = "train images/sec (%s, fwd+bwd+%s)" % (spec["name"], spec["opt"])
     if a.impl == "reference":
         out = run_reference(a, spec)
     else:

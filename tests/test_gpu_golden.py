@@ -240,8 +240,10 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
         np.testing.assert_allclose(losses, d32["losses"], rtol=5e-4)  # TF32 vs the fp32 reference: loss level
         for l in defs.iter_param_layers(net):
             for k in l.learned_params.keys():
-                assert_close(l.learned_params[k].get(), d["final/%s/%s" % (l.layer_name, k)], 30 * tol,
-                             "final %s/%s" % (l.layer_name, k), atol=0.1 * floor + 1e-9)
+                # three momentum steps of this ill-conditioned miniature amplify accumulation-order differences
+                assert_close(l.learned_params[k].get(), d["final/%s/%s" % (l.layer_name, k)],
+                             1e-2 if backend == 0 else 10 * tol, "final %s/%s" % (l.layer_name, k),
+                             atol=0.1 * floor + 1e-9)
         _, st = net.forward(d["X"], None, test_mode=True)
         assert_close(st.get(), d["scores_test"], 20 * tol, "scores_test")
     finally:
