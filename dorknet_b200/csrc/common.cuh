@@ -54,7 +54,7 @@ static inline int stream_grid(int64_t work_items, int per_block, int ctas_per_sm
     return (int)(need < cap ? need : cap);
 }
 
-static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static __host__ __device__ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- device helpers -----------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -186,11 +186,27 @@ __global__ void __launch_bounds__(1024) sumsq_kernel(const float *__restrict__ w
 }
 
 // all l2 terms of a step in one launch: block b reduces tensor b (fixed order) into its own result slot
-__global__ void __launch_bounds__(512) sumsq_multi_kernel(const dk_sumsq_task *__restrict__ tasks) {
+__global__ void __launch_bounds__(1024) sumsq_multi_kernel(const dk_sumsq_task *__restrict__ tasks) {
     __shared__ float red[33];
     const dk_sumsq_task t = tasks[blockIdx.x];
     float s = 0.0f;
-    for (int64_t i = threadIdx.x; i < t.n; i += blockDim.x) s += t.w[i] * t.w[i];
+    int64_t done = 0;
+    if (aligned16(t.w)) {  // 4 x 128-bit loads in flight per thread
+        const int64_t nvec = t.n >> 2;
+        const float4 *w4 = reinterpret_cast<const float4 *>(t.w);
+        int64_t i = threadIdx.x;
+        for (; i + 3 * 1024 < nvec; i += 4 * 1024) {
+            const float4 a = w4[i], b = w4[i + 1024], c = w4[i + 2048], d = w4[i + 3072];
+            s += ((a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w)) + ((b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w)) +
+                 ((c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w)) + ((d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w));
+        }
+        for (; i < nvec; i += 1024) {
+            const float4 a = w4[i];
+            s += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+        }
+        done = nvec << 2;
+    }
+    for (int64_t i = done + threadIdx.x; i < t.n; i += blockDim.x) s += t.w[i] * t.w[i];
     s = block_sum(s, red);
     if (threadIdx.x == 0) t.out[0] = t.scale * s;
 }
@@ -361,7 +377,7 @@ int dk_sumsq(const float *w, float *out, float scale, int64_t n, dk_stream_t str
 int dk_sumsq_multi(const dk_sumsq_task *tasks, int num_tasks, dk_stream_t stream) {
     if (num_tasks <= 0) return DK_OK;
     DK_REQUIRE(tasks != nullptr && num_tasks <= 65535, "dk_sumsq_multi: bad arguments");
-    sumsq_multi_kernel<<<num_tasks, 512, 0, as_stream(stream)>>>(tasks);
+    sumsq_multi_kernel<<<num_tasks, 1024, 0, as_stream(stream)>>>(tasks);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }

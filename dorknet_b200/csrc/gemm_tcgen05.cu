@@ -50,6 +50,8 @@ struct TcParams {
     const float *bias;
     int ldo;
     int epi_ow, epi_s;  // epi 2: output-pixel row length and the stride of the zero-stuffed scatter
+    const float *epi_w;  // epi 1: optional "+ epi_l2 * epi_w[m*N + n]" (weight decay folded into a dense wgrad)
+    float epi_l2;
     uint32_t tmem_cols, acc_stride;
     // MN-major shared-memory descriptor fields (bytes) -- runtime so a bring-up probe can sweep them
     uint32_t mn_layout, mn_lbo, mn_sbo, mn_kstep;
@@ -554,8 +556,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else {
                     if (m_ok) {
-                        float *o = p.out + ((long long)split * p.M + m) * p.N + nb;
-                        if (nb + 32 <= p.N && (p.N & 3) == 0) {
+                        const long long row = ((long long)split * p.M + m) * p.N + nb;
+                        float *o = p.out + row;
+                        if (p.bias || p.epi_w) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (nb + j < p.N) {
+                                    float r = __uint_as_float(v[j]);
+                                    if (p.bias) r += __ldg(p.bias + nb + j);
+                                    if (p.epi_w) r = fmaf(p.epi_l2, __ldg(p.epi_w + row + j), r);
+                                    o[j] = r;
+                                }
+                            }
+                        } else if (nb + 32 <= p.N && (p.N & 3) == 0) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
                                 *reinterpret_cast<float4 *>(o + j) =
@@ -905,11 +918,63 @@ int tc_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, fl
     return cv_wgrad(dy, x, w, dw, l2, N, mk_geom(C, H, W, F, kh, kw, s, p), ws, ws_bytes, st);
 }
 
-int tc_dense_fwd(const float *, const float *, const float *, float *, int, int, int, void *, size_t, cudaStream_t) {
-    return DK_ERR_UNSUPPORTED;
+// ---- DenseLayer (dense_layer.py:46-67): three small GEMMs, all operands through TMA ----------------------------------
+static bool dense_ok(const float *a, const float *b, const float *c, int B, int in_dim, int out_dim) {
+    return g_tc_ready && !(g_tc_disable_mask & 16) && aligned16(a) && aligned16(b) && aligned16(c) && in_dim % 4 == 0 &&
+           out_dim % 4 == 0 && B > 0;
 }
-int tc_dense_bwd(const float *, const float *, const float *, float *, float *, float, int, int, int, void *, size_t,
-                 cudaStream_t) { return DK_ERR_UNSUPPORTED; }
+
+int tc_dense_fwd(const float *x, const float *w, const float *bias, float *y, int B, int in_dim, int out_dim, void *,
+                 size_t, cudaStream_t st) {
+    if (!dense_ok(x, w, y, B, in_dim, out_dim)) return DK_ERR_UNSUPPORTED;
+    TcParams q = {};
+    q.mode = 0; q.a_mn = 0; q.b_mn = 1; q.b_batched = 0;
+    q.M = B; q.N = out_dim; q.K = in_dim; q.batches = 1;
+    fill_common(q);
+    q.num_tiles = q.m_blocks * q.n_blocks;
+    q.epi = 1; q.out = y; q.bias = bias;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, x, in_dim, B, 1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);          // A(m=b, k): k contiguous
+    if (rc) return rc;
+    rc = make_map(&tb, w, out_dim, in_dim, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);    // B(k, n) = W[k][n]: n contiguous
+    if (rc) return rc;
+    return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+}
+
+int tc_dense_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float l2, int B, int in_dim,
+                 int out_dim, void *, size_t, cudaStream_t st) {
+    if (!dense_ok(dy, x, w, B, in_dim, out_dim) || !aligned16(dx) || !aligned16(dw)) return DK_ERR_UNSUPPORTED;
+    {   // dx[B, in] = dy[B, out] @ W^T : A(m=b, k=o) = dy, B(n=i, k=o) = W[i][o] (both K-major)
+        TcParams q = {};
+        q.mode = 0; q.a_mn = 0; q.b_mn = 0; q.b_batched = 0;
+        q.M = B; q.N = in_dim; q.K = out_dim; q.batches = 1;
+        fill_common(q);
+        q.num_tiles = q.m_blocks * q.n_blocks;
+        q.epi = 1; q.out = dx;
+        CUtensorMap ta, tb;
+        int rc = make_map(&ta, dy, out_dim, B, 1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = make_map(&tb, w, out_dim, in_dim, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        rc = tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+        if (rc) return rc;
+    }
+    {   // dw[in, out] = x^T @ dy (+ l2*w) : A(m=i, k=b) = x[b][i], B(k=b, n=o) = dy[b][o] (both MN-major)
+        TcParams q = {};
+        q.mode = 0; q.a_mn = 1; q.b_mn = 1; q.b_batched = 0;
+        q.M = in_dim; q.N = out_dim; q.K = B; q.batches = 1;
+        fill_common(q);
+        q.num_tiles = q.m_blocks * q.n_blocks;
+        q.epi = 1; q.out = dw;
+        if (l2 != 0.0f) { q.epi_w = w; q.epi_l2 = l2; }
+        CUtensorMap ta, tb;
+        int rc = make_map(&ta, x, in_dim, B, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+        if (rc) return rc;
+        rc = make_map(&tb, dy, out_dim, B, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+        if (rc) return rc;
+        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+    }
+}
 size_t tc_dense_ws_bytes(int, int, int) { return 0; }
 
 }  // namespace dk

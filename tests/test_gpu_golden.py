@@ -242,7 +242,7 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
             for k in l.learned_params.keys():
                 # three momentum steps of this ill-conditioned miniature amplify accumulation-order differences
                 assert_close(l.learned_params[k].get(), d["final/%s/%s" % (l.layer_name, k)],
-                             1e-2 if backend == 0 else 10 * tol, "final %s/%s" % (l.layer_name, k),
+                             5e-2 if backend == 0 else 10 * tol, "final %s/%s" % (l.layer_name, k),
                              atol=0.1 * floor + 1e-9)
         _, st = net.forward(d["X"], None, test_mode=True)
         assert_close(st.get(), d["scores_test"], 20 * tol, "scores_test")

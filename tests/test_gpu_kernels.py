@@ -173,3 +173,29 @@ def test_full_size_properties_resnet_shapes():
     lhs = float(np.sum((yb2.astype(np.float64) - ya) * dY))  # <J dx, dY>
     rhs = float(np.sum(1e-2 * X2.astype(np.float64) * dX))    # <dx, J^T dY>
     assert abs(lhs - rhs) <= 2e-3 * abs(rhs)
+
+
+@pytest.mark.parametrize("case", [(64, 512, 120), (8, 128, 12), (130, 64, 300)])
+def test_dense_tcgen05_vs_oracle(O, case):
+    """DenseLayer on the tensor-core path (in/out multiples of 4): fwd, dX, dW (+l2), db."""
+    from dorknet_b200 import _lib
+    from dorknet_b200.layers.dense_layer import DenseLayer
+    from dorknet_b200.regularisers.l2 import l2
+    B, D, K = case
+    rng = np.random.default_rng(B + D + K)
+    X = rng.standard_normal((B, D)).astype(np.float32)
+    Wt = (rng.standard_normal((D, K)) / np.sqrt(D)).astype(np.float32)
+    b = rng.standard_normal(K).astype(np.float32)
+    dY = rng.standard_normal((B, K)).astype(np.float32)
+    lay = DenseLayer("d", D, K, weight_regulariser=l2(1e-2))
+    lay.learned_params["weights"], lay.learned_params["bias"] = Wt, b
+    tc0, _ = _lib.gemm_call_counts()
+    Y = lay.forward(X)
+    assert_close(Y.get(), O.dense_fwd(X, Wt, b), GEMM, "Y")
+    dX = lay.backward(dY)
+    dXo, g = O.dense_bwd(dY, X, Wt, 1e-2, True)
+    assert_close(dX.get(), dXo, GEMM, "dX")
+    assert_close(lay.grads["weights"].get(), g["weights"], GEMM_W, "dW")
+    assert_close(lay.grads["bias"].get(), g["bias"], FP32_RED, "db")
+    tc1, _ = _lib.gemm_call_counts()
+    assert tc1 - tc0 == 2  # forward + backward calls served by the tcgen05 kernels
