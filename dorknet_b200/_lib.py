@@ -8,7 +8,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libdorknet_b200.so")
+LIB_PATH = os.environ.get("DK_LIB_PATH") or os.path.join(HERE, "lib", "libdorknet_b200.so")
 
 DK_OK, DK_ERR_INVALID, DK_ERR_CUDA, DK_ERR_WORKSPACE, DK_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 

@@ -15,6 +15,7 @@
 // floats (128 B): the epilogue is coalesced straight from registers.  fp32 MN-major operands use the
 // 128B-swizzle-with-32B-atom layout (the only MN-major layout the tensor core accepts for 32-bit types).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -437,34 +438,52 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int k0 = kb * TC_BK;
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
+                    // Index arithmetic and copies are issued in explicit batches (pointer arrays + fully unrolled
+                    // inner loops): the compiler's own unrolling of these loops is not stable across builds, and a
+                    // rolled loop serialises address computation behind every single cp.async.
                     if constexpr (AG::kGather) {
                         if constexpr (AG::kMN) {
                             // lanes along m (coalesced pixels), this warp owns k = lw*8 .. lw*8+7
                             typename AG::Row rows[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) rows[j] = ag.row(bb, m0 + 32 * j + lane);
-#pragma unroll 2
-                            for (int kk = 0; kk < 8; ++kk) {
-                                const int k = lw * 8 + kk;
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    cp_async_f32(sA + mn_tile_off(32 * j + lane, k), ag.ptr(rows[j], k0 + k), safe);
+                            for (int kk0 = 0; kk0 < 8; kk0 += 2) {
+                                const float *pp[2][4];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) pp[u][j] = ag.ptr(rows[j], k0 + lw * 8 + kk0 + u);
+#pragma unroll
+                                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        cp_async_f32(sA + mn_tile_off(32 * j + lane, lw * 8 + kk0 + u), pp[u][j], safe);
                             }
                         } else {
                             // lanes along k, this warp owns rows lw, lw+4, ...
                             const auto kc = ag.kcol(bb, k0 + lane);
-#pragma unroll 4
-                            for (int r = lw; r < TC_BM; r += 4)
-                                cp_async_f32(sA + km_tile_off(r, lane), ag.ptr(m0 + r, kc), safe);
+#pragma unroll
+                            for (int r0 = 0; r0 < TC_BM; r0 += 32) {
+                                const float *pp[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) pp[u] = ag.ptr(m0 + r0 + lw + 4 * u, kc);
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) cp_async_f32(sA + km_tile_off(r0 + lw + 4 * u, lane), pp[u], safe);
+                            }
                         }
                     }
                     if constexpr (BG::kGather) {
                         static_assert(!BG::kMN, "gathered B operands are K-major");
                         const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
                         const auto kc = bg.kcol(bbB, k0 + lane);
-#pragma unroll 4
-                        for (int r = lw; r < p.bn; r += 4)
-                            cp_async_f32(sB + km_tile_off(r, lane), bg.ptr(n0 + r, kc), safe);
+                        for (int r0 = 0; r0 < p.bn; r0 += 32) {  // bn is a multiple of 32
+                            const float *pp[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) pp[u] = bg.ptr(n0 + r0 + lw + 4 * u, kc);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) cp_async_f32(sB + km_tile_off(r0 + lw + 4 * u, lane), pp[u], safe);
+                        }
                     }
                     cp_async_commit();
                     ++inflight;
@@ -613,6 +632,7 @@ int init_gemm_tcgen05() {
         return DK_OK;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (const char *m = getenv("DK_TC_DISABLE_MASK")) g_tc_disable_mask = atoi(m);  // diagnostics
     g_tc_ready = true;
     return DK_OK;
 }
