@@ -460,8 +460,19 @@ def run_ours(a, spec):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     ds = dom.summary()[dominant]
     achieved = ds[2] / (ds[1] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dominant)
+        if tr:
+            traffic = tr["traffic_over_algorithmic"] * ds[2] / ds[0]
+            traffic_src = ("profiles/r01_traffic.json: ncu --set full dram bytes / algorithmic bytes = %.3f on the two "
+                           "largest launches of this family, applied to the mean algorithmic bytes per launch"
+                           % tr["traffic_over_algorithmic"])
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "launches_timed": ds[0],
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": ds[2] / ds[0], "launches_timed": ds[0],
                 "avg_launch_us": 1e3 * ds[1] / ds[0],
                 "timing": "CUDA events around each launch of this family, eager pass of %d steps right after the "
                           "graph-replayed timed region" % min(a.steps, 5),
