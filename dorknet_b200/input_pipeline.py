@@ -48,6 +48,28 @@ class HostBatchUploader:
             s["ready"].record(self.stream)
         self._inflight += 1
 
+    def pin(self, X, Y):
+        """Copy a host batch into freshly allocated pinned memory once (what a data loader's output buffers are);
+        returns the pair to pass to submit_from_pinned()."""
+        torch = self.torch
+        hx = torch.empty(int(np.prod(self.x_shape)), dtype=torch.float32).pin_memory()
+        hy = torch.empty(int(np.prod(self.y_shape)), dtype=torch.float32).pin_memory()
+        hx.copy_(torch.from_numpy(np.ascontiguousarray(X, np.float32).reshape(-1)))
+        hy.copy_(torch.from_numpy(np.ascontiguousarray(Y, np.float32).reshape(-1)))
+        return hx, hy
+
+    def submit_from_pinned(self, hx, hy):
+        """Enqueue the H2D copy of an already pinned host batch into the next device slot (no host-side copy)."""
+        torch = self.torch
+        s = self.slots[self._w % len(self.slots)]
+        self._w += 1
+        self.stream.wait_event(s["free"])
+        with torch.cuda.stream(self.stream):
+            s["dx"].t.copy_(hx, non_blocking=True)
+            s["dy"].t.copy_(hy, non_blocking=True)
+            s["ready"].record(self.stream)
+        self._inflight += 1
+
     def submit_pinned(self, slot_filler=None):
         """Like submit() when the producer already wrote the pinned staging tensors in place."""
         torch = self.torch
