@@ -24,6 +24,7 @@ void count_launch() { ++g_launches; }
 
 int init_gemm_tcgen05();  // gemm_tcgen05.cu: opt-in shared memory sizes
 int init_depthwise();     // depthwise.cu
+int init_conv_rows();     // conv_rows.cu
 
 }  // namespace dk
 
@@ -46,6 +47,8 @@ int dk_init(int device) {
     int rc = dk::init_depthwise();
     if (rc) return rc;
     rc = dk::init_gemm_tcgen05();
+    if (rc) return rc;
+    rc = dk::init_conv_rows();
     if (rc) return rc;
     return DK_OK;
 }

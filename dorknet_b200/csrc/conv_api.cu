@@ -21,7 +21,8 @@ static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 static size_t conv_ws(int N, int C, int H, int W, int F, int kh, int kw, int s, int p) {
     const int OH = (H + 2 * p - kh) / s + 1, OW = (W + 2 * p - kw) / s + 1;
     const size_t simt = simt_wgrad_ws_bytes(F, C * kh * kw, (int64_t)N * OH * OW);
-    return max_sz(simt, tc_conv_ws_bytes(N, C, H, W, F, kh, kw, s, p)) + 256;
+    const size_t tc = max_sz(tc_conv_ws_bytes(N, C, H, W, F, kh, kw, s, p), conv_rows_ws_bytes(N, C, H, W, F, kh, kw, s, p));
+    return max_sz(simt, tc) + 256;
 }
 
 }  // namespace dk
@@ -35,8 +36,7 @@ using namespace dk;
             if (_rc == DK_OK) ++g_tc_calls;      \
             return _rc;                          \
         }                                        \
-    }                                            \
-    ++g_simt_calls;
+    }
 
 extern "C" {
 
@@ -56,7 +56,9 @@ int dk_conv2d_fwd(const float *x, const float *w, const float *bias, float *y, i
     int rc = conv_check("dk_conv2d_fwd", N, C, H, W, F, kh, kw, stride, pad);
     if (rc) return rc;
     DK_REQUIRE(x && w && y, "dk_conv2d_fwd: NULL pointer");
+    DK_TRY_TC(conv_rows_fwd(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad, as_stream(stream)));
     DK_TRY_TC(tc_conv_fwd(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
+    ++g_simt_calls;
     return simt_conv_fwd(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad, as_stream(stream));
 }
 
@@ -67,6 +69,7 @@ int dk_conv2d_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     DK_REQUIRE(dy && w && dx, "dk_conv2d_dgrad: NULL pointer");
     const int OH = (H + 2 * pad - kh) / stride + 1, OW = (W + 2 * pad - kw) / stride + 1;
     DK_TRY_TC(tc_conv_dgrad(dy, w, dx, N, C, H, W, F, kh, kw, stride, pad, OH, OW, ws, ws_bytes, as_stream(stream)));
+    ++g_simt_calls;
     return simt_conv_dgrad(dy, w, dx, N, C, H, W, F, kh, kw, stride, pad, OH, OW, as_stream(stream));
 }
 
@@ -81,7 +84,9 @@ int dk_conv2d_wgrad(const float *dy, const float *x, const float *w, float *dw, 
         rc = dk_bias_grad(dy, dbias, N, F, OH * OW, nullptr, 0, stream);
         if (rc) return rc;
     }
+    DK_TRY_TC(conv_rows_wgrad(dy, x, w, dw, l2, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
     DK_TRY_TC(tc_conv_wgrad(dy, x, w, dw, l2, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
+    ++g_simt_calls;
     return simt_conv_wgrad(dy, x, w, dw, l2, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream));
 }
 
@@ -113,6 +118,7 @@ int dk_pwconv_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     if (rc) return rc;
     DK_REQUIRE(dy && w && dx, "dk_pwconv_dgrad: NULL pointer");
     DK_TRY_TC(tc_conv_dgrad(dy, w, dx, N, C, H, W, F, 1, 1, stride, 0, OH, OW, ws, ws_bytes, as_stream(stream)));
+    ++g_simt_calls;
     return simt_conv_dgrad(dy, w, dx, N, C, H, W, F, 1, 1, stride, 0, OH, OW, as_stream(stream));
 }
 
@@ -130,6 +136,7 @@ int dk_dense_fwd(const float *x, const float *w, const float *bias, float *y, in
                  void *ws, size_t ws_bytes, dk_stream_t stream) {
     DK_REQUIRE(B > 0 && in_dim > 0 && out_dim > 0 && x && w && y, "dk_dense_fwd: bad arguments");
     DK_TRY_TC(tc_dense_fwd(x, w, bias, y, B, in_dim, out_dim, ws, ws_bytes, as_stream(stream)));
+    ++g_simt_calls;
     return simt_dense_fwd(x, w, bias, y, B, in_dim, out_dim, as_stream(stream));
 }
 
@@ -142,6 +149,7 @@ int dk_dense_bwd(const float *dy, const float *x, const float *w, float *dx, flo
         if (rc) return rc;
     }
     DK_TRY_TC(tc_dense_bwd(dy, x, w, dx, dw, l2, B, in_dim, out_dim, ws, ws_bytes, as_stream(stream)));
+    ++g_simt_calls;
     return simt_dense_bwd(dy, x, w, dx, dw, l2, B, in_dim, out_dim, ws, ws_bytes, as_stream(stream));
 }
 

@@ -35,4 +35,13 @@ int tc_dense_bwd(const float *dy, const float *x, const float *w, float *dx, flo
 size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
 size_t tc_dense_ws_bytes(int B, int in_dim, int out_dim);
 
+// ---- small-K (C*kh*kw <= 128) row-staged implicit-GEMM convolution: forward + wgrad (conv_rows.cu) -------------------
+int conv_rows_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
+                  int kw, int s, int p, cudaStream_t st);
+int conv_rows_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
+                    int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t conv_rows_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
+extern int g_conv_rows_enabled;
+void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st);
+
 }  // namespace dk

@@ -69,34 +69,6 @@ struct NoGather {
     static constexpr bool kMN = false;
 };
 
-// byte offset of element (m, k) inside an MN-major stage tile (128B swizzle, 32B atom; 32-wide MN blocks of 4 KB)
-__device__ __forceinline__ uint32_t mn_tile_off(int m, int k) {
-    return (uint32_t)(m >> 5) * 4096u + (uint32_t)k * 128u + ((((uint32_t)(m & 31) >> 3) ^ ((uint32_t)k & 3u)) << 5) +
-           ((uint32_t)(m & 7) << 2);
-}
-// byte offset of element (r, k) inside a K-major stage tile (128B swizzle, 16B atom; rows of 128 B)
-__device__ __forceinline__ uint32_t km_tile_off(int r, int k) {
-    return (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
-}
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-// asynchronous 4-byte global -> shared copy (LDGSTS); src == nullptr writes a zero (src-size 0: nothing is read)
-__device__ __forceinline__ void cp_async_f32(uint32_t dst, const float *src, const float *safe) {
-    const uint32_t n = src ? 4u : 0u;
-    const float *q = src ? src : safe;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_pending(int n) {  // wait until at most n groups are still in flight
-    switch (n) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    }
-}
-
 // pixels of a [B, K, SH, SW] tensor subsampled by s: element (b, m = oh*OW + ow, k) = src[b][k][oh*s][ow*s]
 struct PixelGatherMN {
     static constexpr bool kGather = true;
@@ -563,6 +535,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int st2 = p.epi_s;
                         const long long plane = (long long)p.epi_ow * st2 * ((long long)(p.M / p.epi_ow) * st2);
                         float *o = p.out + ((long long)b * p.N + nb) * plane + ((long long)oh * st2) * (p.epi_ow * st2) + ow * st2;
+                        if (st2 == 2 && nb + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.out) & 7u) == 0) {
+                            // the common case: each lane owns a 2x2 cell -> two 8-byte stores, 256 B contiguous per warp and row
+                            const int pitch = p.epi_ow * 2;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float *oj = o + (long long)j * plane;
+                                *reinterpret_cast<float2 *>(oj) = make_float2(__uint_as_float(v[j]), 0.0f);
+                                *reinterpret_cast<float2 *>(oj + pitch) = make_float2(0.0f, 0.0f);
+                            }
+                            continue;
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (nb + j < p.N) {
@@ -743,8 +726,6 @@ static void split_plan(int M, int N, int64_t total_items, int64_t in_bytes, int 
     *per = (int)ceil_div(total_items, s);
     *splits = (int)ceil_div(total_items, *per);
 }
-
-void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st);
 
 static ConvGeom mk_geom(int C, int H, int W, int F, int kh, int kw, int s, int p) {
     ConvGeom g{C, H, W, F, kh, kw, s, p, (H + 2 * p - kh) / s + 1, (W + 2 * p - kw) / s + 1};
@@ -1012,6 +993,7 @@ int dk_tc_debug_set(int key, int value) {
         case 4: dk::g_mn_kstep = value; break;
         case 5: dk::g_mn_swizzle = value; break;
         case 6: dk::g_l2_promo = value; break;  // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
+        case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
         default: dk::set_error("dk_tc_debug_set: unknown key %d", key); return DK_ERR_INVALID;
     }
     {

@@ -140,5 +140,34 @@ __host__ __device__ inline uint32_t idesc_tf32(int M, int N, int a_mn_major, int
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- software-written operand tiles (loader warps) -------------------------------------------------------
+// byte offset of element (m, k) inside an MN-major stage tile (128B swizzle, 32B atom; 32-wide MN blocks of 4 KB)
+__device__ __forceinline__ uint32_t mn_tile_off(int m, int k) {
+    return (uint32_t)(m >> 5) * 4096u + (uint32_t)k * 128u + ((((uint32_t)(m & 31) >> 3) ^ ((uint32_t)k & 3u)) << 5) +
+           ((uint32_t)(m & 7) << 2);
+}
+// byte offset of element (r, k) inside a K-major stage tile (128B swizzle, 16B atom; rows of 128 B)
+__device__ __forceinline__ uint32_t km_tile_off(int r, int k) {
+    return (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// asynchronous 4-byte global -> shared copy (LDGSTS); src == nullptr writes a zero (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async_f32(uint32_t dst, const float *src, const float *safe) {
+    const uint32_t n = src ? 4u : 0u;
+    const float *q = src ? src : safe;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {  // wait until at most n groups are still in flight
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+
 }  // namespace tc
 }  // namespace dk

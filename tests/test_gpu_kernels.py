@@ -120,6 +120,9 @@ CONV_CASES = [
     # N, C, H, W, F, k, s, p
     (2, 3, 33, 33, 8, 5, 2, 1), (2, 3, 65, 65, 64, 5, 2, 1), (2, 32, 14, 14, 64, 4, 2, 1), (2, 64, 16, 16, 64, 3, 1, 1),
     (2, 1, 28, 28, 32, 3, 1, 1), (2, 5, 10, 10, 7, 3, 2, 1), (1, 16, 9, 9, 300, 3, 1, 0),
+    # small-K row-staged kernels (conv_rows.cu): conv0 at full width (OW = 112: partial last pixel chunk), several
+    # tiles per output row, MobileNet conv0, many rows per CTA
+    (2, 3, 225, 225, 64, 5, 2, 1), (1, 3, 40, 300, 16, 3, 1, 1), (3, 3, 224, 224, 32, 3, 2, 1), (40, 3, 33, 33, 24, 5, 2, 1),
 ]
 
 
@@ -130,10 +133,14 @@ def test_conv_tcgen05_vs_oracle(O, case):
     rng = np.random.default_rng(hash(case) & 0xffff)
     X = rng.standard_normal((N, C, H, W)).astype(np.float32)
     Wt = (rng.standard_normal((F, C, k, k)) / np.sqrt(C * k * k)).astype(np.float32)
-    lay = ConvLayer("c", (F, C, k, k), stride=s, padding=p, with_bias=False)
+    bias = (N + F) % 2 == 1
+    b = rng.standard_normal(F).astype(np.float32) if bias else None
+    lay = ConvLayer("c", (F, C, k, k), stride=s, padding=p, with_bias=bias)
     lay.learned_params["weights"] = Wt
+    if bias:
+        lay.learned_params["bias"] = b
     Y = lay.forward(X)
-    Yo, cache = O.conv_fwd(X, Wt, None, s, p)
+    Yo, cache = O.conv_fwd(X, Wt, b, s, p)
     assert np.array_equal(lay.im2col_materialise(X).get(), cache["P"])  # bit-exact im2col index map
     assert_close(Y.get(), Yo, GEMM, "Y")
     dY = rng.standard_normal(Yo.shape).astype(np.float32)
