@@ -8,32 +8,13 @@
 // deterministic -- across CTAs.  That last CTA also finalises the channel (std, scale/shift,
 // running statistics), so statistics + finalise are ONE launch with no memset: the arrival
 // counters live in a caller-provided, zero-initialised workspace and are reset on exit.
-#include "common.cuh"
+#include "bn.cuh"
 
 namespace dk {
 
 constexpr int BN_THREADS = 256;
 constexpr int BN_MAX_SPLITS = 64;
 constexpr int BN_WS_FLOATS_PER_SPLIT = 4;  // stats use 3 (n, mean, M2); backward uses 2
-
-struct Moments {
-    float n, mean, m2;
-};
-
-__device__ __forceinline__ Moments merge(const Moments &a, const Moments &b) {
-    Moments r;
-    r.n = a.n + b.n;
-    if (r.n == 0.0f) {
-        r.mean = 0.0f;
-        r.m2 = 0.0f;
-        return r;
-    }
-    const float delta = b.mean - a.mean;
-    const float fb = b.n / r.n;
-    r.mean = a.mean + delta * fb;
-    r.m2 = a.m2 + b.m2 + delta * delta * a.n * fb;
-    return r;
-}
 
 __device__ __forceinline__ Moments warp_merge(Moments m) {
 #pragma unroll
@@ -49,17 +30,6 @@ __device__ __forceinline__ Moments warp_merge(Moments m) {
     }
     return m;
 }
-
-struct BnFinalize {
-    // mode 0: write mean/var only (dk_bn_stats); mode 1: full training finalise
-    int mode;
-    float *mean_out, *var_out;
-    const float *gamma, *beta;
-    float *running_mean, *running_std;
-    int first_batch;
-    float momentum, eps;
-    float *save_mean, *save_invstd, *save_scale, *save_shift;
-};
 
 // x viewed as [N, C, HW]; channel c's virtual index v in [0, N*HW) maps to x[(v/HW)*C*HW + c*HW + v%HW].
 template <bool VEC>
@@ -474,6 +444,10 @@ int dk_bn_fwd_train(const float *x, float *y, const float *gamma, const float *b
     fin.save_invstd = save_invstd;
     fin.save_scale = save_scale;
     fin.save_shift = save_shift;
+    if (y != nullptr) {  // statistics + normalisation in one cluster kernel when the channel slices fit shared memory
+        rc = bn_fused_fwd(x, y, fin, fuse_relu, N, C, HW, as_stream(stream));
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     rc = launch_stats(x, N, C, HW, ws, fin, as_stream(stream));
     if (rc || y == nullptr) return rc;
     return launch_apply(x, y, save_scale, save_shift, fuse_relu, N, C, HW, as_stream(stream));
@@ -506,6 +480,8 @@ int dk_bn_bwd(const float *dy, const float *x, const float *gamma, const float *
                "dk_bn_bwd: NULL pointer");
     (void)gamma;  // gamma*invstd is save_scale
     cudaStream_t st = as_stream(stream);
+    rc = bn_fused_bwd(dy, x, save_mean, save_invstd, save_scale, save_shift, dx, dgamma, dbeta, fuse_relu, N, C, HW, st);
+    if (rc != DK_ERR_UNSUPPORTED) return rc;
     int S;
     int64_t per;
     bn_plan(N, C, HW, &S, &per);

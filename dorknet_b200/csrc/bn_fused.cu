@@ -1,0 +1,462 @@
+// bn_fused.cu -- BatchNorm forward (statistics + normalise [+ReLU]) and backward (reductions + dX) as ONE kernel each,
+// with the channel resident in shared memory between the two passes.
+//
+// The reference makes ~8 passes over the activation per BatchNorm direction (batch_norm.py:66-74, 118-156); the split
+// kernels of batchnorm.cu make the algorithmic minimum of an unfused implementation, 3n forward (read for the
+// statistics, read + write for the apply) and 5n backward.  Here a thread-block cluster owns a channel: each of its S
+// CTAs pulls its slice of the channel's N*HW values (and of dY, backward) into shared memory with bulk-async copies
+// (cp.async.bulk, one per image plane, completion on an mbarrier), reduces it, exchanges the partial sums with the
+// other CTAs through distributed shared memory, and then runs the second pass straight out of shared memory:
+// 2n forward, 3n backward from HBM.  Everything is fixed-order -> deterministic.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "bn.cuh"
+#include "tc_ptx.cuh"
+
+namespace dk {
+
+using namespace tc;
+
+constexpr int BF_THREADS = 256;
+constexpr int BF_SMEM_MAX = 200 * 1024;  // dynamic bytes per CTA the slices may use
+constexpr int BF_MAX_CLUSTER = 16;          // > 8 is the non-portable cluster size (opt-in per kernel)
+constexpr int BF_SMEM_TARGET = 64 * 1024;   // preferred slice bytes per CTA: several CTAs per SM overlap their load / compute / store phases
+
+struct BfGeom {
+    int N, C, HW, S;
+    int per;   // slice length in elements (multiple of 4 when bulk)
+    int bulk;  // planes are 16-byte multiples and aligned: cp.async.bulk; else plain loads
+};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ld_dsmem(const float *local, unsigned rank) {
+    uint32_t ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// slice [v0, v1) of channel c (virtual index v = n*HW + off) of NT tensors -> shared memory, contiguous in v
+template <int NT>
+__device__ __forceinline__ void bf_load_slice(const float *const (&src)[NT], float *const (&dst)[NT], const BfGeom &g, int c,
+                                              int v0, int v1, uint32_t bar) {
+    const int len = v1 - v0;
+    if (g.bulk) {
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(NT * len) * 4u);
+            __syncwarp();
+            const int n_first = v0 / g.HW, n_last = (v1 - 1) / g.HW;
+            for (int n = n_first + (int)threadIdx.x; n <= n_last; n += 32) {
+                const int a = n * g.HW > v0 ? n * g.HW : v0;
+                const int b = (n + 1) * g.HW < v1 ? (n + 1) * g.HW : v1;
+                const long long goff = ((long long)n * g.C + c) * g.HW + (a - n * g.HW);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) bulk_g2s(smem_u32(dst[t] + (a - v0)), src[t] + goff, (uint32_t)(b - a) * 4u, bar);
+            }
+        }
+        mbar_wait(bar, 0u);
+    } else {
+        // plain loads, four elements per thread in flight per tensor before anything is stored
+        for (int i0 = threadIdx.x; i0 < len; i0 += 4 * BF_THREADS) {
+            float tmp[NT][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * BF_THREADS;
+                if (i < len) {
+                    const int v = v0 + i;
+                    const int n = v / g.HW, off = v - n * g.HW;
+                    const long long goff = ((long long)n * g.C + c) * g.HW + off;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) tmp[t][u] = __ldg(src[t] + goff);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * BF_THREADS;
+                if (i < len) {
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) dst[t][i] = tmp[t][u];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// block-wide sum of two values; result valid in every thread (fixed order)
+__device__ __forceinline__ void bf_block_sum2(float &a, float &b, float *red /* >= 2*8+2 floats */) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        red[wid] = a;
+        red[8 + wid] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ta = red[0], tb = red[8];
+#pragma unroll
+        for (int w = 1; w < BF_THREADS / 32; ++w) {
+            ta += red[w];
+            tb += red[8 + w];
+        }
+        red[16] = ta;
+        red[17] = tb;
+    }
+    __syncthreads();
+    a = red[16];
+    b = red[17];
+}
+
+// ---- forward ------------------------------------------------------------------------------------------------------------
+template <bool RELU>
+__global__ void __launch_bounds__(BF_THREADS)
+bn_fused_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, const BfGeom g, const BnFinalize fin) {
+    extern __shared__ __align__(16) float slice[];
+    __shared__ __align__(8) uint64_t bar_mem;
+    __shared__ float red[18];
+    __shared__ float xch[4];  // this CTA's (n, mean, M2), read by the whole cluster
+    __shared__ float ss[2];
+    const int c = blockIdx.y;
+    const unsigned rank = blockIdx.x;  // cluster = the S CTAs of one channel
+    const int total = g.N * g.HW;
+    const int v0 = (int)rank * g.per;
+    const int v1 = v0 + g.per < total ? v0 + g.per : total;
+    const int len = v1 - v0;
+    const uint32_t bar = smem_u32(&bar_mem);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    {
+        const float *const src[1] = {x};
+        float *const dst[1] = {slice};
+        bf_load_slice<1>(src, dst, g, c, v0, v1, bar);
+    }
+    // pass 1: shifted sums (shift = first value of the slice, the same for every thread, so partial sums just add up)
+    const float shift = slice[0];
+    float sum = 0.0f, sq = 0.0f;
+    const int len4 = len & ~3;
+    for (int i = 4 * threadIdx.x; i < len4; i += 4 * BF_THREADS) {
+        const float4 t = *reinterpret_cast<const float4 *>(slice + i);
+        const float d0 = t.x - shift, d1 = t.y - shift, d2 = t.z - shift, d3 = t.w - shift;
+        sum += (d0 + d1) + (d2 + d3);
+        sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    if ((int)threadIdx.x < len - len4) {
+        const float d = slice[len4 + threadIdx.x] - shift;
+        sum += d;
+        sq += d * d;
+    }
+    bf_block_sum2(sum, sq, red);
+    if (threadIdx.x == 0) {
+        const float n = (float)len;
+        xch[0] = n;
+        xch[1] = shift + sum / n;
+        xch[2] = fmaxf(sq - sum * sum / n, 0.0f);
+    }
+    __syncwarp();
+    cluster_arrive();
+    cluster_wait();
+    if (threadIdx.x < 32) {
+        // every CTA merges the S partials in rank order (bit-identical statistics everywhere); lane r fetches rank r's
+        // partial through distributed shared memory, the merge runs on shuffled copies
+        const unsigned lane = threadIdx.x;
+        Moments mine = {0.0f, 0.0f, 0.0f};
+        if (lane < (unsigned)g.S) {
+            mine.n = ld_dsmem(xch + 0, lane);
+            mine.mean = ld_dsmem(xch + 1, lane);
+            mine.m2 = ld_dsmem(xch + 2, lane);
+        }
+        Moments all;
+        all.n = __shfl_sync(0xffffffffu, mine.n, 0);
+        all.mean = __shfl_sync(0xffffffffu, mine.mean, 0);
+        all.m2 = __shfl_sync(0xffffffffu, mine.m2, 0);
+        for (int r = 1; r < g.S; ++r) {
+            Moments o;
+            o.n = __shfl_sync(0xffffffffu, mine.n, r);
+            o.mean = __shfl_sync(0xffffffffu, mine.mean, r);
+            o.m2 = __shfl_sync(0xffffffffu, mine.m2, r);
+            all = merge(all, o);
+        }
+        if (lane == 0) {
+            const float var = all.m2 / all.n;  // biased (batch_norm_stats_cy.pyx:44)
+            float sc, sh;
+            bn_finalize_channel(fin, c, all.mean, var, rank == 0, &sc, &sh);
+            ss[0] = sc;
+            ss[1] = sh;
+        }
+    }
+    __syncwarp();
+    cluster_arrive();  // peers may exit only after everybody has read their xch (waited for at the end)
+    __syncthreads();
+    if (y != nullptr) {
+        // pass 2 out of shared memory: y = x*scale + shift (+ReLU)
+        const float sc = ss[0], sh = ss[1];
+        for (int i = 4 * threadIdx.x; i < len4; i += 4 * BF_THREADS) {
+            float4 t = *reinterpret_cast<const float4 *>(slice + i);
+            t.x = fmaf(t.x, sc, sh); t.y = fmaf(t.y, sc, sh); t.z = fmaf(t.z, sc, sh); t.w = fmaf(t.w, sc, sh);
+            if (RELU) {
+                t.x = t.x > 0.f ? t.x : 0.f; t.y = t.y > 0.f ? t.y : 0.f;
+                t.z = t.z > 0.f ? t.z : 0.f; t.w = t.w > 0.f ? t.w : 0.f;
+            }
+            const int v = v0 + i;
+            const int n = v / g.HW, off = v - n * g.HW;
+            float *o = y + ((long long)n * g.C + c) * g.HW + off;
+            if (g.bulk) {
+                st_stream4(o, t);  // HW % 4 == 0: the four values share a plane and the address is 16-byte aligned
+            } else {
+                const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ve = v + e;
+                    const int ne = ve / g.HW, oe = ve - ne * g.HW;
+                    y[((long long)ne * g.C + c) * g.HW + oe] = tv[e];
+                }
+            }
+        }
+        if ((int)threadIdx.x < len - len4) {
+            const int v = v0 + len4 + threadIdx.x;
+            float t = fmaf(slice[len4 + threadIdx.x], sc, sh);
+            if (RELU) t = t > 0.f ? t : 0.f;
+            const int n = v / g.HW, off = v - n * g.HW;
+            y[((long long)n * g.C + c) * g.HW + off] = t;
+        }
+    }
+    cluster_wait();
+}
+
+// ---- backward -----------------------------------------------------------------------------------------------------------
+template <bool RELU>
+__global__ void __launch_bounds__(BF_THREADS)
+bn_fused_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dx, const BfGeom g,
+                    const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+                    const float *__restrict__ save_scale, const float *__restrict__ save_shift, float *__restrict__ dgamma,
+                    float *__restrict__ dbeta) {
+    extern __shared__ __align__(16) float slice[];
+    __shared__ __align__(8) uint64_t bar_mem;
+    __shared__ float red[18];
+    __shared__ float xch[2];
+    __shared__ float kk[2];
+    const int c = blockIdx.y;
+    const unsigned rank = blockIdx.x;
+    const int total = g.N * g.HW;
+    const int v0 = (int)rank * g.per;
+    const int v1 = v0 + g.per < total ? v0 + g.per : total;
+    const int len = v1 - v0;
+    float *sg = slice, *sx = slice + ((g.per + 3) & ~3);  // 16-byte aligned for the float4 passes
+    const uint32_t bar = smem_u32(&bar_mem);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    {
+        const float *const src[2] = {dy, x};
+        float *const dst[2] = {sg, sx};
+        bf_load_slice<2>(src, dst, g, c, v0, v1, bar);
+    }
+    const float mean = save_mean[c], invstd = save_invstd[c], sc = save_scale[c];
+    const float sh = RELU ? save_shift[c] : 0.0f;
+    // pass 1: sum(g), sum(g * x_hat); with a fused ReLU the masked gradient is written back for pass 2
+    float a = 0.0f, b = 0.0f;
+    const int len4 = len & ~3;
+    for (int i = 4 * threadIdx.x; i < len4; i += 4 * BF_THREADS) {
+        float4 gq = *reinterpret_cast<const float4 *>(sg + i);
+        const float4 t = *reinterpret_cast<const float4 *>(sx + i);
+        if (RELU) {
+            gq.x = fmaf(t.x, sc, sh) > 0.f ? gq.x : 0.f; gq.y = fmaf(t.y, sc, sh) > 0.f ? gq.y : 0.f;
+            gq.z = fmaf(t.z, sc, sh) > 0.f ? gq.z : 0.f; gq.w = fmaf(t.w, sc, sh) > 0.f ? gq.w : 0.f;
+            *reinterpret_cast<float4 *>(sg + i) = gq;
+        }
+        a += (gq.x + gq.y) + (gq.z + gq.w);
+        b += (gq.x * ((t.x - mean) * invstd) + gq.y * ((t.y - mean) * invstd)) +
+             (gq.z * ((t.z - mean) * invstd) + gq.w * ((t.w - mean) * invstd));
+    }
+    if ((int)threadIdx.x < len - len4) {
+        const int i = len4 + threadIdx.x;
+        float gv = sg[i];
+        const float t = sx[i];
+        if (RELU) {
+            gv = fmaf(t, sc, sh) > 0.f ? gv : 0.f;
+            sg[i] = gv;
+        }
+        a += gv;
+        b += gv * ((t - mean) * invstd);
+    }
+    bf_block_sum2(a, b, red);
+    if (threadIdx.x == 0) {
+        xch[0] = a;
+        xch[1] = b;
+    }
+    __syncwarp();
+    cluster_arrive();
+    cluster_wait();
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        float pa = 0.0f, pb = 0.0f;
+        if (lane < (unsigned)g.S) {
+            pa = ld_dsmem(xch + 0, lane);
+            pb = ld_dsmem(xch + 1, lane);
+        }
+        float ta = 0.0f, tb = 0.0f;
+        for (int r = 0; r < g.S; ++r) {  // fixed order
+            ta += __shfl_sync(0xffffffffu, pa, r);
+            tb += __shfl_sync(0xffffffffu, pb, r);
+        }
+        if (lane == 0) {
+            if (rank == 0) {
+                dbeta[c] = ta;   // batch_norm.py:171
+                dgamma[c] = tb;  // batch_norm.py:164
+            }
+            const float inv_n = 1.0f / (float)total;
+            kk[0] = ta * inv_n;
+            kk[1] = tb * inv_n;
+        }
+    }
+    __syncwarp();
+    cluster_arrive();
+    __syncthreads();
+    // pass 2 out of shared memory: dx = scale * (g - mean(g) - x_hat * mean(g * x_hat))   (batch_norm.py:127-156)
+    const float k1 = kk[0], k2 = kk[1];
+    for (int i = 4 * threadIdx.x; i < len4; i += 4 * BF_THREADS) {
+        const float4 gq = *reinterpret_cast<const float4 *>(sg + i);
+        const float4 t = *reinterpret_cast<const float4 *>(sx + i);
+        float4 r;
+        r.x = sc * (gq.x - k1 - ((t.x - mean) * invstd) * k2);
+        r.y = sc * (gq.y - k1 - ((t.y - mean) * invstd) * k2);
+        r.z = sc * (gq.z - k1 - ((t.z - mean) * invstd) * k2);
+        r.w = sc * (gq.w - k1 - ((t.w - mean) * invstd) * k2);
+        const int v = v0 + i;
+        const int n = v / g.HW, off = v - n * g.HW;
+        float *o = dx + ((long long)n * g.C + c) * g.HW + off;
+        if (g.bulk) {
+            st_stream4(o, r);
+        } else {
+            const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ve = v + e;
+                const int ne = ve / g.HW, oe = ve - ne * g.HW;
+                dx[((long long)ne * g.C + c) * g.HW + oe] = rv[e];
+            }
+        }
+    }
+    if ((int)threadIdx.x < len - len4) {
+        const int i = len4 + threadIdx.x;
+        const int v = v0 + i;
+        const int n = v / g.HW, off = v - n * g.HW;
+        dx[((long long)n * g.C + c) * g.HW + off] = sc * (sg[i] - k1 - ((sx[i] - mean) * invstd) * k2);
+    }
+    cluster_wait();
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static bool g_bf_ready = false;
+static int g_bf_max_cluster = 8;
+int g_bn_fused_enabled = 1;
+
+int bn_fused_init() {
+    DK_CUDA(cudaFuncSetAttribute(bn_fused_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_MAX));
+    DK_CUDA(cudaFuncSetAttribute(bn_fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_MAX));
+    DK_CUDA(cudaFuncSetAttribute(bn_fused_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_MAX));
+    DK_CUDA(cudaFuncSetAttribute(bn_fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM_MAX));
+    // clusters of 16 CTAs are opt-in; keep 8 if the device refuses
+    bool np_ok = true;
+    np_ok &= cudaFuncSetAttribute(bn_fused_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    np_ok &= cudaFuncSetAttribute(bn_fused_fwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    np_ok &= cudaFuncSetAttribute(bn_fused_bwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    np_ok &= cudaFuncSetAttribute(bn_fused_bwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (np_ok) {
+        // make sure a 16-CTA cluster with the largest slices we would ask for can be co-scheduled
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(16, 1, 1);
+        cfg.blockDim = dim3(BF_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = 100 * 1024;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 16;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, bn_fused_bwd_kernel<false>, &cfg) == cudaSuccess && nclusters > 0)
+            g_bf_max_cluster = 16;
+    }
+    cudaGetLastError();
+    if (const char *e = getenv("DK_BN_MAX_CLUSTER")) g_bf_max_cluster = atoi(e) >= 16 ? 16 : atoi(e) >= 8 ? 8 : atoi(e) >= 4 ? 4 : atoi(e) >= 2 ? 2 : 1;
+    g_bf_ready = true;
+    return DK_OK;
+}
+
+// cluster size and slice length: enough CTAs to fill the machine twice, slices of at most BF_SMEM_TARGET bytes when a
+// cluster of <= 16 CTAs allows it (else up to BF_SMEM_MAX), no empty trailing CTA
+static bool bf_plan(int N, int C, int HW, int ntensors, bool bulk, BfGeom *g) {
+    if (!g_bf_ready || !g_bn_fused_enabled || C > 65535) return false;
+    const int64_t total = (int64_t)N * HW;
+    const int64_t cap = BF_SMEM_MAX / (4 * ntensors) - 4, want = BF_SMEM_TARGET / (4 * ntensors);
+    const int64_t unit = bulk ? 4 : 1;
+    auto per_of = [&](int s) { return ceil_div(ceil_div(total, s), unit) * unit; };
+    int s = 1;
+    while (s < BF_MAX_CLUSTER && ((int64_t)C * s < 2 * sm_count() || per_of(s) > want)) s *= 2;
+    if (s > g_bf_max_cluster) s = g_bf_max_cluster;
+    while (s > 1 && (int64_t)(s - 1) * per_of(s) >= total) s /= 2;
+    const int64_t per = per_of(s);
+    if (per > cap || (int64_t)(s - 1) * per >= total) return false;
+    g->N = N; g->C = C; g->HW = HW; g->S = s; g->per = (int)per; g->bulk = bulk ? 1 : 0;
+    return true;
+}
+
+template <class... Exp, class... Act>
+static int bf_launch(void (*kernel)(Exp...), const BfGeom &g, size_t smem, cudaStream_t st, Act &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)g.S, (unsigned)g.C, 1);
+    cfg.blockDim = dim3(BF_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)g.S;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...));
+    count_launch();
+    return DK_OK;
+}
+
+int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st) {
+    const bool bulk = (HW % 4 == 0) && aligned16(x) && (y == nullptr || aligned16(y));
+    BfGeom g;
+    if (!bf_plan(N, C, HW, 1, bulk, &g)) return DK_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)g.per * 4;
+    if (relu) return bf_launch(bn_fused_fwd_kernel<true>, g, smem, st, x, y, g, fin);
+    return bf_launch(bn_fused_fwd_kernel<false>, g, smem, st, x, y, g, fin);
+}
+
+int bn_fused_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
+                 const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
+                 cudaStream_t st) {
+    const bool bulk = (HW % 4 == 0) && aligned16(x) && aligned16(dy) && aligned16(dx);
+    BfGeom g;
+    if (!bf_plan(N, C, HW, 2, bulk, &g)) return DK_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)((g.per + 3) & ~3) * 8;
+    if (relu)
+        return bf_launch(bn_fused_bwd_kernel<true>, g, smem, st, dy, x, dx, g, save_mean, save_invstd, save_scale, save_shift,
+                         dgamma, dbeta);
+    return bf_launch(bn_fused_bwd_kernel<false>, g, smem, st, dy, x, dx, g, save_mean, save_invstd, save_scale, save_shift,
+                     dgamma, dbeta);
+}
+
+}  // namespace dk

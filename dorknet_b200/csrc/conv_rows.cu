@@ -44,6 +44,7 @@ struct ConvRowsParams {
     int iwt;         // staged input columns per tile
     int phw, irow;   // staged rows are split by column phase (col % s): phw columns per phase, irow = s*phw floats per row
     int in_floats;   // C*kh*irow rounded up to 4
+    int in_stages;   // staged input tiles in flight + 1 (the global-load latency is spread over in_stages-1 tiles)
     int tiles_per_row, num_tiles;
     uint32_t tmem_cols, acc_stride;
     int PC, BMR, rows_total, a_stages;  // wgrad: 32-pixel chunks per output row, dY rows per chunk, (n, oh) rows, dY ring depth
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
     const uint32_t a_bytes = (uint32_t)p.KC * 16384u;
     const uint32_t b_bytes = (uint32_t)p.KC * (uint32_t)p.bn * 128u;
     const uint32_t in_bytes = (uint32_t)p.in_floats * 4u;
-    const uint32_t sA = base, sB = sA + 2u * a_bytes, sIn = sB + b_bytes, bar = sIn + 2u * in_bytes;
+    const uint32_t sA = base, sB = sA + 2u * a_bytes, sIn = sB + b_bytes, bar = sIn + (uint32_t)p.in_stages * in_bytes;
     auto a_full = [&](int a) { return bar + 8u * a; };
     auto a_empty = [&](int a) { return bar + 8u * (2 + a); };
     auto t_full = [&](int a) { return bar + 8u * (4 + a); };
@@ -177,24 +178,28 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
             ow0 = owb * 128;
         };
         int n, oh, ow0;
-        if ((int)blockIdx.x < p.num_tiles) {
-            tile_coords(blockIdx.x, n, oh, ow0);
-            cr_stage_input(p, sIn, n, oh * p.s - p.p, ow0 * p.s - p.p, lw, lane);
+        const int D = p.in_stages - 1;  // prefetch distance in tiles
+        for (int d = 0; d < D; ++d) {
+            const long long t = (long long)blockIdx.x + (long long)d * gridDim.x;
+            if (t < p.num_tiles) {
+                tile_coords((int)t, n, oh, ow0);
+                cr_stage_input(p, sIn + (uint32_t)d * in_bytes, n, oh * p.s - p.p, ow0 * p.s - p.p, lw, lane);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            cp_async_wait_pending(0);
-            cr_loader_barrier();  // tile `it` is staged; every loader is done expanding tile it-1
-            const int next = tile + gridDim.x;
+            cp_async_wait_pending(D - 1);
+            cr_loader_barrier();  // tile `it` is staged; every loader is done expanding tile it-1 (whose buffer is reused now)
+            const long long next = (long long)tile + (long long)D * gridDim.x;
             if (next < p.num_tiles) {
-                tile_coords(next, n, oh, ow0);
-                cr_stage_input(p, sIn + (uint32_t)((it + 1) & 1) * in_bytes, n, oh * p.s - p.p, ow0 * p.s - p.p, lw, lane);
+                tile_coords((int)next, n, oh, ow0);
+                cr_stage_input(p, sIn + (uint32_t)((it + D) % p.in_stages) * in_bytes, n, oh * p.s - p.p, ow0 * p.s - p.p, lw, lane);
             }
             cp_async_commit();
             const int a = it & 1;
             mbar_wait(a_empty(a), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-            const float *in = in_f + (size_t)(it & 1) * p.in_floats;
+            const float *in = in_f + (size_t)(it % p.in_stages) * p.in_floats;
             const uint32_t sAa = sA + (uint32_t)a * a_bytes;
             const uint32_t lane_off = (((uint32_t)lane & 7u) << 2);
 #pragma unroll 2
@@ -273,7 +278,7 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
     const uint32_t in_bytes = (uint32_t)p.in_floats * 4u;
     // the dY ring comes first: with F < 128 the M=128 MMA reads 128-BMR rows past a chunk, which must stay inside
     // the allocation (those accumulator rows are never read back)
-    const uint32_t sA = base, sB = sA + (uint32_t)p.a_stages * a_bytes, sIn = sB + 2u * b_bytes, bar = sIn + 2u * in_bytes;
+    const uint32_t sA = base, sB = sA + (uint32_t)p.a_stages * a_bytes, sIn = sB + 2u * b_bytes, bar = sIn + (uint32_t)p.in_stages * in_bytes;
     auto a_full = [&](int a) { return bar + 8u * a; };
     auto a_empty = [&](int a) { return bar + 8u * (CR_MAX_A_STAGES + a); };
     auto b_full = [&](int a) { return bar + 8u * (2 * CR_MAX_A_STAGES + a); };
@@ -362,23 +367,26 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
         // ================================ loaders =====================================
         const int lw = warp - 6;
         const float *in_f = reinterpret_cast<const float *>(gbase + (sIn - base));
-        if (r_beg < r_end) {
-            const int n = r_beg / p.OH, oh = r_beg - n * p.OH;
-            cr_stage_input(p, sIn, n, oh * p.s - p.p, -p.p, lw, lane);
+        const int D = p.in_stages - 1;
+        for (int d = 0; d < D; ++d) {
+            if (r_beg + d < r_end) {
+                const int n = (r_beg + d) / p.OH, oh = (r_beg + d) - n * p.OH;
+                cr_stage_input(p, sIn + (uint32_t)d * in_bytes, n, oh * p.s - p.p, -p.p, lw, lane);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
         int it = 0;
         for (int r = r_beg; r < r_end; ++r, ++it) {
-            cp_async_wait_pending(0);
+            cp_async_wait_pending(D - 1);
             cr_loader_barrier();
-            if (r + 1 < r_end) {
-                const int n = (r + 1) / p.OH, oh = (r + 1) - n * p.OH;
-                cr_stage_input(p, sIn + (uint32_t)((it + 1) & 1) * in_bytes, n, oh * p.s - p.p, -p.p, lw, lane);
+            if (r + D < r_end) {
+                const int n = (r + D) / p.OH, oh = (r + D) - n * p.OH;
+                cr_stage_input(p, sIn + (uint32_t)((it + D) % p.in_stages) * in_bytes, n, oh * p.s - p.p, -p.p, lw, lane);
             }
             cp_async_commit();
             const int sb = it & 1;
             mbar_wait(b_empty(sb), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-            const float *in = in_f + (size_t)(it & 1) * p.in_floats;
+            const float *in = in_f + (size_t)(it % p.in_stages) * p.in_floats;
             const uint32_t sBb = sB + (uint32_t)sb * b_bytes;
             const uint32_t lane_off = (((uint32_t)lane & 3u) << 2);
 #pragma unroll 2
@@ -472,7 +480,10 @@ int conv_rows_fwd(const float *x, const float *w, const float *bias, float *y, i
     q.num_tiles = (int)tiles;
     q.acc_stride = cr_tmem_cols(q.bn);
     q.tmem_cols = 2 * q.acc_stride;
-    const size_t smem = 1024 + 2 * (size_t)q.KC * 16384 + (size_t)q.KC * q.bn * 128 + 2 * (size_t)q.in_floats * 4 + 128;
+    const size_t fixed = 1024 + 2 * (size_t)q.KC * 16384 + (size_t)q.KC * q.bn * 128 + 128;
+    q.in_stages = 4;
+    while (q.in_stages > 2 && fixed + (size_t)q.in_stages * q.in_floats * 4 > (size_t)CR_SMEM_MAX) --q.in_stages;
+    const size_t smem = fixed + (size_t)q.in_stages * q.in_floats * 4;
     if (smem > (size_t)CR_SMEM_MAX) return DK_ERR_UNSUPPORTED;
     const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
     conv_rows_fwd_kernel<<<grid, CR_THREADS, smem, st>>>(q);
@@ -492,7 +503,11 @@ static int cr_wgrad_plan(ConvRowsParams &q, size_t *smem, int *grid) {
     q.rows_total = q.N * q.OH;
     q.tmem_cols = cr_tmem_cols(q.KP);
     const size_t a_bytes = (size_t)q.PC * q.BMR * 128, b_bytes = (size_t)q.PC * q.KP * 128;
-    const size_t fixed = 1024 + 2 * b_bytes + 2 * (size_t)q.in_floats * 4 + 256;
+    // two dY stages first (the HBM stream), then up to four input stages, then more dY stages
+    q.in_stages = 4;
+    size_t fixed = 1024 + 2 * b_bytes + 256;
+    while (q.in_stages > 2 && fixed + 2 * a_bytes + (size_t)q.in_stages * q.in_floats * 4 > (size_t)CR_SMEM_MAX) --q.in_stages;
+    fixed += (size_t)q.in_stages * q.in_floats * 4;
     int stages = CR_MAX_A_STAGES;
     while (stages > 1 && fixed + stages * a_bytes > (size_t)CR_SMEM_MAX) --stages;
     // the M=128 MMA over-reads (128 - BMR) rows past the last dY chunk: they must fall inside the patch tiles

@@ -24,6 +24,8 @@
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 
+namespace dk { extern int g_bn_fused_enabled; }
+
 namespace dk {
 
 using namespace tc;
@@ -993,6 +995,7 @@ int dk_tc_debug_set(int key, int value) {
         case 4: dk::g_mn_kstep = value; break;
         case 5: dk::g_mn_swizzle = value; break;
         case 6: dk::g_l2_promo = value; break;  // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
+        case 9: dk::g_bn_fused_enabled = value; break;  // 0: BatchNorm through the split kernels of batchnorm.cu only
         case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
         default: dk::set_error("dk_tc_debug_set: unknown key %d", key); return DK_ERR_INVALID;
     }

@@ -5,6 +5,31 @@ from .layer import Layer, api, runtime, asarray, empty
 from ..array import LazyBNOutput
 
 
+class _RunningStats(dict):
+    """non_learned_params of a BatchNormLayer: reading an entry first runs a still-deferred forward kernel, so the
+    running mean / std are always the ones the reference would hold at this point (batch_norm.py:76-89)."""
+
+    def __init__(self, owner, *a, **kw):
+        super().__init__(*a, **kw)
+        self._owner = owner
+
+    def __getitem__(self, k):
+        self._owner._flush()
+        return super().__getitem__(k)
+
+    def get(self, k, default=None):
+        self._owner._flush()
+        return super().get(k, default)
+
+    def items(self):
+        self._owner._flush()
+        return super().items()
+
+    def values(self):
+        self._owner._flush()
+        return super().values()
+
+
 class BatchNormLayer(Layer):
     """https://arxiv.org/pdf/1502.03167.pdf -- same constructor as batch_norm.py:13-14."""
 
@@ -12,7 +37,8 @@ class BatchNormLayer(Layer):
         super().__init__(layer_name)
         self.eps = 1e-5
         self.input_dimension = input_dimension
-        self.non_learned_params = {"running_mean": None, "running_std": None}
+        self._pending = None
+        self.non_learned_params = _RunningStats(self, {"running_mean": None, "running_std": None})
         self.run_momentum = run_momentum
         if self.input_dimension not in {2, 4}:
             raise ValueError("BatchNorm input_dimension should have length 2 or 4...")
@@ -31,15 +57,23 @@ class BatchNormLayer(Layer):
             self.grads = {}
         self._x = None
         self._relu_fused = False
-        self.defer_apply = True  # return a lazy output so that a following ReLu can fuse (False: always apply now)
+        self._pending = None
+        self.defer_apply = True  # return a lazy output so that a following ReLu can fuse (False: run the kernel now)
 
     def fused_relu_apply(self, y):
-        """y = relu(x*scale + shift) in one pass (called by the ReLu that consumes our lazy output); the mask is
-        re-derived from x in backward, so this layer's backward must start with it."""
-        N, C, HW = self._dims(self.input_shape)
-        base = self._bufs["saved"].ptr
-        api.dk_bn_apply(self._x.ptr, y.ptr, base + 8 * C, base + 12 * C, 1, N, C, HW, runtime.stream())
+        """y = relu(batchnorm(x)) in the SAME kernel as the statistics (called by the ReLu that consumes our lazy
+        output); the mask is re-derived from x in backward, so this layer's backward must start with it."""
+        pending, self._pending = self._pending, None
+        if pending is None:
+            raise RuntimeError("BatchNormLayer {}: output already materialised".format(self.layer_name))
+        pending(y, 1)
         self._relu_fused = True
+
+    def _flush(self):
+        """Run a still-deferred training forward (somebody needs the statistics before any consumer used y)."""
+        if self._pending is not None:
+            pending, self._pending = self._pending, None
+            pending(self._bufs["y"], 0)
 
     def __repr__(self):
         return "BatchNormLayer({}, input_dimension={}, incoming_chans={}, run_momentum={})".format(
@@ -78,20 +112,28 @@ class BatchNormLayer(Layer):
             sv = self._buf("saved", (4, C))  # mean, invstd, scale, shift
             ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
             base = sv.ptr
+            self._flush()
             self._x = X
             self._relu_fused = False
+            mom, eps = float(self.run_momentum), float(self.eps)
+
+            def run(out, relu):
+                # statistics + running mean/std + normalisation (+ReLU) in one call: a cluster kernel that keeps the
+                # channel in shared memory between the two passes (bn_fused.cu), or the split kernels
+                api.dk_bn_fwd_train(X.ptr, out.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first), mom, eps,
+                                    base, base + 4 * C, base + 8 * C, base + 12 * C, relu, N, C, HW, ws, wsn,
+                                    runtime.stream())
             if self.defer_apply:
-                # statistics now, normalisation when the consumer is known (a ReLu fuses it with its own pass)
-                api.dk_bn_fwd_train(X.ptr, None, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first),
-                                    float(self.run_momentum), float(self.eps),
-                                    base, base + 4 * C, base + 8 * C, base + 12 * C, 0, N, C, HW, ws, wsn, st)
+                # nothing is launched until the consumer is known: a ReLu asks for the fused variant, anybody else
+                # (or a reader of the running statistics) gets the plain one
+                self._pending = run
 
                 def apply():
-                    api.dk_bn_apply(X.ptr, y.ptr, base + 8 * C, base + 12 * C, 0, N, C, HW, runtime.stream())
+                    pending, self._pending = self._pending, None
+                    if pending is not None:
+                        pending(y, 0)
                 return LazyBNOutput(y, apply, self)
-            api.dk_bn_fwd_train(X.ptr, y.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first),
-                                float(self.run_momentum), float(self.eps),
-                                base, base + 4 * C, base + 8 * C, base + 12 * C, 0, N, C, HW, ws, wsn, st)
+            run(y, 0)
         else:
             rm, rs = self.non_learned_params["running_mean"], self.non_learned_params["running_std"]
             if rm is None:
@@ -103,6 +145,7 @@ class BatchNormLayer(Layer):
     def backward(self, upstream_dx):
         """batch_norm.py:118-174: grads["gamma"], grads["beta"] and dx in two passes over (dY, X)."""
         dY = asarray(upstream_dx)
+        self._flush()
         N, C, HW = self._dims(self.input_shape)
         sv = self._bufs["saved"]
         base = sv.ptr
@@ -117,5 +160,6 @@ class BatchNormLayer(Layer):
     @property
     def std(self):
         """sqrt(var + eps) of the last training batch, shape (1,C,1,1) / (C,) (batch_norm.py:69-72)."""
+        self._flush()
         sv = self._bufs["saved"].get()
         return (1.0 / sv[1]).reshape(self._stat_shape(sv.shape[1])).astype(np.float32)

@@ -193,8 +193,8 @@ def test_optimisers(golden, L, nm):
         assert_close(lay.learned_params["bias"].get(), d["b%d" % (i + 1)], 2e-6, "b step %d" % i)
 
 
-@pytest.mark.parametrize("backend", [0, 1])
-def test_mini_resnet_three_training_steps(golden, L, backend):
+@pytest.mark.parametrize("backend,bn_fused", [(0, 0), (0, 1), (1, 1)])
+def test_mini_resnet_three_training_steps(golden, L, backend, bn_fused):
     """conv s2 - BN - ReLU - pw s2 - BN - ReLU - 2 residual blocks (identity and pw-s2 skip) - GAP -
     dense - softmax, 3 SGDMomentum steps: losses, first-step gradients and final weights.
 
@@ -202,7 +202,17 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
     just as tightly, to the reference run whose conv / pointwise GEMM operands were truncated to TF32
     (tests/golden/make_golden.py net_case("rz")): that is exactly what the tensor core does with fp32 operands, and
     this miniature net is ill-conditioned enough (BatchNorm over 8x2x2 samples) that the truncation alone moves
-    some gradients of the fp32 reference by ~10 % -- so the fp32 golden is only used for the loss there."""
+    some gradients of the fp32 reference by ~10 % -- so the fp32 golden is only used for the loss there.
+
+    That bit-level agreement with the TF32-truncated reference only holds while every fp32 value that reaches a GEMM
+    rounds as the reference's does: with the fused BatchNorm cluster kernels (bn_fused.cu, the default) the
+    statistics are summed in a different order, BatchNorm outputs move by an ulp, a handful of TF32 truncations
+    land on the other side, and in THIS net the 1/std of near-constant channels plus ReLU mask flips blow that up to
+    a few per cent on some gradients (tests/mini_net_diag.py --layerwise shows the cascade; every BatchNorm is
+    within 1.5e-7 of a float64 evaluation of its own input in both modes, and with fp32 GEMMs the two modes agree
+    to 4e-7).  So: (0, 0) split BatchNorm kernels pin the TF32 arithmetic model tightly, (1, 1) pins the fused
+    BatchNorm tightly on fp32 GEMMs, and (0, 1) -- the product default -- is held to the loss, the scores and a
+    5 % gradient band."""
     import importlib.util
     import os
     from dorknet_b200 import api
@@ -213,6 +223,8 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
     d = golden("mini_net_tf32rz" if backend == 0 else "mini_net")
     d32 = golden("mini_net")
     api.dk_set_gemm_backend(backend)
+    api.dk_tc_debug_set(9, bn_fused)
+    chaotic = backend == 0 and bn_fused == 1
     try:
         net = defs.build_small_net(L, seed=123)
         for l in defs.iter_param_layers(net):
@@ -234,10 +246,10 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
                 for l in defs.iter_param_layers(net):
                     for k in l.grads.keys():
                         assert_close(l.grads[k].get(), d["grad0/%s/%s" % (l.layer_name, k)], 10 * tol,
-                                     "grad0 %s/%s" % (l.layer_name, k), atol=floor)
+                                     "grad0 %s/%s" % (l.layer_name, k), atol=50 * floor if chaotic else floor)
             opt.update_weights()
-        np.testing.assert_allclose(losses, d["losses"], rtol=tol)
-        np.testing.assert_allclose(losses, d32["losses"], rtol=5e-4)  # TF32 vs the fp32 reference: loss level
+        np.testing.assert_allclose(losses, d["losses"], rtol=2e-3 if chaotic else tol)
+        np.testing.assert_allclose(losses, d32["losses"], rtol=2e-3 if chaotic else 5e-4)  # TF32 vs the fp32 reference: loss level
         for l in defs.iter_param_layers(net):
             for k in l.learned_params.keys():
                 # three momentum steps of this ill-conditioned miniature amplify accumulation-order differences
@@ -245,6 +257,7 @@ def test_mini_resnet_three_training_steps(golden, L, backend):
                              5e-2 if backend == 0 else 10 * tol, "final %s/%s" % (l.layer_name, k),
                              atol=0.1 * floor + 1e-9)
         _, st = net.forward(d["X"], None, test_mode=True)
-        assert_close(st.get(), d["scores_test"], 20 * tol, "scores_test")
+        assert_close(st.get(), d["scores_test"], (200 if chaotic else 20) * tol, "scores_test")
     finally:
         api.dk_set_gemm_backend(0)
+        api.dk_tc_debug_set(9, 1)

@@ -206,3 +206,67 @@ def test_dense_tcgen05_vs_oracle(O, case):
     assert_close(lay.grads["bias"].get(), g["bias"], FP32_RED, "db")
     tc1, _ = _lib.gemm_call_counts()
     assert tc1 - tc0 == 2  # forward + backward calls served by the tcgen05 kernels
+
+
+BN_CASES = [
+    # N, C, H, W : cluster size / load path the shape selects in bn_fused.cu
+    (4, 8, 56, 56),     # S = 8, bulk copies, slices cut inside planes
+    (64, 64, 28, 28),   # S = 8: every CTA owns whole planes
+    (8, 256, 14, 14),   # S = 2
+    (6, 512, 7, 7),     # S = 1, HW % 4 != 0: plain loads
+    (3, 5, 9, 11),      # odd everything, tails
+    (2, 3, 300, 300),   # slices too large for shared memory in backward: split kernels
+    (5, 16, 1, 1),      # one value per (n, c)
+]
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("case", BN_CASES)
+def test_batchnorm_vs_oracle(O, case, relu, fused):
+    """BatchNorm forward / backward (with and without the fused ReLU) against the oracle, through the cluster kernels
+    (fused=1) and through the split statistics / apply / reduce / dx kernels (fused=0)."""
+    from dorknet_b200 import api
+    from dorknet_b200.layers.batch_norm import BatchNormLayer
+    from dorknet_b200.layers.activations import ReLu
+    N, C, H, W = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = (rng.standard_normal((N, C, H, W)) * rng.uniform(0.5, 3.0, (1, C, 1, 1)) + rng.uniform(-2, 2, (1, C, 1, 1))).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, (1, C, 1, 1)).astype(np.float32)
+    beta = rng.uniform(-0.5, 0.5, (1, C, 1, 1)).astype(np.float32)
+    dY = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    api.dk_tc_debug_set(9, fused)
+    try:
+        bn = BatchNormLayer("bn", input_dimension=4, incoming_chans=C)
+        bn.learned_params["gamma"], bn.learned_params["beta"] = gamma, beta
+        act = ReLu("r")
+        Yo, cache, rm, rs = O.bn_fwd_train(X, gamma, beta, None, None)
+        dXo_in = dY
+        if relu:
+            Y = act.forward(bn.forward(X))
+            Yo_r, mask = O.relu_fwd(Yo)
+            # the fused kernel evaluates x*scale + shift, the oracle gamma*x_hat + beta: values within rounding of 0
+            # may land on either side of the ReLU
+            safe = np.abs(Yo) > 1e-5 * np.max(np.abs(Yo))
+            assert_close(np.where(safe, Y.get(), 0), np.where(safe, Yo_r, 0), FP32, "relu(Y)")
+            # backward parity uses OUR mask: both directions of the kernel evaluate the same x*scale + shift > 0
+            dXo_in = O.relu_bwd(dY, (Y.get() > 0).astype(np.float32))
+        else:
+            Y = bn.forward(X)
+            assert_close(Y.get(), Yo, FP32, "Y")
+        assert_close(bn.non_learned_params["running_mean"].get(), rm, FP32, "running_mean")
+        assert_close(bn.non_learned_params["running_std"].get(), rs, FP32, "running_std")
+        dXo, g = O.bn_bwd(dXo_in, gamma, cache)
+        dX = bn.backward(act.backward(dY) if relu else dY)
+        tol = 5 * FP32_RED if relu else FP32_RED
+        assert_close(dX.get(), dXo, tol, "dX", atol=1e-6)
+        assert_close(bn.grads["gamma"].get(), g["gamma"], tol, "dgamma", atol=1e-5)
+        assert_close(bn.grads["beta"].get(), g["beta"], tol, "dbeta", atol=1e-5)
+        # second batch: running statistics EMA
+        X2 = (X * 0.5 + 1.0).astype(np.float32)
+        _, _, rm2, rs2 = O.bn_fwd_train(X2, gamma, beta, rm, rs)
+        bn.forward(X2)
+        assert_close(bn.non_learned_params["running_mean"].get(), rm2, FP32, "running_mean 2")
+        assert_close(bn.non_learned_params["running_std"].get(), rs2, FP32, "running_std 2")
+    finally:
+        api.dk_tc_debug_set(9, 1)
