@@ -457,12 +457,29 @@ int dw_rows_fwd(const float *x, const float *w, const float *bias, float *y, int
 int dw_rows_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
                 float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, void *ws, size_t ws_bytes,
                 cudaStream_t st);
+// planes-in-shared-memory path for 3x3 / pad 1 / stride 1 or 2 (depthwise_planes.cu)
+size_t dw_planes_ws_bytes(int N, int C);
+int init_dw_planes();
+int dw_planes_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int kh, int kw,
+                  int s, int p, cudaStream_t st);
+int dw_planes_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
+                  float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, void *ws, size_t ws_bytes,
+                  cudaStream_t st);
 static int g_dw_rows_enabled = 1;
+// 0: never, 1: where measured faster than the register-window kernels (dw_use_planes), 2: wherever it applies
+static int g_dw_planes_mode = 1;
 extern int g_dwr_bwd_rb, g_dwr_bwd_vec_cap;
 
 int init_depthwise() {
     // budgets are within the 48 KB default for forward; backward may slightly exceed with the filter stash
-    return DK_OK;
+    return init_dw_planes();
+}
+
+static bool dw_use_planes(bool backward, int H, int W, int s) {
+    if (g_dw_planes_mode == 0) return false;
+    if (g_dw_planes_mode == 2) return true;
+    (void)backward; (void)H; (void)W;
+    return s == 2;  // TODO(measure): stride-1 shapes
 }
 
 template <int KH, int KW, int S>
@@ -501,7 +518,9 @@ size_t dk_dwconv_ws_bytes(int N, int C, int H, int W, int kh, int kw, int stride
     if (dw_geom(g, N, C, H, W, kh, kw, stride, pad, true, "dk_dwconv_ws_bytes")) return 0;
     const size_t tiles = (size_t)g.planes * g.bands * (kh * kw + 1) * sizeof(float);
     const size_t rows = dw_rows_ws_bytes(N, C, H, W, kh, kw, stride, pad);
-    return tiles > rows ? tiles : rows;
+    const size_t planes = dw_planes_ws_bytes(N, C);
+    const size_t m = tiles > rows ? tiles : rows;
+    return m > planes ? m : planes;
 }
 
 int dk_dwconv_fwd(const float *x, const float *w, const float *bias, float *y, const float *in_scale,
@@ -513,6 +532,10 @@ int dk_dwconv_fwd(const float *x, const float *w, const float *bias, float *y, c
     DK_REQUIRE(x && w && y, "dk_dwconv_fwd: NULL pointer");
     DK_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "dk_dwconv_fwd: in_scale/in_shift must come together");
     cudaStream_t st = as_stream(stream);
+    if (in_scale == nullptr && dw_use_planes(false, H, W, stride)) {
+        rc = dw_planes_fwd(x, w, bias, y, N, C, H, W, kh, kw, stride, pad, st);
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     if (g_dw_rows_enabled && in_scale == nullptr) {
         rc = dw_rows_fwd(x, w, bias, y, N, C, H, W, kh, kw, stride, pad, st);
         if (rc != DK_ERR_UNSUPPORTED) return rc;
@@ -531,6 +554,10 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
     if (rc) return rc;
     DK_REQUIRE(dy && x && w && dx && dw, "dk_dwconv_bwd: NULL pointer");
     DK_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "dk_dwconv_bwd: in_scale/in_shift must come together");
+    if (in_scale == nullptr && dw_use_planes(true, H, W, stride)) {
+        rc = dw_planes_bwd(dy, x, w, dx, dw, dbias, dx_add, l2, N, C, H, W, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream));
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     if (g_dw_rows_enabled && in_scale == nullptr) {
         rc = dw_rows_bwd(dy, x, w, dx, dw, dbias, dx_add, l2, N, C, H, W, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream));
         if (rc != DK_ERR_UNSUPPORTED) return rc;
@@ -551,11 +578,18 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
     return DK_OK;
 }
 
-/* test hook: 0 = always use the shared-memory tile kernels, 1 = register-window fast path where it applies */
+/* test hook: 0 = always use the shared-memory tile kernels, 1 = default dispatch, 2 = planes-in-smem kernels wherever
+   they apply, 3 = register-window kernels without the planes kernels */
 int dk_dw_debug_set(int enable_rows) {
-    if (enable_rows >= 20) g_dwr_bwd_vec_cap = enable_rows - 20;  // 21 / 22 / 24
+    if (enable_rows == 2 || enable_rows == 3) {
+        g_dw_rows_enabled = 1;
+        g_dw_planes_mode = enable_rows == 2 ? 2 : 0;
+    } else if (enable_rows >= 20) g_dwr_bwd_vec_cap = enable_rows - 20;  // 21 / 22 / 24
     else if (enable_rows >= 10) g_dwr_bwd_rb = enable_rows - 10;  // 12 / 14: rows per iteration of the backward kernel
-    else g_dw_rows_enabled = enable_rows;
+    else {
+        g_dw_rows_enabled = enable_rows;
+        g_dw_planes_mode = enable_rows ? 1 : 0;
+    }
     return DK_OK;
 }
 

@@ -72,7 +72,7 @@ def main():
     saved = empty((4, C))
     bn_ws = runtime.zeroed_workspace(api.dk_bn_ws_bytes(C))
     ws_ptr, ws_n = runtime.scratch(max(api.dk_pwconv_ws_bytes(N, C, H, W, F, s), api.dk_conv2d_ws_bytes(N, C, H, W, F, 3, 3, 1, 1),
-                                       api.dk_dwconv_ws_bytes(N, C, H, W, 3, 3, 1, 1), 1 << 20))
+                                       api.dk_dwconv_ws_bytes(N, C, H, W, 3, 3, s, 1), 1 << 20))
     sv = saved.ptr
     # make the saved BN statistics valid once
     api.dk_bn_fwd_train(xs[0].ptr, y_c.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, 1, 0.95, 1e-5, sv, sv + 4 * C, sv + 8 * C,
@@ -87,10 +87,11 @@ def main():
                                                        bn_ws.data_ptr(), bn_ws.numel(), st()), 4 * 3 * n_in, 0),
         "bn_bwd": (lambda i: api.dk_bn_bwd(dys_c[i].ptr, xs[i].ptr, gamma.ptr, sv, sv + 4 * C, sv + 8 * C, sv + 12 * C, dx.ptr,
                                            dg.ptr, db.ptr, 0, N, C, H * W, bn_ws.data_ptr(), bn_ws.numel(), st()), 4 * 5 * n_in, 0),
-        "dw_fwd": (lambda i: api.dk_dwconv_fwd(xs[i].ptr, w_dw.ptr, None, y_c.ptr, None, None, 0, N, C, H, W, 3, 3, 1, 1, st()),
-                   4 * 2 * n_in, 2 * n_in * 9),
-        "dw_bwd": (lambda i: api.dk_dwconv_bwd(dys_c[i].ptr, xs[i].ptr, w_dw.ptr, dx.ptr, dw_dw.ptr, None, None, None, 0, None,
-                                               0.0, N, C, H, W, 3, 3, 1, 1, ws_ptr, ws_n, st()), 4 * 3 * n_in, 4 * n_in * 9),
+        "dw_fwd": (lambda i: api.dk_dwconv_fwd(xs[i].ptr, w_dw.ptr, None, y_c.ptr, None, None, 0, N, C, H, W, 3, 3, s, 1, st()),
+                   4 * (n_in + N * C * OH * OW), 2 * N * C * OH * OW * 9),
+        "dw_bwd": (lambda i: api.dk_dwconv_bwd((dys_c[i] if s == 1 else dys_pw[i]).ptr, xs[i].ptr, w_dw.ptr, dx.ptr, dw_dw.ptr,
+                                               None, None, None, 0, None, 0.0, N, C, H, W, 3, 3, s, 1, ws_ptr, ws_n, st()),
+                   4 * (2 * n_in + N * C * OH * OW), 4 * N * C * OH * OW * 9),
         "pw_fwd": (lambda i: api.dk_pwconv_fwd(xs[i].ptr, w_pw.ptr, None, y_pw.ptr, N, C, H, W, F, s, ws_ptr, ws_n, st()),
                    4 * (N * C * OH * OW + n_out_pw), 2 * N * OH * OW * F * C),
         "pw_dgrad": (lambda i: api.dk_pwconv_dgrad(dys_pw[i].ptr, w_pw.ptr, dx.ptr, N, C, OH, OW, F, s, ws_ptr, ws_n, st()),

@@ -25,12 +25,16 @@ DW_CASES = [
     (1, 5, 9, 112, 3, 1, 1, False),   # 28 strips/row
     (1, 3, 12, 224, 3, 1, 1, False),  # a row spans two warps (56 strips)
     (2, 8, 11, 13, 3, 1, 1, False),   # odd sizes -> scalar strips
-    (2, 8, 56, 56, 3, 2, 1, False),   # stride 2 (x.5 patch count): tile kernel
+    (2, 8, 56, 56, 3, 2, 1, False),   # stride 2 (x.5 patch count): tile / planes kernel
+    (3, 16, 28, 28, 3, 2, 1, True),   # stride 2, vec 4 output rows
+    (3, 24, 14, 14, 3, 2, 1, False),  # stride 2, scalar items, several planes per CTA
+    (5, 40, 7, 7, 3, 2, 1, True),     # stride 2, odd plane (7 -> 4), ragged last group
+    (2, 5, 13, 9, 3, 2, 1, False),    # stride 2, odd non-square
     (2, 6, 15, 15, 5, 1, 2, True),    # 5x5: generic tile kernel
 ]
 
 
-@pytest.mark.parametrize("rows", [1, 0])
+@pytest.mark.parametrize("rows", [1, 0, 2, 3])  # default dispatch, tiles, planes-in-smem, register windows
 @pytest.mark.parametrize("case", DW_CASES)
 def test_depthwise_vs_oracle(O, case, rows):
     from dorknet_b200 import api
