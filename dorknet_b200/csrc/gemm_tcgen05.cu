@@ -729,6 +729,11 @@ static void split_plan(int M, int N, int64_t total_items, int64_t in_bytes, int 
     *splits = (int)ceil_div(total_items, *per);
 }
 
+static int g_repack_mask = 3;  // bit0: misaligned stride-1 planes, bit1: stride-s planes of <= TC_REPACK_MAX_P pixels
+constexpr int64_t TC_REPACK_MAX_P = 1024;
+static int64_t repack_pitch(int64_t P) { return (P + 3) / 4 * 4; }
+static size_t repack_bytes(int64_t rows, int64_t P) { return (size_t)(rows * repack_pitch(P)) * sizeof(float) + 256; }
+
 static ConvGeom mk_geom(int C, int H, int W, int F, int kh, int kw, int s, int p) {
     ConvGeom g{C, H, W, F, kh, kw, s, p, (H + 2 * p - kh) / s + 1, (W + 2 * p - kw) / s + 1};
     return g;
@@ -740,14 +745,79 @@ size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s
     const int Kf = C * kh * kw;
     int splits, per;
     split_plan(F, Kf, (int64_t)N * ceil_div(P, TC_BK), (int64_t)N * P * (F + Kf) * 4, &splits, &per);
-    return (size_t)splits * F * Kf * sizeof(float);
+    size_t repack = 0;  // padded copies of dY and X (pointwise only; fwd / dgrad need one of the two)
+    if (kh == 1 && kw == 1 && p == 0 && ((P % 4) != 0 || s > 1) && P <= 4 * TC_REPACK_MAX_P)
+        repack = repack_bytes((int64_t)N * F, P) + repack_bytes((int64_t)N * C, P) + 512;
+    return (size_t)splits * F * Kf * sizeof(float) + repack;
 }
 
 static bool dims_ok(int64_t a, int64_t b) { return a > 0 && b > 0 && a < (1 << 30) && b < (1 << 30); }
 
+// ---- plane repacking ------------------------------------------------------------------------------------------------
+// TMA needs 16-byte row pitches.  Planes whose pixel count is not a multiple of 4 (7x7 = 49 floats = 196 B) and
+// stride-s subsampled planes used to go through the loader warps' 4-byte gathers, which are bound by the issue rate of
+// four warps (ncu: 33 instructions per cp.async, stages published one item at a time).  Small planes are instead
+// copied once into the workspace with the pitch rounded up to 4 floats (pad = 0, so padded k contribute nothing to a
+// reduction and padded m are masked by the epilogue) and every operand goes through TMA.
+
+__global__ void __launch_bounds__(256)
+repack_planes_kernel(const float *__restrict__ src, float *__restrict__ dst, long long rows, int plane, int SW, int OW, int s,
+                     int P, int Pp) {
+    const int q4 = Pp >> 2;
+    const long long total = rows * q4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / q4;
+        const int j0 = (int)(i - row * q4) * 4;
+        const float *sp = src + row * plane;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j0 + e;
+            float t = 0.0f;
+            if (j < P) {
+                if (s == 1) t = __ldg(sp + j);
+                else {
+                    const int oh = j / OW, ow = j - oh * OW;
+                    t = __ldg(sp + (long long)oh * s * SW + ow * s);
+                }
+            }
+            v[e] = t;
+        }
+        *reinterpret_cast<float4 *>(dst + row * Pp + j0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// measured on B200 (tests/pw_sweep.py, batch 64): 7x7 planes fwd/dgrad 26 -> 18 us, wgrad 71 -> 33 us; stride-2 wgrad
+// 28x28 -> 14x14 26 -> 20 us, 14x14 -> 7x7 40 -> 26 us; a stride-2 FORWARD whose output planes are TMA-friendly is
+// faster through the gather loaders (the repack would re-read what the gather reads once), so it keeps them
+static bool repack_wanted(const float *ptr, int64_t P, int s, bool reduction_operand) {
+    if (s == 1) return (g_repack_mask & 1) && !tma_ok(ptr, P) && P <= 4 * TC_REPACK_MAX_P;
+    if (!(g_repack_mask & 2) || P > TC_REPACK_MAX_P) return false;
+    return reduction_operand || (P % 4) != 0;
+}
+// carve `bytes` (256-byte aligned) off the front of the workspace; nullptr if it does not fit
+static float *ws_carve(void *&ws, size_t &ws_bytes, size_t bytes) {
+    if (ws == nullptr) return nullptr;
+    uintptr_t a = (reinterpret_cast<uintptr_t>(ws) + 255u) & ~(uintptr_t)255u;
+    const size_t skip = a - reinterpret_cast<uintptr_t>(ws);
+    if (ws_bytes < skip + bytes) return nullptr;
+    ws = reinterpret_cast<void *>(a + bytes);
+    ws_bytes -= skip + bytes;
+    return reinterpret_cast<float *>(a);
+}
+// [rows][SH][SW] sampled at stride s -> dst[rows][Pp]
+static int repack_launch(const float *src, float *dst, int64_t rows, int SH, int SW, int OW, int s, int64_t P, cudaStream_t st) {
+    const int Pp = (int)repack_pitch(P);
+    const long long total = rows * (Pp / 4);
+    const int grid = (int)(ceil_div(total, 256) < 8 * sm_count() ? ceil_div(total, 256) : 8 * sm_count());
+    repack_planes_kernel<<<grid, 256, 0, st>>>(src, dst, rows, SH * SW, SW, OW, s, (int)P, Pp);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
 // ---- pointwise (1x1, pad 0, stride s) ------------------------------------------------------------------------
 static int pw_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int s,
-                  cudaStream_t st) {
+                  void *ws, size_t ws_bytes, cudaStream_t st) {
     const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
     const int64_t P = (int64_t)OH * OW;
     if (!tma_ok(w, C) || !dims_ok(P, (int64_t)H * W)) return DK_ERR_UNSUPPORTED;
@@ -765,10 +835,20 @@ static int pw_fwd(const float *x, const float *w, const float *bias, float *y, i
         if (rc) return rc;
         return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
     }
+    if (repack_wanted(x, P, s, false)) {
+        if (float *xp = ws_carve(ws, ws_bytes, repack_bytes((int64_t)N * C, P))) {
+            rc = repack_launch(x, xp, (int64_t)N * C, H, W, OW, s, P, st);
+            if (rc) return rc;
+            rc = make_map(&ta, xp, repack_pitch(P), C, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+            if (rc) return rc;
+            return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+        }
+    }
     return tc_launch(ta, tb, q, PixelGatherMN{x, C, H, W, OW, (int)P, s}, NoGather{}, st);
 }
 
-static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, int OH, int OW, int F, int s, cudaStream_t st) {
+static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, int OH, int OW, int F, int s, void *ws,
+                    size_t ws_bytes, cudaStream_t st) {
     const int64_t P = (int64_t)OH * OW;
     if (!tma_ok(w, C) || !dims_ok(P, P * s * s)) return DK_ERR_UNSUPPORTED;
     TcParams q = {};
@@ -785,6 +865,15 @@ static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
         rc = make_map(&ta, dy, P, F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
         if (rc) return rc;
         return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+    }
+    if (repack_wanted(dy, P, 1, false)) {
+        if (float *gp = ws_carve(ws, ws_bytes, repack_bytes((int64_t)N * F, P))) {
+            rc = repack_launch(dy, gp, (int64_t)N * F, OH, OW, OW, 1, P, st);
+            if (rc) return rc;
+            rc = make_map(&ta, gp, repack_pitch(P), F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+            if (rc) return rc;
+            return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+        }
     }
     return tc_launch(ta, tb, q, PixelGatherMN{dy, F, OH, OW, OW, (int)P, 1}, NoGather{}, st);
 }
@@ -808,11 +897,30 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     }
     q.epi = 1; q.out = reinterpret_cast<float *>(ws); q.bias = nullptr; q.ldo = 0;
     CUtensorMap ta = {}, tb = {};
-    const bool a_tma = tma_ok(dy, P), b_tma = (s == 1) && tma_ok(x, P);
+    bool a_tma = tma_ok(dy, P), b_tma = (s == 1) && tma_ok(x, P);
     int rc = DK_OK;
-    if (a_tma) rc = make_map(&ta, dy, P, F, N, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    int64_t pa = P, pb = P;  // row pitches of the operands the maps describe
+    {
+        void *rest = reinterpret_cast<char *>(ws) + need;
+        size_t rest_bytes = ws_bytes - need;
+        if (!a_tma && repack_wanted(dy, P, 1, true)) {
+            if (float *gp = ws_carve(rest, rest_bytes, repack_bytes((int64_t)N * F, P))) {
+                rc = repack_launch(dy, gp, (int64_t)N * F, OH, OW, OW, 1, P, st);
+                if (rc) return rc;
+                dy = gp; pa = repack_pitch(P); a_tma = true;
+            }
+        }
+        if (a_tma && !b_tma && repack_wanted(x, P, s, true)) {
+            if (float *xp = ws_carve(rest, rest_bytes, repack_bytes((int64_t)N * C, P))) {
+                rc = repack_launch(x, xp, (int64_t)N * C, H, W, OW, s, P, st);
+                if (rc) return rc;
+                x = xp; pb = repack_pitch(P); b_tma = true;
+            }
+        }
+    }
+    if (a_tma) rc = make_map(&ta, dy, pa, F, N, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    if (b_tma) rc = make_map(&tb, x, P, C, N, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (b_tma) rc = make_map(&tb, x, pb, C, N, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const PixelGatherKM ga{dy, F, OH, OW, OW, (int)P, 1}, gb{x, C, H, W, OW, (int)P, s};
     if (a_tma && b_tma) rc = tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
@@ -894,20 +1002,18 @@ static int cv_dgrad(const float *dy, const float *w, float *dx, int N, const Con
 
 int tc_conv_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
                 int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
-    (void)ws; (void)ws_bytes;
     if (!g_tc_ready || (g_tc_disable_mask & 1)) return DK_ERR_UNSUPPORTED;
-    if (kh == 1 && kw == 1 && p == 0) return pw_fwd(x, w, bias, y, N, C, H, W, F, s, st);
+    if (kh == 1 && kw == 1 && p == 0) return pw_fwd(x, w, bias, y, N, C, H, W, F, s, ws, ws_bytes, st);
     if (g_tc_disable_mask & 8) return DK_ERR_UNSUPPORTED;
     return cv_fwd(x, w, bias, y, N, mk_geom(C, H, W, F, kh, kw, s, p), st);
 }
 
 int tc_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int s,
                   int p, int OH, int OW, void *ws, size_t ws_bytes, cudaStream_t st) {
-    (void)ws; (void)ws_bytes;
     if (!g_tc_ready || (g_tc_disable_mask & 2)) return DK_ERR_UNSUPPORTED;
     if (kh == 1 && kw == 1 && p == 0) {
         if (H != OH * s || W != OW * s) return DK_ERR_UNSUPPORTED;
-        return pw_dgrad(dy, w, dx, N, C, OH, OW, F, s, st);
+        return pw_dgrad(dy, w, dx, N, C, OH, OW, F, s, ws, ws_bytes, st);
     }
     if (g_tc_disable_mask & 8) return DK_ERR_UNSUPPORTED;
     return cv_dgrad(dy, w, dx, N, mk_geom(C, H, W, F, kh, kw, s, p), st);
@@ -996,6 +1102,7 @@ int dk_tc_debug_set(int key, int value) {
         case 5: dk::g_mn_swizzle = value; break;
         case 6: dk::g_l2_promo = value; break;  // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
         case 9: dk::g_bn_fused_enabled = value; break;  // 0: BatchNorm through the split kernels of batchnorm.cu only
+        case 10: dk::g_repack_mask = value; break;  // bit0: pad misaligned planes for TMA, bit1: repack small strided planes
         case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
         default: dk::set_error("dk_tc_debug_set: unknown key %d", key); return DK_ERR_INVALID;
     }
