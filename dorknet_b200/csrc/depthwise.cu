@@ -465,6 +465,9 @@ int dw_planes_fwd(const float *x, const float *w, const float *bias, float *y, i
 int dw_planes_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
                   float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, void *ws, size_t ws_bytes,
                   cudaStream_t st);
+int dw_chan_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
+                float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, cudaStream_t st);
+extern int g_dw_chan_enabled;
 static int g_dw_rows_enabled = 1;
 // 0: never, 1: where measured faster than the register-window kernels (dw_use_planes), 2: wherever it applies
 static int g_dw_planes_mode = 1;
@@ -554,6 +557,10 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
     if (rc) return rc;
     DK_REQUIRE(dy && x && w && dx && dw, "dk_dwconv_bwd: NULL pointer");
     DK_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "dk_dwconv_bwd: in_scale/in_shift must come together");
+    if (in_scale == nullptr) {
+        rc = dw_chan_bwd(dy, x, w, dx, dw, dbias, dx_add, l2, N, C, H, W, kh, kw, stride, pad, as_stream(stream));
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     if (in_scale == nullptr && dw_use_planes(true, H, W, stride)) {
         rc = dw_planes_bwd(dy, x, w, dx, dw, dbias, dx_add, l2, N, C, H, W, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream));
         if (rc != DK_ERR_UNSUPPORTED) return rc;
@@ -579,16 +586,23 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
 }
 
 /* test hook: 0 = always use the shared-memory tile kernels, 1 = default dispatch, 2 = planes-in-smem kernels wherever
-   they apply, 3 = register-window kernels without the planes kernels */
+   they apply, 3 = register-window kernels without the planes kernels (2 and 3 also switch the per-channel backward
+   kernel off), 4 = default dispatch without the per-channel backward kernel */
 int dk_dw_debug_set(int enable_rows) {
     if (enable_rows == 2 || enable_rows == 3) {
         g_dw_rows_enabled = 1;
         g_dw_planes_mode = enable_rows == 2 ? 2 : 0;
+        g_dw_chan_enabled = 0;
+    } else if (enable_rows == 4) {
+        g_dw_rows_enabled = 1;
+        g_dw_planes_mode = 1;
+        g_dw_chan_enabled = 0;
     } else if (enable_rows >= 20) g_dwr_bwd_vec_cap = enable_rows - 20;  // 21 / 22 / 24
     else if (enable_rows >= 10) g_dwr_bwd_rb = enable_rows - 10;  // 12 / 14: rows per iteration of the backward kernel
     else {
         g_dw_rows_enabled = enable_rows;
         g_dw_planes_mode = enable_rows ? 1 : 0;
+        g_dw_chan_enabled = enable_rows ? 1 : 0;
     }
     return DK_OK;
 }

@@ -353,7 +353,258 @@ dw_planes_reduce_kernel(const float *__restrict__ partial, const float *__restri
     }
 }
 
+
+// ============================================================================================== per-channel backward
+// dw_chan_bwd_kernel: stride 1.  A CTA owns ONE channel c and a range of images; it streams the (dY, X) planes of that
+// channel through a ring of shared-memory stages filled by cp.async.bulk (P images per stage, `nst` stages in flight:
+// the loads need no registers, so ~100 KB per CTA are on their way while the warps compute), and keeps the 9 dW sums
+// and db in registers across ALL its planes -- one block reduction at the very end instead of one per plane, and no
+// [N*C][10] partial buffer.  The R CTAs of a channel form a thread-block cluster; rank 0 adds their partials in rank
+// order through distributed shared memory (deterministic, no atomics, no second kernel).
+constexpr int DC_THREADS = 224;  // 7 warps: 14 bands x 14 strips of a 56x56 plane (and 4 x 7x7 of 28x28) fill them exactly once
+constexpr int DC_WARPS = DC_THREADS / 32;
+constexpr int DC_MAX_STAGES = 8;
+constexpr int DC_SMEM_2CTA = 100 * 1024;  // ring bytes that still let two CTAs share an SM
+constexpr int DC_SMEM_MAX = 200 * 1024;
+
+struct DcGeom {
+    int N, C, H, W;
+    int R;    // CTAs per channel (cluster size along y)
+    int per;  // images per CTA (multiple of P)
+    int P;    // images per stage
+    int nst;  // stages
+};
+
+__device__ __forceinline__ void dc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void dc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float dc_ld_dsmem(const float *local, unsigned rank) {
+    uint32_t ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+constexpr int DC_RB = 4;  // rows per band
+
+// r[0..VEC+1] = columns w0-1 .. w0+VEC of one row of a plane in shared memory.  `row` points at column w0 of the row, or
+// into a row of zeros kept behind the ring (rows outside the image, idle lanes), so the loads are unconditional.  The VEC
+// inner values are one vector load; the halo columns are the neighbouring lanes' edge values (lane l-1 holds the strip to
+// the left whenever sp > 0), except at the two ends of a warp, where that one lane reads shared memory (fl / fr), and at
+// the image border (neither shuffle nor load: zero).  Branch-free: the first version of this kernel spent more issue slots
+// on BSSY/BSYNC/ISETP and index divisions than on its FMAs (ncu: 29 M warp instructions, 9 M of them FFMA).
+template <int VEC>
+__device__ __forceinline__ void dc_load_row(const float *row, bool sl, bool sr, bool fl, bool fr, float (&r)[VEC + 2]) {
+    float q[VEC];
+    if (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(row);
+        q[0] = t.x; q[VEC > 1 ? 1 : 0] = t.y; q[VEC > 2 ? 2 : 0] = t.z; q[VEC > 3 ? 3 : 0] = t.w;
+    } else if (VEC == 2) {
+        const float2 t = *reinterpret_cast<const float2 *>(row);
+        q[0] = t.x; q[VEC > 1 ? 1 : 0] = t.y;
+    } else {
+        q[0] = row[0];
+    }
+    float lf = 0.0f, rt = 0.0f;
+    if (fl) lf = row[-1];
+    if (fr) rt = row[VEC];
+    const float left = __shfl_up_sync(0xffffffffu, q[VEC - 1], 1);
+    const float right = __shfl_down_sync(0xffffffffu, q[0], 1);
+    r[0] = sl ? left : lf;   // sl: the left neighbour's value is the halo; else lf (0 at the image border)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) r[1 + e] = q[e];
+    r[VEC + 1] = sr ? right : rt;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(DC_THREADS, 2)
+dw_chan_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ w,
+                   float *__restrict__ dx, const float *__restrict__ dx_add, float *__restrict__ dw,
+                   float *__restrict__ dbias, float l2, const DcGeom g) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t bars[DC_MAX_STAGES];
+    __shared__ float red[DC_WARPS][10];
+    __shared__ float xch[10];
+    const int c = blockIdx.x, rank = blockIdx.y;
+    const int H = g.H, W = g.W, HW = H * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = rank * g.per;
+    const int n1 = n0 + g.per < g.N ? n0 + g.per : g.N;
+    const int groups = n1 > n0 ? (n1 - n0 + g.P - 1) / g.P : 0;
+    const int stage_floats = 2 * g.P * HW;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.nst; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    // warp 0: fill stage (gi % nst) with the planes of images na .. na+cnt-1 (one bulk copy per plane and tensor)
+    auto issue = [&](int gi) {
+        const int slot = gi % g.nst;
+        const uint32_t bar = smem_u32(&bars[slot]);
+        const int na = n0 + gi * g.P;
+        const int cnt = n1 - na < g.P ? n1 - na : g.P;
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)(2 * cnt * HW) * 4u);
+        __syncwarp();
+        float *sg = sm + (size_t)slot * stage_floats, *sx = sg + (size_t)g.P * HW;
+        for (int j = lane; j < cnt; j += 32) {
+            const long long off = ((long long)(na + j) * g.C + c) * HW;
+            dp_bulk_g2s(smem_u32(sg + (size_t)j * HW), dy + off, (uint32_t)HW * 4u, bar);
+            dp_bulk_g2s(smem_u32(sx + (size_t)j * HW), x + off, (uint32_t)HW * 4u, bar);
+        }
+    };
+    if (warp == 0)
+        for (int gi = 0; gi < g.nst && gi < groups; ++gi) issue(gi);
+    float k[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+    float acc[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = 0.0f;
+    // An item is a band of DC_RB rows x a strip of VEC columns.  The thread walks down the band with a 3-row register
+    // window of dY and X, so every staged row is read from shared memory 1.5 times instead of 3, and the two halo
+    // columns come from the neighbouring lanes by shuffle (a strip-of-4 access pattern makes scalar shared-memory
+    // loads 4-way bank conflicted: they were the bottleneck of the first version of this kernel).
+    const int SP = W / VEC, NB = (H + DC_RB - 1) / DC_RB;
+    // a row of zeros behind the ring: what out-of-image rows and idle lanes read
+    float *zrow = sm + (size_t)g.nst * stage_floats + 4;
+    for (int i = threadIdx.x; i < W + 8; i += DC_THREADS) zrow[i - 4] = 0.0f;
+    __syncthreads();
+    // item t = (plane p, band, strip sp) for t = tid, and how it moves when t advances by the CTA size
+    int sp_0, band_0, p_0;
+    {
+        const int pb = (int)threadIdx.x / SP;
+        sp_0 = (int)threadIdx.x - pb * SP;
+        p_0 = pb / NB;
+        band_0 = pb - p_0 * NB;
+    }
+    const int d_sp = DC_THREADS % SP, d_pb = DC_THREADS / SP;
+    const int d_band = d_pb % NB, d_p = d_pb / NB;
+    for (int gi = 0; gi < groups; ++gi) {
+        const int slot = gi % g.nst;
+        mbar_wait(smem_u32(&bars[slot]), (uint32_t)(gi / g.nst) & 1u);
+        const int na = n0 + gi * g.P;
+        const int cnt = n1 - na < g.P ? n1 - na : g.P;
+        const float *sg = sm + (size_t)slot * stage_floats, *sx = sg + (size_t)g.P * HW;
+        const int items = cnt * NB * SP;
+        int sp = sp_0, band = band_0, p = p_0;
+        for (int base = 0; base < items; base += DC_THREADS) {  // CTA-uniform trip count: the shuffles need whole warps
+            const bool valid = p < cnt;
+            const int w0 = sp * VEC, h0 = band * DC_RB;
+            // halo sources: neighbour lane (sl/sr), own shared-memory read at a warp end (fl/fr), or the zero border
+            const bool sl = sp != 0 && lane != 0, sr = sp != SP - 1 && lane != 31;
+            const bool fl = sp != 0 && lane == 0, fr = sp != SP - 1 && lane == 31;
+            const int pv = valid ? p : 0;
+            const float *gr = sg + (size_t)pv * HW + (h0 - 1) * W + w0;  // row h0-1 of dY (never read when outside)
+            const float *xr = sx + (size_t)pv * HW + (h0 - 1) * W + w0;
+            const float *zr = zrow + w0;
+            float rg[3][VEC + 2], rx[3][VEC + 2];
+            {
+                const bool ok0 = valid && h0 > 0;  // row h0-1; row h0 exists whenever the item does
+                dc_load_row<VEC>(ok0 ? gr : zr, sl, sr, fl, fr, rg[0]);
+                dc_load_row<VEC>(ok0 ? xr : zr, sl, sr, fl, fr, rx[0]);
+                dc_load_row<VEC>(valid ? gr + W : zr, sl, sr, fl, fr, rg[1]);
+                dc_load_row<VEC>(valid ? xr + W : zr, sl, sr, fl, fr, rx[1]);
+            }
+            float *orow = dx + ((long long)(na + pv) * g.C + c) * HW + h0 * W + w0;
+            const float *arow = dx_add ? dx_add + ((long long)(na + pv) * g.C + c) * HW + h0 * W + w0 : nullptr;
+#pragma unroll
+            for (int rr = 0; rr < DC_RB; ++rr) {
+                const int h = h0 + rr;
+                const bool okn = valid && h + 1 < H;
+                dc_load_row<VEC>(okn ? gr + (rr + 2) * W : zr, sl, sr, fl, fr, rg[2]);
+                dc_load_row<VEC>(okn ? xr + (rr + 2) * W : zr, sl, sr, fl, fr, rx[2]);
+                float o[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    // dX[h][w] = sum_{a,b} dY[h+a-1][w+b-1] * k[2-a][2-b]
+                    float sacc = 0.0f;
+#pragma unroll
+                    for (int a2 = 0; a2 < 3; ++a2)
+#pragma unroll
+                        for (int b2 = 0; b2 < 3; ++b2) sacc = fmaf(rg[a2][v + b2], k[(2 - a2) * 3 + (2 - b2)], sacc);
+                    o[v] = sacc;
+                    const float gv = rg[1][v + 1];  // zero outside the image / for idle lanes
+                    acc[9] += gv;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) acc[i * 3 + j] = fmaf(gv, rx[i][v + j], acc[i * 3 + j]);
+                }
+                if (valid && h < H) {
+                    if (arow) {
+                        if (VEC == 4) {
+                            const float4 q = ld_stream4(arow + rr * W);
+                            o[0] += q.x; o[VEC > 1 ? 1 : 0] += q.y; o[VEC > 2 ? 2 : 0] += q.z; o[VEC > 3 ? 3 : 0] += q.w;
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) o[v] += __ldg(arow + rr * W + v);
+                        }
+                    }
+                    if (VEC == 2) *reinterpret_cast<float2 *>(orow + rr * W) = make_float2(o[0], o[VEC > 1 ? 1 : 0]);
+                    else dp_store<VEC>(orow + rr * W, o);
+                }
+#pragma unroll
+                for (int e = 0; e < VEC + 2; ++e) {
+                    rg[0][e] = rg[1][e]; rg[1][e] = rg[2][e];
+                    rx[0][e] = rx[1][e]; rx[1][e] = rx[2][e];
+                }
+            }
+            // next item of this thread: t += DC_THREADS
+            sp += d_sp;
+            int carry = 0;
+            if (sp >= SP) { sp -= SP; carry = 1; }
+            band += d_band + carry;
+            carry = 0;
+            if (band >= NB) { band -= NB; carry = 1; }
+            p += d_p + carry;
+        }
+        __syncthreads();  // everybody is done with this stage: refill it
+        if (warp == 0 && gi + g.nst < groups) issue(gi + g.nst);
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) red[warp][i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        float t = 0.0f;
+#pragma unroll
+        for (int q = 0; q < DC_WARPS; ++q) t += red[q][threadIdx.x];
+        xch[threadIdx.x] = t;
+    }
+    if (g.R > 1) {
+        __syncthreads();
+        dc_cluster_arrive();
+        dc_cluster_wait();
+    } else {
+        __syncthreads();
+    }
+    if (rank == 0 && threadIdx.x < 10) {
+        const int i = threadIdx.x;
+        float t = xch[i];
+        for (int q = 1; q < g.R; ++q) t += dc_ld_dsmem(xch + i, (unsigned)q);  // rank order
+        if (i < 9) dw[c * 9 + i] = t + (l2 != 0.0f ? l2 * __ldg(w + c * 9 + i) : 0.0f);
+        else if (dbias) dbias[c] = t;
+    }
+    if (g.R > 1) {
+        // nobody leaves while rank 0 may still read its shared memory
+        dc_cluster_arrive();
+        dc_cluster_wait();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- host
+static bool g_dc_ready = false;
+int g_dw_chan_enabled = 1;
+
+template <int VEC>
+static int dc_set_attrs() {
+    DK_CUDA(cudaFuncSetAttribute(dw_chan_bwd_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_MAX));
+    return DK_OK;
+}
+
 int g_dw_planes_enabled = 1;
 static bool g_dp_ready = false;
 
@@ -371,6 +622,10 @@ int init_dw_planes() {
     if ((rc = dp_set_attrs<2, 4>())) return rc;
     if ((rc = dp_set_attrs<2, 1>())) return rc;
     g_dp_ready = true;
+    if ((rc = dc_set_attrs<4>())) return rc;
+    if ((rc = dc_set_attrs<2>())) return rc;
+    if ((rc = dc_set_attrs<1>())) return rc;
+    g_dc_ready = true;
     return DK_OK;
 }
 
@@ -394,6 +649,62 @@ static bool dp_plan(DpGeom &g, int N, int C, int H, int W, int kh, int kw, int s
     g.bulk = al16 && ((long long)G * HW) % 4 == 0 && ((long long)G * OHW) % 4 == 0 && (g.planes * HW) % 4 == 0 &&
              (g.planes * OHW) % 4 == 0;
     return true;
+}
+
+
+// ---- per-channel backward: plan + launch
+
+static bool dc_plan(DcGeom &g, int N, int C, int H, int W, size_t *smem) {
+    const long long HW = (long long)H * W;
+    const long long pair = 2 * HW * 4;  // bytes of one image's (dY, X) planes
+    if (HW % 4 != 0 || 2 * pair > DC_SMEM_MAX || C > 65535) return false;
+    int P = 1;
+    const int SP = W / (W % 4 == 0 ? 4 : W % 2 == 0 ? 2 : 1);
+    while (P < 16 && P < N && (long long)(2 * P) * pair <= 32 * 1024 && (long long)P * ceil_div(H, DC_RB) * SP < DC_THREADS) P *= 2;
+    const long long stage = P * pair;
+    const long long budget = 2 * stage <= DC_SMEM_2CTA ? DC_SMEM_2CTA : DC_SMEM_MAX;
+    int nst = (int)(budget / stage);
+    if (nst > DC_MAX_STAGES) nst = DC_MAX_STAGES;
+    if (nst < 2) return false;
+    const int ctas_target = sm_count() * (budget == DC_SMEM_2CTA ? 2 : 1);
+    int R = ctas_target / C;
+    if (R < 1) R = 1;
+    if (R > 8) R = 8;
+    const int groups_total = (int)ceil_div(N, P);
+    if (R > groups_total) R = groups_total;
+    int per = (int)ceil_div(groups_total, R) * P;
+    R = (int)ceil_div(N, per);
+    const int groups = per / P;
+    if (nst > groups) nst = groups < 2 ? 2 : groups;
+    g.N = N; g.C = C; g.H = H; g.W = W; g.R = R; g.per = per; g.P = P; g.nst = nst;
+    *smem = (size_t)nst * stage + (size_t)(W + 8) * 4;
+    return true;
+}
+
+int dw_chan_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
+                float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, cudaStream_t st) {
+    if (!g_dc_ready || !g_dw_chan_enabled || kh != 3 || kw != 3 || s != 1 || p != 1) return DK_ERR_UNSUPPORTED;
+    if (!(aligned16(dy) && aligned16(x) && aligned16(dx) && (dx_add == nullptr || aligned16(dx_add)))) return DK_ERR_UNSUPPORTED;
+    DcGeom g;
+    size_t smem = 0;
+    if (!dc_plan(g, N, C, H, W, &smem)) return DK_ERR_UNSUPPORTED;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C, (unsigned)g.R, 1);
+    cfg.blockDim = dim3(DC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)g.R;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (W % 4 == 0) DK_CUDA(cudaLaunchKernelEx(&cfg, dw_chan_bwd_kernel<4>, dy, x, w, dx, dx_add, dw, dbias, l2, g));
+    else if (W % 2 == 0) DK_CUDA(cudaLaunchKernelEx(&cfg, dw_chan_bwd_kernel<2>, dy, x, w, dx, dx_add, dw, dbias, l2, g));
+    else DK_CUDA(cudaLaunchKernelEx(&cfg, dw_chan_bwd_kernel<1>, dy, x, w, dx, dx_add, dw, dbias, l2, g));
+    count_launch();
+    return DK_OK;
 }
 
 size_t dw_planes_ws_bytes(int N, int C) { return (size_t)N * C * 10 * sizeof(float); }

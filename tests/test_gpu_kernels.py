@@ -30,11 +30,14 @@ DW_CASES = [
     (3, 24, 14, 14, 3, 2, 1, False),  # stride 2, scalar items, several planes per CTA
     (5, 40, 7, 7, 3, 2, 1, True),     # stride 2, odd plane (7 -> 4), ragged last group
     (2, 5, 13, 9, 3, 2, 1, False),    # stride 2, odd non-square
+    (70, 4, 14, 14, 3, 1, 1, True),   # per-channel backward: several stages of 16 images, ragged last stage, cluster of 5
+    (19, 3, 28, 28, 3, 1, 1, False),  # per-channel backward: cluster of 5 ranks, ragged image ranges
+    (9, 2, 56, 56, 3, 1, 1, True),    # per-channel backward: more stage items than ring slots
     (2, 6, 15, 15, 5, 1, 2, True),    # 5x5: generic tile kernel
 ]
 
 
-@pytest.mark.parametrize("rows", [1, 0, 2, 3])  # default dispatch, tiles, planes-in-smem, register windows
+@pytest.mark.parametrize("rows", [1, 0, 2, 3, 4])  # default dispatch (per-channel backward), tiles, planes-in-smem, register windows, default without per-channel
 @pytest.mark.parametrize("case", DW_CASES)
 def test_depthwise_vs_oracle(O, case, rows):
     from dorknet_b200 import api
