@@ -70,6 +70,57 @@ __device__ __forceinline__ void bn_finalize_channel(const BnFinalize &fin, int c
     }
 }
 
+// The same finalise with the channel's parameters already in registers: the loads are issued when the kernel starts and
+// have landed long before the statistics are ready, instead of sitting on the critical path between the two passes.
+struct BnChannelParams {
+    float gamma, beta, rmean, rstd;
+};
+__device__ __forceinline__ BnChannelParams bn_load_channel_params(const BnFinalize &fin, int c) {
+    BnChannelParams p = {1.0f, 0.0f, 0.0f, 0.0f};
+    if (fin.mode != 0) {
+        p.gamma = fin.gamma[c];
+        p.beta = fin.beta[c];
+        if (fin.running_mean && !fin.first_batch) {
+            p.rmean = fin.running_mean[c];
+            p.rstd = fin.running_std[c];
+        }
+    }
+    return p;
+}
+__device__ __forceinline__ void bn_finalize_channel(const BnFinalize &fin, const BnChannelParams &p, int c, float mean, float var,
+                                                    bool write, float *scale_out, float *shift_out) {
+    if (fin.mode == 0) {
+        if (write) {
+            fin.mean_out[c] = mean;
+            fin.var_out[c] = var;
+        }
+        *scale_out = 1.0f;
+        *shift_out = 0.0f;
+        return;
+    }
+    const float std = sqrtf(var + fin.eps);  // batch_norm.py:69
+    const float invstd = 1.0f / std;
+    const float scale = p.gamma * invstd;
+    const float shift = p.beta - mean * scale;
+    *scale_out = scale;
+    *shift_out = shift;
+    if (!write) return;
+    fin.save_mean[c] = mean;
+    fin.save_invstd[c] = invstd;
+    fin.save_scale[c] = scale;
+    fin.save_shift[c] = shift;
+    if (fin.running_mean) {  // batch_norm.py:76-89 (tracks std, not var)
+        if (fin.first_batch) {
+            fin.running_mean[c] = mean;
+            fin.running_std[c] = std;
+        } else {
+            const float mo = fin.momentum;
+            fin.running_mean[c] = mo * p.rmean + (1.0f - mo) * mean;
+            fin.running_std[c] = mo * p.rstd + (1.0f - mo) * std;
+        }
+    }
+}
+
 // bn_fused.cu: return DK_ERR_UNSUPPORTED (no error text) when the channel slices do not fit shared memory
 int bn_fused_init();
 int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st);
