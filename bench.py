@@ -465,8 +465,8 @@ def run_ours(a, spec):
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(dominant)
         if tr:
             traffic = tr["traffic_over_algorithmic"] * ds[2] / ds[0]
-            traffic_src = ("profiles/r01_traffic.json: ncu --set full dram bytes / algorithmic bytes = %.3f on the two "
-                           "largest launches of this family, applied to the mean algorithmic bytes per launch"
+            traffic_src = ("profiles/r01_traffic.json: ncu --set full dram bytes / algorithmic bytes = %.3f, byte-weighted "
+                           "over the launches of this family in one step, applied to the mean algorithmic bytes per launch"
                            % tr["traffic_over_algorithmic"])
     except Exception:  # noqa: BLE001
         pass

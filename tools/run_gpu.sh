@@ -1,7 +1,5 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --maxfail=8 > gpurun_out/t22.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t22.log
-grep -E "^(FAILED|ERROR)|passed|failed|rc=|Error|assert" gpurun_out/t22.log | head -20
-timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --per-kernel gpurun_out/perkernel_r1ad.json > gpurun_out/bench_r1ad.json 2> gpurun_out/bench_r1ad.err
-cut -c1-300 gpurun_out/bench_r1ad.json; tail -3 gpurun_out/bench_r1ad.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bn_fused_bwd|bn_bwd_" -s 60 -c 12 -f -o gpurun_out/prof_bnbwd_r1af python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-graph > gpurun_out/ncu_bnbwd_r1af.log 2>&1
+tail -2 gpurun_out/ncu_bnbwd_r1af.log
