@@ -108,7 +108,10 @@ class ClockSampler:
 
     def _pump(self):
         n = self.nvml
-        calls = os.environ.get("BENCH_CLOCK_CALLS", "clock,power,reasons").split(",")
+        # no power query by default: nvmlDeviceGetPowerUsage stalls NCCL's launches on a multi-GPU box (2 x B200,
+        # measured: 4.99 ms/step with it, 4.37 with clock + reasons only, 4.26 without the sampler; with the default
+        # 50 ms period it once cost a factor of two)
+        calls = os.environ.get("BENCH_CLOCK_CALLS", "clock,reasons").split(",")
         while not self._stop.is_set():
             try:
                 sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM) if "clock" in calls else 0
