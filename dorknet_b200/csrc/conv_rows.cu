@@ -43,7 +43,8 @@ struct ConvRowsParams {
     int bn;          // forward: MMA N (F rounded up to 32)
     int iwt;         // staged input columns per tile
     int phw, irow;   // staged rows are split by column phase (col % s): phw columns per phase, irow = s*phw floats per row
-    int in_floats;   // C*kh*irow rounded up to 4
+    int in_floats;   // C*kh*irow rounded up to 4 (span staging: C*slot + over-read slack)
+    int slot;        // span staging: floats per channel slot (4 front pad + kh*W + alignment slop)
     int in_stages;   // staged input tiles in flight + 1 (the global-load latency is spread over in_stages-1 tiles)
     int tiles_per_row, num_tiles;
     uint32_t tmem_cols, acc_stride;
@@ -86,9 +87,121 @@ __device__ __forceinline__ void cr_fill_ktab(const ConvRowsParams &p, int *ktab)
     }
 }
 
+
+// ---- span staging (fast path) ---------------------------------------------------------------------------------------
+// When an output row spans the whole image width, the kh input rows a tile needs are ONE contiguous span per channel
+// (kh*W floats).  A single lane per channel pulls it in with cp.async.bulk (16-byte aligned superset of the span: `mis`
+// = first wanted float's index mod 4) -- no per-element address arithmetic, no registers, completion on an mbarrier.
+// The expansion then gives every thread 4 consecutive output pixels: it reads its 3*S+KW input columns with aligned
+// 16-byte shared loads, realigns them in registers (the misalignment is warp-uniform) and writes each filter tap of
+// the 4 pixels as ONE 16-byte store into the swizzled operand tile (4 consecutive pixels are contiguous in both the
+// MN-major A of the forward and the K-major B of the wgrad).  Per (c, i) row and warp: NL loads + KW stores instead of
+// 4*KW loads + 4*KW stores with their index arithmetic.
+__device__ __forceinline__ void cr_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// one warp: rows ih0 .. ih0+kh-1 (clipped to the image) of every channel of image n -> stage slots
+__device__ __forceinline__ void cr_span_issue(const ConvRowsParams &p, uint32_t dst_stage, uint32_t bar, int n, int ih0, int lane) {
+    const int lo = ih0 > 0 ? ih0 : 0;
+    int hi = ih0 + p.kh - 1;
+    if (hi > p.H - 1) hi = p.H - 1;
+    uint32_t bytes = 0;
+    const float *src = p.x;
+    if (lane < p.C && hi >= lo) {
+        const long long g0 = (((long long)n * p.C + lane) * p.H + lo) * p.W;
+        const long long g1 = g0 + (long long)(hi - lo + 1) * p.W;
+        const long long al = g0 & ~3ll;
+        bytes = (uint32_t)(((g1 - al) + 3ll) & ~3ll) * 4u;
+        src = p.x + al;
+    }
+    uint32_t total = bytes;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) mbar_expect_tx(bar, total);
+    __syncwarp();
+    if (bytes) cr_bulk_g2s(dst_stage + (uint32_t)(lane * p.slot + 4) * 4u, src, bytes, bar);
+}
+
+// expand row (c, i) of a staged tile: taps k = kbase .. kbase+KW-1 of pixels 4*lane .. 4*lane+3
+template <int S, int KW, bool WGRAD>
+__device__ __forceinline__ void cr_expand_row(const float *stage, int row_off, bool rok, int W, int pad, int kbase, int lane,
+                                              uint32_t tile_base, uint32_t chunk_bytes) {
+    constexpr int WIN = 3 * S + KW;
+    constexpr int NL = (WIN + 3 + 3) / 4;
+    float w[WIN];
+    if (rok) {
+        const int a = row_off + S * 4 * lane;
+        const int R = a & 3;  // warp-uniform: S*4*lane is a multiple of 4
+        const float4 *src = reinterpret_cast<const float4 *>(stage + (a - R));
+        float r[NL * 4];
+#pragma unroll
+        for (int u = 0; u < NL; ++u) {
+            const float4 v = src[u];
+            r[4 * u] = v.x; r[4 * u + 1] = v.y; r[4 * u + 2] = v.z; r[4 * u + 3] = v.w;
+        }
+        if (R == 0) {
+#pragma unroll
+            for (int t = 0; t < WIN; ++t) w[t] = r[t];
+        } else if (R == 1) {
+#pragma unroll
+            for (int t = 0; t < WIN; ++t) w[t] = r[t + 1];
+        } else if (R == 2) {
+#pragma unroll
+            for (int t = 0; t < WIN; ++t) w[t] = r[t + 2];
+        } else {
+#pragma unroll
+            for (int t = 0; t < WIN; ++t) w[t] = r[t + 3];
+        }
+        // zero padding columns: window element t is input column S*4*lane - pad + t
+        const int lo_bad = pad - S * 4 * lane, hi_ok = W + pad - S * 4 * lane;
+        if (lo_bad > 0 || hi_ok < WIN) {
+#pragma unroll
+            for (int t = 0; t < WIN; ++t)
+                if (t < lo_bad || t >= hi_ok) w[t] = 0.0f;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < WIN; ++t) w[t] = 0.0f;
+    }
+    const uint32_t l = (uint32_t)lane;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        const uint32_t k = (uint32_t)(kbase + j);
+        uint32_t dst;
+        if (WGRAD) dst = tile_base + (l >> 3) * chunk_bytes + k * 128u + (((l & 7u) ^ (k & 7u)) << 4);  // km_tile_off(k, 4*lane % 32)
+        else dst = tile_base + (k >> 5) * 16384u + (l >> 3) * 4096u + (k & 31u) * 128u + ((((l & 7u) >> 1) ^ (k & 3u)) << 5) +
+                   ((l & 1u) << 4);  // mn_tile_off(4*lane, k)
+        st_shared_v4(dst, w[j], w[S + j], w[2 * S + j], w[3 * S + j]);
+    }
+}
+
+// all loader warps: expand staged tile (n, oh) into an operand tile
+template <int S, int KW, bool WGRAD>
+__device__ __forceinline__ void cr_expand_tile(const ConvRowsParams &p, const float *stage, int n, int ih0, int lw, int lane,
+                                               uint32_t tile_base, uint32_t chunk_bytes) {
+    if (4 * lane >= p.OW) return;
+    const int lo = ih0 > 0 ? ih0 : 0;
+    const int rows = p.C * p.kh;
+    for (int r = lw; r < rows; r += CR_LOADER_WARPS) {
+        const int c = r / p.kh, i = r - c * p.kh;
+        const int ih = ih0 + i;
+        const bool rok = ih >= 0 && ih < p.H;
+        const int mis = (int)(((((long long)n * p.C + c) * p.H + lo) * p.W) & 3ll);
+        const int row_off = c * p.slot + 4 + mis + (ih - lo) * p.W - p.p;
+        cr_expand_row<S, KW, WGRAD>(stage, row_off, rok, p.W, p.p, r * KW, lane, tile_base, chunk_bytes);
+    }
+}
+
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
+// S = 0: generic staging (4-byte cp.async, any geometry); S > 0: span staging for stride S, KW filter columns
+template <int S, int KW>
 __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const ConvRowsParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -103,9 +216,10 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
     auto t_full = [&](int a) { return bar + 8u * (4 + a); };
     auto t_empty = [&](int a) { return bar + 8u * (6 + a); };
     const uint32_t tmem_slot = bar + 64u;
+    auto in_full = [&](int st) { return bar + 80u + 8u * st; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ int ktab[128];
-    cr_fill_ktab(p, ktab);
+    if (S == 0) cr_fill_ktab(p, ktab);
 
     if (threadIdx.x == 0) {
         for (int a = 0; a < 2; ++a) {
@@ -114,6 +228,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
             mbar_init(t_full(a), 1);
             mbar_init(t_empty(a), 4);
         }
+        for (int st = 0; st < p.in_stages; ++st) mbar_init(in_full(st), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -179,6 +294,38 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
         };
         int n, oh, ow0;
         const int D = p.in_stages - 1;  // prefetch distance in tiles
+        if constexpr (S > 0) {
+            // span staging: tiles_per_row == 1, so tile = (n, oh)
+            if (lw == 0) {
+                for (int d = 0; d < D; ++d) {
+                    const long long t = (long long)blockIdx.x + (long long)d * gridDim.x;
+                    if (t < p.num_tiles) {
+                        tile_coords((int)t, n, oh, ow0);
+                        cr_span_issue(p, sIn + (uint32_t)d * in_bytes, in_full(d), n, oh * p.s - p.p, lane);
+                    }
+                }
+            }
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int stg = it % p.in_stages;
+                mbar_wait(in_full(stg), (uint32_t)(it / p.in_stages) & 1u);
+                cr_loader_barrier();  // every loader is done expanding tile it-1, whose buffer is refilled now
+                const long long next = (long long)tile + (long long)D * gridDim.x;
+                if (lw == 0 && next < p.num_tiles) {
+                    const int sn = (it + D) % p.in_stages;
+                    tile_coords((int)next, n, oh, ow0);
+                    cr_span_issue(p, sIn + (uint32_t)sn * in_bytes, in_full(sn), n, oh * p.s - p.p, lane);
+                }
+                const int a = it & 1;
+                mbar_wait(a_empty(a), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tile_coords(tile, n, oh, ow0);
+                cr_expand_tile<S, KW, false>(p, in_f + (size_t)stg * p.in_floats, n, oh * p.s - p.p, lw, lane,
+                                             sA + (uint32_t)a * a_bytes, 0u);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full(a));
+            }
+        } else {
         for (int d = 0; d < D; ++d) {
             const long long t = (long long)blockIdx.x + (long long)d * gridDim.x;
             if (t < p.num_tiles) {
@@ -218,6 +365,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
             if (lane == 0) mbar_arrive(a_full(a));
         }
         cp_async_wait_pending(0);
+        }
     } else if (warp >= 2) {
         // ================================ epilogue ====================================
         const int q = warp & 3;
@@ -267,6 +415,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
 // =====================================================================================================================
 // wgrad
 // =====================================================================================================================
+template <int S, int KW>
 __global__ void __launch_bounds__(CR_THREADS, 1)
 conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -285,9 +434,10 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
     auto b_empty = [&](int a) { return bar + 8u * (2 * CR_MAX_A_STAGES + 2 + a); };
     const uint32_t t_full = bar + 8u * (2 * CR_MAX_A_STAGES + 4);
     const uint32_t tmem_slot = t_full + 8u;
+    auto in_full = [&](int st) { return t_full + 16u + 8u * st; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ int ktab[128];
-    cr_fill_ktab(p, ktab);
+    if (S == 0) cr_fill_ktab(p, ktab);
 
     // this CTA's contiguous range of (n, oh) rows
     const int r_beg = (int)(((long long)p.rows_total * blockIdx.x) / gridDim.x);
@@ -304,6 +454,7 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
             mbar_init(b_empty(a), 1);
         }
         mbar_init(t_full, 1);
+        for (int st = 0; st < p.in_stages; ++st) mbar_init(in_full(st), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -368,6 +519,35 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
         const int lw = warp - 6;
         const float *in_f = reinterpret_cast<const float *>(gbase + (sIn - base));
         const int D = p.in_stages - 1;
+        if constexpr (S > 0) {
+            if (lw == 0) {
+                for (int d = 0; d < D; ++d) {
+                    if (r_beg + d < r_end) {
+                        const int n = (r_beg + d) / p.OH, oh = (r_beg + d) - n * p.OH;
+                        cr_span_issue(p, sIn + (uint32_t)d * in_bytes, in_full(d), n, oh * p.s - p.p, lane);
+                    }
+                }
+            }
+            int it = 0;
+            for (int r = r_beg; r < r_end; ++r, ++it) {
+                const int stg = it % p.in_stages;
+                mbar_wait(in_full(stg), (uint32_t)(it / p.in_stages) & 1u);
+                cr_loader_barrier();
+                if (lw == 0 && r + D < r_end) {
+                    const int sn = (it + D) % p.in_stages;
+                    const int n = (r + D) / p.OH, oh = (r + D) - n * p.OH;
+                    cr_span_issue(p, sIn + (uint32_t)sn * in_bytes, in_full(sn), n, oh * p.s - p.p, lane);
+                }
+                const int sb = it & 1;
+                mbar_wait(b_empty(sb), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                const int n = r / p.OH, oh = r - n * p.OH;
+                cr_expand_tile<S, KW, true>(p, in_f + (size_t)stg * p.in_floats, n, oh * p.s - p.p, lw, lane,
+                                            sB + (uint32_t)sb * b_bytes, b_chunk);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_full(sb));
+            }
+        } else {
         for (int d = 0; d < D; ++d) {
             if (r_beg + d < r_end) {
                 const int n = (r_beg + d) / p.OH, oh = (r_beg + d) - n * p.OH;
@@ -404,6 +584,7 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
             if (lane == 0) mbar_arrive(b_full(sb));
         }
         cp_async_wait_pending(0);
+        }
     } else if (warp >= 2) {
         // ================================ epilogue: partial dW of this CTA ============
         const int q = warp & 3;
@@ -434,7 +615,7 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn3 g_encode3 = nullptr;
 static bool g_cr_ready = false;
-int g_conv_rows_enabled = 1;
+int g_conv_rows_enabled = 1;  // 0: off; 1: span staging where the geometry allows; 2: generic staging only
 
 int init_conv_rows() {
     void *fn = nullptr;
@@ -445,13 +626,35 @@ int init_conv_rows() {
         return DK_OK;
     }
     g_encode3 = reinterpret_cast<EncodeTiledFn3>(fn);
-    DK_CUDA(cudaFuncSetAttribute(conv_rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_MAX));
-    DK_CUDA(cudaFuncSetAttribute(conv_rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_MAX));
+#define CR_SET_ATTR(S, KW)                                                                                                       \
+    DK_CUDA(cudaFuncSetAttribute(conv_rows_fwd_kernel<S, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_MAX));       \
+    DK_CUDA(cudaFuncSetAttribute(conv_rows_wgrad_kernel<S, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_MAX));
+    CR_SET_ATTR(0, 0) CR_SET_ATTR(1, 3) CR_SET_ATTR(1, 5) CR_SET_ATTR(2, 3) CR_SET_ATTR(2, 5)
+#undef CR_SET_ATTR
     g_cr_ready = true;
     return DK_OK;
 }
 
 static int cr_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// span staging (cr_span_issue / cr_expand_tile): one output row per tile, bulk-copyable input, instantiated (stride, kw)
+static bool cr_span_ok(const ConvRowsParams &q) {
+    const bool inst = (q.s == 1 || q.s == 2) && (q.kw == 3 || q.kw == 5);
+    return g_conv_rows_enabled == 1 && inst && q.OW <= 128 && q.p <= 4 && q.C <= 32 && aligned16(q.x) &&
+           ((long long)q.N * q.C * q.H * q.W) % 4 == 0;
+}
+static void cr_span_layout(ConvRowsParams &q) {
+    q.slot = 4 + cr_round_up(q.kh * q.W + 3, 4) + 4;
+    q.in_floats = q.C * q.slot + 128 * q.s + 64;  // + what pixels past OW over-read (never used)
+}
+#define CR_DISPATCH(KERNEL, q, ...)                                                \
+    do {                                                                           \
+        if (!span) KERNEL<0, 0> __VA_ARGS__;                                       \
+        else if (q.s == 1 && q.kw == 3) KERNEL<1, 3> __VA_ARGS__;                  \
+        else if (q.s == 1 && q.kw == 5) KERNEL<1, 5> __VA_ARGS__;                  \
+        else if (q.s == 2 && q.kw == 3) KERNEL<2, 3> __VA_ARGS__;                  \
+        else KERNEL<2, 5> __VA_ARGS__;                                             \
+    } while (0)
 static uint32_t cr_tmem_cols(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
 
 static bool cr_common(ConvRowsParams &q, int N, int C, int H, int W, int F, int kh, int kw, int s, int p) {
@@ -465,8 +668,8 @@ static bool cr_common(ConvRowsParams &q, int N, int C, int H, int W, int F, int 
 int conv_rows_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
                   int kw, int s, int p, cudaStream_t st) {
     ConvRowsParams q = {};
-    if (!cr_common(q, N, C, H, W, F, kh, kw, s, p) || F > 256) return DK_ERR_UNSUPPORTED;
     q.x = x; q.w = w; q.bias = bias; q.out = y;
+    if (!cr_common(q, N, C, H, W, F, kh, kw, s, p) || F > 256) return DK_ERR_UNSUPPORTED;
     q.KP = cr_round_up(q.Kf, 8);
     q.KC = (q.KP + 31) / 32;
     q.bn = cr_round_up(F, 32);
@@ -474,6 +677,8 @@ int conv_rows_fwd(const float *x, const float *w, const float *bias, float *y, i
     q.phw = (q.iwt + s - 1) / s;
     q.irow = s * q.phw;
     q.in_floats = cr_round_up(C * kh * q.irow, 4);
+    const bool span = cr_span_ok(q);
+    if (span) cr_span_layout(q);
     q.tiles_per_row = (q.OW + 127) / 128;
     const long long tiles = (long long)N * q.OH * q.tiles_per_row;
     if (tiles >= (1ll << 31)) return DK_ERR_UNSUPPORTED;
@@ -486,12 +691,12 @@ int conv_rows_fwd(const float *x, const float *w, const float *bias, float *y, i
     const size_t smem = fixed + (size_t)q.in_stages * q.in_floats * 4;
     if (smem > (size_t)CR_SMEM_MAX) return DK_ERR_UNSUPPORTED;
     const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
-    conv_rows_fwd_kernel<<<grid, CR_THREADS, smem, st>>>(q);
+    CR_DISPATCH(conv_rows_fwd_kernel, q, <<<grid, CR_THREADS, smem, st>>>(q));
     DK_LAUNCH_CHECK();
     return DK_OK;
 }
 
-static int cr_wgrad_plan(ConvRowsParams &q, size_t *smem, int *grid) {
+static int cr_wgrad_plan(ConvRowsParams &q, size_t *smem, int *grid, bool *span_out) {
     if (q.F > 128 || q.OW > 128 || (q.OW % 4) != 0) return DK_ERR_UNSUPPORTED;
     q.KP = cr_round_up(q.Kf, 16);
     q.PC = (q.OW + 31) / 32;
@@ -500,6 +705,8 @@ static int cr_wgrad_plan(ConvRowsParams &q, size_t *smem, int *grid) {
     q.phw = (q.iwt + q.s - 1) / q.s;
     q.irow = q.s * q.phw;
     q.in_floats = cr_round_up(q.C * q.kh * q.irow, 4);
+    *span_out = cr_span_ok(q);
+    if (*span_out) cr_span_layout(q);
     q.rows_total = q.N * q.OH;
     q.tmem_cols = cr_tmem_cols(q.KP);
     const size_t a_bytes = (size_t)q.PC * q.BMR * 128, b_bytes = (size_t)q.PC * q.KP * 128;
@@ -527,10 +734,12 @@ size_t conv_rows_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int
 int conv_rows_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
                     int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
     ConvRowsParams q = {};
+    q.x = x;
     if (!cr_common(q, N, C, H, W, F, kh, kw, s, p) || !aligned16(dy)) return DK_ERR_UNSUPPORTED;
     size_t smem;
     int grid;
-    if (cr_wgrad_plan(q, &smem, &grid) != DK_OK) return DK_ERR_UNSUPPORTED;
+    bool span;
+    if (cr_wgrad_plan(q, &smem, &grid, &span) != DK_OK) return DK_ERR_UNSUPPORTED;
     const size_t need = (size_t)grid * F * q.Kf * sizeof(float);
     if (ws == nullptr || ws_bytes < need) return DK_ERR_UNSUPPORTED;
     q.x = x; q.w = w; q.bias = nullptr; q.out = reinterpret_cast<float *>(ws);
@@ -549,7 +758,7 @@ int conv_rows_wgrad(const float *dy, const float *x, const float *w, float *dw, 
             return DK_ERR_CUDA;
         }
     }
-    conv_rows_wgrad_kernel<<<grid, CR_THREADS, smem, st>>>(tm, q);
+    CR_DISPATCH(conv_rows_wgrad_kernel, q, <<<grid, CR_THREADS, smem, st>>>(tm, q));
     DK_LAUNCH_CHECK();
     splitk_reduce_launch(q.out, w, dw, l2, (int64_t)F * q.Kf, grid, st);
     DK_LAUNCH_CHECK();

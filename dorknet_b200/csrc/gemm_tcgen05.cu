@@ -56,6 +56,7 @@ struct TcParams {
     const float *epi_w;  // epi 1: optional "+ epi_l2 * epi_w[m*N + n]" (weight decay folded into a dense wgrad)
     float epi_l2;
     uint32_t tmem_cols, acc_stride;
+    uint32_t a_tx;   // bytes one stage's A tile receives from TMA (a K-major A with fewer than 128 rows loads only those)
     // MN-major shared-memory descriptor fields (bytes) -- runtime so a bring-up probe can sweep them
     uint32_t mn_layout, mn_lbo, mn_sbo, mn_kstep;
 };
@@ -309,7 +310,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
                     const uint32_t fb = full_bar(s);
-                    mbar_expect_tx(fb, (AG::kGather ? 0u : (uint32_t)TC_A_BYTES) + (BG::kGather ? 0u : b_bytes));
+                    mbar_expect_tx(fb, (AG::kGather ? 0u : p.a_tx) + (BG::kGather ? 0u : b_bytes));
                     int kb = it, bb = b;
                     if (p.mode == 1) {
                         const int kk = item0 + it;
@@ -686,6 +687,7 @@ static void fill_common(TcParams &p) {
     int st = TC_SMEM_BUDGET / stage_bytes;
     if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
     p.stages = st;
+    p.a_tx = TC_A_BYTES;
     p.mn_layout = (uint32_t)g_mn_layout;
     p.mn_lbo = (uint32_t)g_mn_lbo;
     p.mn_sbo = (uint32_t)g_mn_sbo;
@@ -729,6 +731,7 @@ static void split_plan(int M, int N, int64_t total_items, int64_t in_bytes, int 
     *splits = (int)ceil_div(total_items, *per);
 }
 
+static int g_short_a = 0;  // 1: wgrad TMA box of the dY operand covers only its F < 128 real rows (measured: no gain, 31.0 us either way at 64x64x56x56)
 static int g_repack_mask = 3;  // bit0: misaligned stride-1 planes, bit1: stride-s planes of <= TC_REPACK_MAX_P pixels
 constexpr int64_t TC_REPACK_MAX_P = 1024;
 static int64_t repack_pitch(int64_t P) { return (P + 3) / 4 * 4; }
@@ -918,7 +921,13 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
             }
         }
     }
-    if (a_tma) rc = make_map(&ta, dy, pa, F, N, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    // F < 128: the box stops at the real rows (the rest of the 128-row MMA operand is stale shared memory whose
+    // accumulator rows the epilogue never reads) -- half the TMA row requests per stage at F = 64
+    const int a_rows = (g_short_a && F < TC_BM) ? round_up(F, 8) : TC_BM;
+    if (a_tma) {
+        rc = make_map(&ta, dy, pa, F, N, TC_BK, a_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+        q.a_tx = (uint32_t)a_rows * TC_BK * 4;
+    }
     if (rc) return rc;
     if (b_tma) rc = make_map(&tb, x, pb, C, N, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -975,8 +984,10 @@ static int cv_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     const ConvPatchKM gb{x, g};
     int rc;
     if (tma_ok(dy, P)) {
-        rc = make_map(&ta, dy, P, g.F, N, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        const int a_rows = (g_short_a && g.F < TC_BM) ? round_up(g.F, 8) : TC_BM;
+        rc = make_map(&ta, dy, P, g.F, N, TC_BK, a_rows, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
+        q.a_tx = (uint32_t)a_rows * TC_BK * 4;
         rc = tc_launch(ta, tb, q, NoGather{}, gb, st);
     } else {
         rc = tc_launch(ta, tb, q, PixelGatherKM{dy, g.F, g.OH, g.OW, g.OW, (int)P, 1}, gb, st);
@@ -1102,6 +1113,7 @@ int dk_tc_debug_set(int key, int value) {
         case 5: dk::g_mn_swizzle = value; break;
         case 6: dk::g_l2_promo = value; break;  // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
         case 9: dk::g_bn_fused_enabled = value; break;  // 0: BatchNorm through the split kernels of batchnorm.cu only
+        case 11: dk::g_short_a = value; break;  // 0: wgrad dY boxes always 128 rows
         case 10: dk::g_repack_mask = value; break;  // bit0: pad misaligned planes for TMA, bit1: repack small strided planes
         case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
         default: dk::set_error("dk_tc_debug_set: unknown key %d", key); return DK_ERR_INVALID;

@@ -130,11 +130,30 @@ CONV_CASES = [
     # small-K row-staged kernels (conv_rows.cu): conv0 at full width (OW = 112: partial last pixel chunk), several
     # tiles per output row, MobileNet conv0, many rows per CTA
     (2, 3, 225, 225, 64, 5, 2, 1), (1, 3, 40, 300, 16, 3, 1, 1), (3, 3, 224, 224, 32, 3, 2, 1), (40, 3, 33, 33, 24, 5, 2, 1),
+    # span staging (bulk-copied row spans + 16-byte expansion stores; needs N*C*H*W % 4 == 0): conv0 itself, padding 2 and 0,
+    # stride 1 with 5 columns, clipped top / bottom rows, OW not a multiple of 4 (forward only takes it)
+    (4, 3, 225, 225, 64, 5, 2, 1), (4, 3, 224, 224, 16, 5, 2, 2), (4, 2, 30, 30, 8, 5, 1, 2), (4, 3, 19, 19, 8, 3, 1, 0),
+    (8, 3, 31, 31, 40, 3, 2, 1),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_tcgen05_vs_oracle(O, case):
+    _conv_case(O, case)
+
+
+@pytest.mark.parametrize("case", [(4, 3, 225, 225, 64, 5, 2, 1), (2, 1, 28, 28, 32, 3, 1, 1)])
+def test_conv_rows_generic_staging_vs_oracle(O, case):
+    """the same small-K kernels with span staging switched off (4-byte cp.async staging of any geometry)"""
+    from dorknet_b200 import api
+    api.dk_tc_debug_set(8, 2)
+    try:
+        _conv_case(O, case)
+    finally:
+        api.dk_tc_debug_set(8, 1)
+
+
+def _conv_case(O, case):
     from dorknet_b200.layers.convolution import ConvLayer
     N, C, H, W, F, k, s, p = case
     rng = np.random.default_rng(hash(case) & 0xffff)
