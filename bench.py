@@ -74,16 +74,23 @@ def build_net(M, spec, seed=0):
 
 # ------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled DURING the timed region, through NVML in a thread of this process
-    (an `nvidia-smi -lms` child polling a multi-GPU box stalls NCCL traffic, so it is only the fallback)."""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML -- as few queries as possible, because a
+    query is not free here (measured on B200, 40 steps of 3.95 ms): one NVML call blocks its caller for ~13 ms, so four
+    calls made from the timing loop itself starve the GPU (5.29 ms/step); a thread polling every 50 ms costs nothing on
+    one GPU (3.953 vs 3.953) but 0.1-1.4 ms/step on two (the query stalls NCCL's launches); an `nvidia-smi -lms` child
+    is worse still.  Default mode "trigger": a helper thread takes ONE sample when the timing loop signals that half of
+    the steps are enqueued (the loop itself never waits), and the loop takes a second one after the last step is
+    enqueued, while the GPU is still working through its queue.  BENCH_CLOCK_MODE=thread is the old 50 ms poller."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.05, mode="trigger"):
         self.index = index
         self.period = period
+        self.mode = mode
         self.samples = []
         self._stop = threading.Event()
+        self._go = threading.Event()
         self.thread = None
         self.nvml = None
 
@@ -103,10 +110,26 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.nvml = None
             return
-        self.thread = threading.Thread(target=self._pump, daemon=True)
-        self.thread.start()
+        if self.mode == "thread":
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        elif self.mode == "trigger":
+            self.thread = threading.Thread(target=self._one_shot, daemon=True)
+            self.thread.start()
 
-    def _pump(self):
+    def trigger(self):
+        self._go.set()
+
+    def _one_shot(self):
+        self._go.wait()
+        if not self._stop.is_set():
+            self._pump(once=True)
+
+    def sample(self):
+        if self.nvml is not None:
+            self._pump(once=True)
+
+    def _pump(self, once=False):
         n = self.nvml
         # no power query by default: nvmlDeviceGetPowerUsage stalls NCCL's launches on a multi-GPU box (2 x B200,
         # measured: 4.99 ms/step with it, 4.37 with clock + reasons only, 4.26 without the sampler; with the default
@@ -125,13 +148,17 @@ class ClockSampler:
                 self.samples.append((time.time(), sm, pw, rs))
             except Exception:  # noqa: BLE001
                 pass
+            if once:
+                return
             self._stop.wait(self.period)
 
     def stop(self, t0, t1):
         if self.nvml is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
         self._stop.set()
-        self.thread.join(timeout=2)
+        self._go.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
         rows = [r for r in self.samples if t0 - 0.02 <= r[0] <= t1 + 0.02] or self.samples
         sm = sorted(r[1] for r in rows)
         reasons = set()
@@ -353,11 +380,11 @@ def run_ours(a, spec):
     M = W.ours()
     net, opt = build_net(M, spec, seed=0)
     net.to_gpu()
-    # eager mode: bucketed all-reduce overlapped with backward; graph mode: one all-reduce of the flat gradient
-    # buffer between the forward+backward graph and the optimiser graph
+    # bucketed all-reduce issued from inside backward (overlapped with the rest of it); in graph mode the NCCL
+    # launches are captured into the step's graph (GraphedTrainStep), with a between-graphs fallback
     dp = None
     if world > 1:
-        dp = DataParallel(net, opt, num_buckets=3 if a.no_graph else 1, overlap=bool(a.no_graph))
+        dp = DataParallel(net, opt, num_buckets=int(os.environ.get("DK_DP_BUCKETS", "3")), overlap=True)
     if dp is not None:
         dp.broadcast_parameters(0)
     B = spec["batch"]
@@ -422,8 +449,10 @@ def run_ours(a, spec):
             json.dump({"by_family": fmt(table), "by_call_shape": fmt(by_shape)}, f, indent=1)
 
     # ---- timed region: K steps, inputs resident in HBM (one CUDA-graph replay per step) -----------------------
-    clocks = ClockSampler(torch.cuda.current_device(), period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.05"))) if (
+    clocks = ClockSampler(torch.cuda.current_device(), period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.05")),
+                          mode=os.environ.get("BENCH_CLOCK_MODE", "trigger")) if (
         rank == 0 and os.environ.get("BENCH_NO_CLOCKS") != "1") else None
+    trigger_at = a.steps // 2 if (clocks and clocks.mode == "trigger") else -1
     barrier()
     if clocks:
         clocks.start()
@@ -434,9 +463,14 @@ def run_ours(a, spec):
     dbg_sync = os.environ.get("BENCH_SYNC_EVERY") == "1"  # diagnostics only
     for i in range(a.steps):
         loss = train_step(*ring[i % nring][2:])
+        if i == trigger_at:
+            clocks.trigger()  # half of the steps are enqueued: the helper thread samples now, this loop does not wait
         if dbg_sync:
             torch.cuda.current_stream().synchronize()
     e1.record()
+    if trigger_at >= 0:
+        clocks.sample()  # everything is enqueued, the GPU is still inside the last steps
+        tail_under_load = not e1.query()
     barrier()
     t_wall1 = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -444,6 +478,8 @@ def run_ours(a, spec):
     value = world * B * a.steps / (ms_total / 1e3)
     launches = launches_per_step * a.steps  # kernels inside the replayed graphs (counted on an eager step)
     clock_info = clocks.stop(t_wall0, t_wall1) if clocks else None
+    if clock_info is not None and trigger_at >= 0:
+        clock_info["mode"] = "one NVML sample mid-region (helper thread) + one after the last enqueue (GPU still busy: %s)" % tail_under_load
     # the dominant kernel family, bracketed with CUDA events on the launching stream: the same step, same buffers,
     # launched eagerly right after the timed region (events cannot sit inside a replayed graph)
     dom = CallTimer(torch, BYTES_FN)
@@ -530,6 +566,9 @@ def run_ours(a, spec):
         "config": {"workload": "%s, %s, batch %d per GPU, %s%s" % (spec["name"], spec["note"], B, spec["opt"],
                                                                  ", mixup" if a.mixup else ""),
                    "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "allreduce": ("none" if dp is None else ("nccl, %d buckets captured inside the step's CUDA graph, overlapped with backward"
+                                                            % len(dp.buckets) if graphed.dp_in_graph else
+                                                            "nccl, issued from backward hooks" if a.no_graph else "nccl, between two graphs")),
                    "l2_flush": "none needed: per-step working set (activations) >> 126 MB L2; inputs rotate over %d batches" % nring},
         "roofline": roofline, "network_roofline": net_roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clock_info, "final_loss": final_loss,

@@ -127,6 +127,13 @@ int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int 
 int bn_fused_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
                  const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
                  cudaStream_t st);
-extern int g_bn_fused_enabled;
+extern int g_bn_fused_enabled;  // 0: split kernels only; 1: group kernels (small planes) and cluster kernels; 2: cluster kernels only
+
+// bn_group.cu: channel-group kernels for small planes (same contract: DK_ERR_UNSUPPORTED when the shape does not fit)
+int bn_group_init();
+int bn_group_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st);
+int bn_group_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
+                 const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
+                 cudaStream_t st);
 
 }  // namespace dk

@@ -396,7 +396,7 @@ int bn_fused_init() {
     cudaGetLastError();
     if (const char *e = getenv("DK_BN_MAX_CLUSTER")) g_bf_max_cluster = atoi(e) >= 16 ? 16 : atoi(e) >= 8 ? 8 : atoi(e) >= 4 ? 4 : atoi(e) >= 2 ? 2 : 1;
     g_bf_ready = true;
-    return DK_OK;
+    return bn_group_init();
 }
 
 // cluster size and slice length: enough CTAs to fill the machine twice, slices of at most BF_SMEM_TARGET bytes when a
@@ -437,6 +437,10 @@ static int bf_launch(void (*kernel)(Exp...), const BfGeom &g, size_t smem, cudaS
 }
 
 int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st) {
+    {
+        const int rc = bn_group_fwd(x, y, fin, relu, N, C, HW, st);
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     const bool bulk = (HW % 4 == 0) && aligned16(x) && (y == nullptr || aligned16(y));
     BfGeom g;
     if (!bf_plan(N, C, HW, 1, bulk, &g)) return DK_ERR_UNSUPPORTED;
@@ -448,6 +452,10 @@ int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int 
 int bn_fused_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
                  const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
                  cudaStream_t st) {
+    {
+        const int rc = bn_group_bwd(dy, x, save_mean, save_invstd, save_scale, save_shift, dx, dgamma, dbeta, relu, N, C, HW, st);
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     const bool bulk = (HW % 4 == 0) && aligned16(x) && aligned16(dy) && aligned16(dx);
     BfGeom g;
     if (!bf_plan(N, C, HW, 2, bulk, &g)) return DK_ERR_UNSUPPORTED;

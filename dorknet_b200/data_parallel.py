@@ -78,6 +78,7 @@ class DataParallel:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap
         self._pending = []
+        self.hooks_enabled = True  # GraphedTrainStep switches the backward hooks off for its between-graphs fallback
         self.device = device  # None: the process's B200; tests pass torch.device("cpu") with the gloo backend
         # parameter layers in REVERSE execution order = the order backward produces gradients
         layers = list(iter_param_layers(network, include_skip=True))
@@ -130,12 +131,15 @@ class DataParallel:
 
             def wrapped(*a, _orig=orig, _bs=bs, **kw):
                 out = _orig(*a, **kw)
-                for b in _bs:
-                    self._launch(b)
+                if self.hooks_enabled:
+                    for b in _bs:
+                        self._launch(b)
                 return out
             layer.backward = wrapped
 
     def _launch(self, b):
+        if os.environ.get("DK_DP_SKIP_ALLREDUCE") == "1":  # (diagnostics knob)
+            return
         work = self.dist.all_reduce(self.flat[b["lo"]:b["hi"]], op=self.dist.ReduceOp.SUM, group=self.group,
                                     async_op=True)
         self._pending.append(work)
@@ -144,11 +148,14 @@ class DataParallel:
         """Call after network.backward(): (issue and) wait for every bucket on the compute stream."""
         if self.world <= 1 or os.environ.get("DK_DP_SKIP_ALLREDUCE") == "1":  # (diagnostics knob)
             return
-        if not self.overlap:
+        if not self.overlap or not self.hooks_enabled:
             for b in self.buckets:
                 self._launch(b)
         for w in self._pending:
             w.wait()  # makes the current (compute) stream wait; the host does not block
+        self._pending = []
+
+    def drop_pending(self):
         self._pending = []
 
     def step(self):

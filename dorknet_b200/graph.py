@@ -17,15 +17,22 @@ class GraphedTrainStep:
     X / Y must be DeviceArrays that stay alive (static input buffers, e.g. the slots of a HostBatchUploader):
     one graph is captured per distinct (X, Y) buffer pair and replayed whenever that pair comes back.  Host
     arrays are accepted too: they are uploaded into an internal static pair first.  `warmup` eager steps run
-    before the first capture (they are real training steps).  With a DataParallel wrapper the gradient all-reduce
-    runs between two graphs (forward+backward | optimiser)."""
+    before the first capture (they are real training steps).  With a DataParallel wrapper the bucketed NCCL
+    all-reduces are captured INSIDE the graph (issued from the wrapped layer.backward on NCCL's stream, forked
+    from and joined back into the capture stream, so they overlap the rest of backward and a step stays ONE
+    host launch); `dp_in_graph=False` (or DK_DP_IN_GRAPH=0, or a failed capture) falls back to one all-reduce
+    between two graphs (forward+backward | optimiser)."""
 
-    def __init__(self, network, optimiser, data_parallel=None, warmup=1, enabled=True):
+    def __init__(self, network, optimiser, data_parallel=None, warmup=1, enabled=True, dp_in_graph=None):
+        import os
         self.net = network
         self.opt = optimiser
         self.dp = data_parallel
         self.warmup = warmup
         self.enabled = enabled
+        if dp_in_graph is None:
+            dp_in_graph = os.environ.get("DK_DP_IN_GRAPH", "1") != "0"
+        self.dp_in_graph = bool(dp_in_graph) and data_parallel is not None
         self._graphs = {}
         self._seen = 0
         self._static = None
@@ -61,25 +68,50 @@ class GraphedTrainStep:
         if entry is None:
             self.opt.push_hyper()
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                loss, _ = self.net.forward(X, Y)
-                self.net.backward()
-                if self.dp is None:
-                    self.opt.update_weights()
-            entry = (g, loss, X, Y)
+            entry = None
+            if self.dp_in_graph:
+                try:
+                    entry = self._capture_whole(X, Y)
+                except Exception as e:  # NCCL would not be captured on this stack: keep training, between graphs
+                    import sys
+                    sys.stderr.write("dorknet_b200: all-reduce inside the CUDA graph failed (%s); falling back\n" % e)
+                    self.dp_in_graph = False
+                    self.dp.drop_pending()
+                    torch.cuda.synchronize()
+            if entry is None:
+                if self.dp is not None:
+                    self.dp.hooks_enabled = False  # fallback: one all-reduce after the graph, not from the hooks
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    loss, _ = self.net.forward(X, Y)
+                    self.net.backward()
+                    if self.dp is None:
+                        self.opt.update_weights()
+                entry = (g, loss, X, Y)
+                if self.dp is not None and self._opt_graph is None:
+                    og = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(og):
+                        self.opt.update_weights()
+                    self._opt_graph = og
             self._graphs[key] = entry
-            if self.dp is not None and self._opt_graph is None:
-                og = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(og):
-                    self.opt.update_weights()
-                self._opt_graph = og
         self.opt.push_hyper()
         entry[0].replay()
-        if self.dp is not None:
+        if self.dp is not None and not self.dp_in_graph:
             self.dp.finish()
             self._opt_graph.replay()
         return entry[1]
+
+    def _capture_whole(self, X, Y):
+        """forward + backward (+ bucketed all-reduces on NCCL's stream) + optimiser in ONE graph"""
+        import torch
+        g = torch.cuda.CUDAGraph()
+        self.dp.hooks_enabled = True
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            loss, _ = self.net.forward(X, Y)
+            self.net.backward()
+            self.dp.finish()  # joins NCCL's stream back into the capture stream
+            self.opt.update_weights()
+        return (g, loss, X, Y)
 
     @property
     def num_graphs(self):

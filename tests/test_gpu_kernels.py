@@ -243,15 +243,17 @@ BN_CASES = [
     (3, 5, 9, 11),      # odd everything, tails
     (2, 3, 300, 300),   # slices too large for shared memory in backward: split kernels
     (5, 16, 1, 1),      # one value per (n, c)
+    # channel-group kernels (bn_group.cu; fused=1): 4 channels of 7x7 / one of 14x14 per CTA, all images resident
+    (64, 512, 7, 7), (64, 256, 14, 14), (3, 300, 6, 6), (5, 296, 5, 6), (32, 512, 1, 1), (70, 592, 3, 3),
 ]
 
 
-@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("fused", [1, 2, 0])
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("case", BN_CASES)
 def test_batchnorm_vs_oracle(O, case, relu, fused):
-    """BatchNorm forward / backward (with and without the fused ReLU) against the oracle, through the cluster kernels
-    (fused=1) and through the split statistics / apply / reduce / dx kernels (fused=0)."""
+    """BatchNorm forward / backward (with and without the fused ReLU) against the oracle, through the channel-group / cluster
+    kernels (fused=1), the cluster kernels alone (fused=2) and through the split statistics / apply / reduce / dx kernels (fused=0)."""
     from dorknet_b200 import api
     from dorknet_b200.layers.batch_norm import BatchNormLayer
     from dorknet_b200.layers.activations import ReLu
