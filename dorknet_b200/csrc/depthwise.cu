@@ -468,6 +468,13 @@ int dw_planes_bwd(const float *dy, const float *x, const float *w, float *dx, fl
 int dw_chan_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
                 float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, cudaStream_t st);
 extern int g_dw_chan_enabled;
+// depthwise_group.cu: channel-group kernels for 7x7 / 14x14 planes (3x3, stride 1, pad 1)
+int init_dw_group();
+int dw_group_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int kh, int kw,
+                 int s, int p, cudaStream_t st);
+int dw_group_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
+                 float l2, int N, int C, int H, int W, int kh, int kw, int s, int p, cudaStream_t st);
+extern int g_dw_group_enabled;
 static int g_dw_rows_enabled = 1;
 // 0: never, 1: where measured faster than the register-window kernels (dw_use_planes), 2: wherever it applies
 static int g_dw_planes_mode = 1;
@@ -475,6 +482,8 @@ extern int g_dwr_bwd_rb, g_dwr_bwd_vec_cap;
 
 int init_depthwise() {
     // budgets are within the 48 KB default for forward; backward may slightly exceed with the filter stash
+    int rc = init_dw_group();
+    if (rc) return rc;
     return init_dw_planes();
 }
 
@@ -535,6 +544,10 @@ int dk_dwconv_fwd(const float *x, const float *w, const float *bias, float *y, c
     DK_REQUIRE(x && w && y, "dk_dwconv_fwd: NULL pointer");
     DK_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "dk_dwconv_fwd: in_scale/in_shift must come together");
     cudaStream_t st = as_stream(stream);
+    if (in_scale == nullptr) {
+        rc = dw_group_fwd(x, w, bias, y, N, C, H, W, kh, kw, stride, pad, st);
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     if (in_scale == nullptr && dw_use_planes(false, H, W, stride)) {
         rc = dw_planes_fwd(x, w, bias, y, N, C, H, W, kh, kw, stride, pad, st);
         if (rc != DK_ERR_UNSUPPORTED) return rc;
@@ -558,6 +571,8 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
     DK_REQUIRE(dy && x && w && dx && dw, "dk_dwconv_bwd: NULL pointer");
     DK_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "dk_dwconv_bwd: in_scale/in_shift must come together");
     if (in_scale == nullptr) {
+        rc = dw_group_bwd(dy, x, w, dx, dw, dbias, dx_add, l2, N, C, H, W, kh, kw, stride, pad, as_stream(stream));
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
         rc = dw_chan_bwd(dy, x, w, dx, dw, dbias, dx_add, l2, N, C, H, W, kh, kw, stride, pad, as_stream(stream));
         if (rc != DK_ERR_UNSUPPORTED) return rc;
     }
@@ -587,8 +602,10 @@ int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, fl
 
 /* test hook: 0 = always use the shared-memory tile kernels, 1 = default dispatch, 2 = planes-in-smem kernels wherever
    they apply, 3 = register-window kernels without the planes kernels (2 and 3 also switch the per-channel backward
-   kernel off), 4 = default dispatch without the per-channel backward kernel */
+   kernel off), 4 = default dispatch without the per-channel backward kernel, 5 = default dispatch without the channel-group kernels
+   of depthwise_group.cu (only mode 1 uses them) */
 int dk_dw_debug_set(int enable_rows) {
+    if (enable_rows < 10) g_dw_group_enabled = enable_rows == 1 ? 1 : 0;  // 5 = default dispatch without the channel-group kernels
     if (enable_rows == 2 || enable_rows == 3) {
         g_dw_rows_enabled = 1;
         g_dw_planes_mode = enable_rows == 2 ? 2 : 0;

@@ -34,10 +34,12 @@ DW_CASES = [
     (19, 3, 28, 28, 3, 1, 1, False),  # per-channel backward: cluster of 5 ranks, ragged image ranges
     (9, 2, 56, 56, 3, 1, 1, True),    # per-channel backward: more stage items than ring slots
     (2, 6, 15, 15, 5, 1, 2, True),    # 5x5: generic tile kernel
+    # channel-group kernels (depthwise_group.cu; rows=1): 4 channels of 7x7 / one of 14x14 per CTA, all images resident
+    (64, 512, 7, 7, 3, 1, 1, False), (5, 296, 7, 7, 3, 1, 1, True), (64, 256, 14, 14, 3, 1, 1, True), (3, 80, 14, 14, 3, 1, 1, False),
 ]
 
 
-@pytest.mark.parametrize("rows", [1, 0, 2, 3, 4])  # default dispatch (per-channel backward), tiles, planes-in-smem, register windows, default without per-channel
+@pytest.mark.parametrize("rows", [1, 0, 2, 3, 4, 5])  # default dispatch (channel-group / per-channel kernels), tiles, planes-in-smem, register windows, default without per-channel, default without channel-group
 @pytest.mark.parametrize("case", DW_CASES)
 def test_depthwise_vs_oracle(O, case, rows):
     from dorknet_b200 import api
