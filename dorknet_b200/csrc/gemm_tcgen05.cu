@@ -606,6 +606,9 @@ static bool g_tc_ready = false;
 static int g_mn_layout = LAYOUT_SW128_BASE32B, g_mn_lbo = 4096, g_mn_sbo = 512, g_mn_kstep = 1024;
 static int g_mn_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 static int g_l2_promo = (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+static int g_smem_budget = TC_SMEM_BUDGET;  // bytes of operand stages per CTA
+static int g_two_per_sm = 1;                 // see tc_launch
+static int g_ctas_per_sm = 1;                // persistent CTAs per SM the grids / split plans are sized for
 static int g_tc_disable_mask = 0;  // bit0 fwd, bit1 dgrad, bit2 wgrad (bring-up / tests)
 
 int init_gemm_tcgen05() {
@@ -684,7 +687,7 @@ static void fill_common(TcParams &p) {
     p.acc_stride = p.bn <= 32 ? 32 : p.bn <= 64 ? 64 : p.bn <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
     const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 4;
-    int st = TC_SMEM_BUDGET / stage_bytes;
+    int st = g_smem_budget / stage_bytes;
     if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
     p.stages = st;
     p.a_tx = TC_A_BYTES;
@@ -694,9 +697,13 @@ static void fill_common(TcParams &p) {
     p.mn_kstep = (uint32_t)g_mn_kstep;
 }
 
+// two_per_sm: forward / dgrad GEMMs with at least two tiles per SM run TWO persistent CTAs per SM on half the stage budget
+// each (the epilogue of one overlaps the loads of the other, and 448 tiles no longer cost 4 rounds of 148): measured at
+// batch 64, 28x28x128 fwd 15.2 -> 12.4 us, dgrad 15.6 -> 12.9 us, 56x56x64 19.9 -> 17.6 us; wgrad and the gather variants
+// lose (more split-K partials / loader warps competing), so they keep one CTA per SM
 template <class AG, class BG>
-static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParams &p, const AG &ag, const BG &bg,
-                     cudaStream_t st) {
+static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, TcParams p, const AG &ag, const BG &bg,
+                     cudaStream_t st, bool two_per_sm = false) {
     static bool attr_set = false;
     if (!attr_set) {
         DK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<AG, BG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -704,8 +711,17 @@ static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParam
         attr_set = true;
     }
     const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 4;
+    int per_sm = g_ctas_per_sm;
+    if (two_per_sm && g_two_per_sm && per_sm == 1 && p.num_tiles >= 2 * sm_count() && p.tmem_cols <= 256) {
+        const int st2 = (98 * 1024) / stage_bytes;
+        if (st2 >= 3) {
+            per_sm = 2;
+            if (p.stages > st2) p.stages = st2;
+        }
+    }
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * TC_MAX_STAGES + 8);
-    const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+    const int cap = sm_count() * per_sm;
+    const int grid = p.num_tiles < cap ? p.num_tiles : cap;
     const int threads = (AG::kGather || BG::kGather) ? TC_GATHER_THREADS : TC_THREADS;
     tc_gemm_kernel<AG, BG><<<grid, threads, smem, st>>>(ta, tb, p, ag, bg);
     DK_LAUNCH_CHECK();
@@ -717,7 +733,7 @@ static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, const TcParam
 static void split_plan(int M, int N, int64_t total_items, int64_t in_bytes, int *splits, int *per) {
     const int bn = N >= 256 ? 256 : round_up(N, 32);
     const int tiles = (int)(ceil_div(M, TC_BM) * ceil_div(N, bn));
-    int64_t s = sm_count() / tiles;
+    int64_t s = (int64_t)sm_count() * g_ctas_per_sm / tiles;
     const int64_t out_bytes = (int64_t)M * N * 4;
     // partial sums are written once and read once: keep them under ~1/4 of the input bytes, but never refuse the
     // first 32 MB of them (tiny layers would otherwise run on a handful of SMs)
@@ -836,7 +852,7 @@ static int pw_fwd(const float *x, const float *w, const float *bias, float *y, i
     if (s == 1 && tma_ok(x, P)) {
         rc = make_map(&ta, x, P, C, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
         if (rc) return rc;
-        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st, true);
     }
     if (repack_wanted(x, P, s, false)) {
         if (float *xp = ws_carve(ws, ws_bytes, repack_bytes((int64_t)N * C, P))) {
@@ -867,7 +883,7 @@ static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     if (tma_ok(dy, P)) {
         rc = make_map(&ta, dy, P, F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
         if (rc) return rc;
-        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st, s == 1);
     }
     if (repack_wanted(dy, P, 1, false)) {
         if (float *gp = ws_carve(ws, ws_bytes, repack_bytes((int64_t)N * F, P))) {
@@ -1113,6 +1129,12 @@ int dk_tc_debug_set(int key, int value) {
         case 5: dk::g_mn_swizzle = value; break;
         case 6: dk::g_l2_promo = value; break;  // CUtensorMapL2promotion: 0 none, 1 64B, 2 128B, 3 256B
         case 9: dk::g_bn_fused_enabled = value; break;  // 0: BatchNorm through the split kernels of batchnorm.cu only
+        case 12: dk::g_smem_budget = value * 1024; break;  // operand stage bytes per CTA (KB)
+        case 13:  // persistent CTAs per SM (2: the stage budget is halved so that two CTAs fit)
+            dk::g_ctas_per_sm = value;
+            dk::g_smem_budget = value >= 2 ? 98 * 1024 : dk::TC_SMEM_BUDGET;
+            break;
+        case 14: dk::g_two_per_sm = value; break;  // 0: forward / dgrad GEMMs never run two CTAs per SM
         case 11: dk::g_short_a = value; break;  // 0: wgrad dY boxes always 128 rows
         case 10: dk::g_repack_mask = value; break;  // bit0: pad misaligned planes for TMA, bit1: repack small strided planes
         case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
