@@ -34,6 +34,7 @@ PROTOS = {
     "dk_bn_ws_bytes": (Z, [I]),
     "dk_bn_stats": (I, [P, P, P, I, I, I, P, Z, P]),
     "dk_bn_fwd_train": (I, [P, P, P, P, P, P, I, F, F, P, P, P, P, I, I, I, I, P, Z, P]),
+    "dk_bn_fwd_train_add": (I, [P, P, P, P, P, P, P, I, F, F, P, P, P, P, I, I, I, I, P, Z, P]),
     "dk_bn_fwd_infer": (I, [P, P, P, P, P, P, I, I, I, I, P]),
     "dk_bn_apply": (I, [P, P, P, P, I, I, I, I, P]),
     "dk_bn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P, Z, P]),

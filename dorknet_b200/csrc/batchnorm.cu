@@ -422,10 +422,10 @@ int dk_bn_stats(const float *x, float *mean, float *var, int N, int C, int HW, v
     return launch_stats(x, N, C, HW, ws, fin, as_stream(stream));
 }
 
-int dk_bn_fwd_train(const float *x, float *y, const float *gamma, const float *beta, float *running_mean,
-                    float *running_std, int first_batch, float momentum, float eps, float *save_mean,
-                    float *save_invstd, float *save_scale, float *save_shift, int fuse_relu, int N, int C, int HW,
-                    void *ws, size_t ws_bytes, dk_stream_t stream) {
+static int bn_fwd_train_impl(const float *x, const float *add, float *y, const float *gamma, const float *beta,
+                             float *running_mean, float *running_std, int first_batch, float momentum, float eps,
+                             float *save_mean, float *save_invstd, float *save_scale, float *save_shift, int fuse_relu, int N,
+                             int C, int HW, void *ws, size_t ws_bytes, dk_stream_t stream) {
     int rc = bn_check("dk_bn_fwd_train", N, C, HW, ws, ws_bytes);
     if (rc) return rc;
     DK_REQUIRE(x && gamma && beta && save_mean && save_invstd && save_scale && save_shift,
@@ -445,12 +445,34 @@ int dk_bn_fwd_train(const float *x, float *y, const float *gamma, const float *b
     fin.save_scale = save_scale;
     fin.save_shift = save_shift;
     if (y != nullptr) {  // statistics + normalisation in one cluster kernel when the channel slices fit shared memory
-        rc = bn_fused_fwd(x, y, fin, fuse_relu, N, C, HW, as_stream(stream));
+        rc = bn_fused_fwd(x, y, fin, fuse_relu, N, C, HW, as_stream(stream), add);
         if (rc != DK_ERR_UNSUPPORTED) return rc;
     }
     rc = launch_stats(x, N, C, HW, ws, fin, as_stream(stream));
     if (rc || y == nullptr) return rc;
-    return launch_apply(x, y, save_scale, save_shift, fuse_relu, N, C, HW, as_stream(stream));
+    if (add == nullptr) return launch_apply(x, y, save_scale, save_shift, fuse_relu, N, C, HW, as_stream(stream));
+    // residual join on the split path: plain apply, then y = relu(y + add) in place (never the case in the networks here)
+    rc = launch_apply(x, y, save_scale, save_shift, 0, N, C, HW, as_stream(stream));
+    if (rc) return rc;
+    if (fuse_relu) return dk_add_relu_fwd(y, add, y, (int64_t)N * C * HW, stream);
+    return dk_add(y, add, y, (int64_t)N * C * HW, stream);
+}
+
+int dk_bn_fwd_train(const float *x, float *y, const float *gamma, const float *beta, float *running_mean,
+                    float *running_std, int first_batch, float momentum, float eps, float *save_mean,
+                    float *save_invstd, float *save_scale, float *save_shift, int fuse_relu, int N, int C, int HW,
+                    void *ws, size_t ws_bytes, dk_stream_t stream) {
+    return bn_fwd_train_impl(x, nullptr, y, gamma, beta, running_mean, running_std, first_batch, momentum, eps, save_mean,
+                             save_invstd, save_scale, save_shift, fuse_relu, N, C, HW, ws, ws_bytes, stream);
+}
+
+int dk_bn_fwd_train_add(const float *x, const float *add, float *y, const float *gamma, const float *beta,
+                        float *running_mean, float *running_std, int first_batch, float momentum, float eps,
+                        float *save_mean, float *save_invstd, float *save_scale, float *save_shift, int fuse_relu, int N,
+                        int C, int HW, void *ws, size_t ws_bytes, dk_stream_t stream) {
+    DK_REQUIRE(add != nullptr && y != nullptr, "dk_bn_fwd_train_add: NULL pointer");
+    return bn_fwd_train_impl(x, add, y, gamma, beta, running_mean, running_std, first_batch, momentum, eps, save_mean,
+                             save_invstd, save_scale, save_shift, fuse_relu, N, C, HW, ws, ws_bytes, stream);
 }
 
 int dk_bn_apply(const float *x, float *y, const float *scale, const float *shift, int fuse_relu, int N, int C,

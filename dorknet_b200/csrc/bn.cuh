@@ -123,7 +123,9 @@ __device__ __forceinline__ void bn_finalize_channel(const BnFinalize &fin, const
 
 // bn_fused.cu: return DK_ERR_UNSUPPORTED (no error text) when the channel slices do not fit shared memory
 int bn_fused_init();
-int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st);
+// add != nullptr: y = relu?(x*scale + shift + add) -- the residual join folded into the normalisation pass
+int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st,
+                 const float *add = nullptr);
 int bn_fused_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
                  const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
                  cudaStream_t st);
@@ -131,7 +133,8 @@ extern int g_bn_fused_enabled;  // 0: split kernels only; 1: group kernels (smal
 
 // bn_group.cu: channel-group kernels for small planes (same contract: DK_ERR_UNSUPPORTED when the shape does not fit)
 int bn_group_init();
-int bn_group_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st);
+int bn_group_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st,
+                 const float *add = nullptr);
 int bn_group_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
                  const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
                  cudaStream_t st);

@@ -84,7 +84,8 @@ __device__ __forceinline__ void bg_channel_sums(const float (&pa)[4], const floa
 
 template <bool RELU>
 __global__ void __launch_bounds__(BG_THREADS)
-bn_group_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, const BgGeom g, const BnFinalize fin) {
+bn_group_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ add, const BgGeom g,
+                    const BnFinalize fin) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar_mem;
     __shared__ float tot[2 * BG_MAX_G];
@@ -144,14 +145,30 @@ bn_group_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, const Bg
             sc[e] = chs[ce[e]];
             sh[e] = chh[ce[e]];
         }
-        for (int n = n0; n < n1; ++n) {
-            float4 v = *reinterpret_cast<const float4 *>(tile + (size_t)n * L + 4 * q);
-            v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]); v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
-            if (RELU) {
-                v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
-                v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+        for (int nb = n0; nb < n1; nb += 4) {
+            // the skip values of four rows are requested before anything is stored (see bn_fused.cu)
+            float4 a[4];
+            if (add != nullptr) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (nb + u < n1) a[u] = ld_stream4(add + ((long long)(nb + u) * g.C + c0) * g.HW + 4 * q);
             }
-            st_stream4(y + ((long long)n * g.C + c0) * g.HW + 4 * q, v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int n = nb + u;
+                if (n < n1) {
+                    float4 v = *reinterpret_cast<const float4 *>(tile + (size_t)n * L + 4 * q);
+                    v.x = fmaf(v.x, sc[0], sh[0]); v.y = fmaf(v.y, sc[1], sh[1]); v.z = fmaf(v.z, sc[2], sh[2]); v.w = fmaf(v.w, sc[3], sh[3]);
+                    if (add != nullptr) {
+                        v.x += a[u].x; v.y += a[u].y; v.z += a[u].z; v.w += a[u].w;
+                    }
+                    if (RELU) {
+                        v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+                        v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+                    }
+                    st_stream4(y + ((long long)n * g.C + c0) * g.HW + 4 * q, v);
+                }
+            }
         }
     }
 }
@@ -268,12 +285,15 @@ static bool bg_plan(int N, int C, int HW, int ntensors, BgGeom *g, size_t *smem)
     return true;
 }
 
-int bn_group_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st) {
+int bn_group_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st,
+                 const float *add) {
     BgGeom g;
     size_t smem;
-    if (fin.mode == 0 || !aligned16(x) || (y != nullptr && !aligned16(y)) || !bg_plan(N, C, HW, 1, &g, &smem)) return DK_ERR_UNSUPPORTED;
-    if (relu) bn_group_fwd_kernel<true><<<C / g.G, BG_THREADS, smem, st>>>(x, y, g, fin);
-    else bn_group_fwd_kernel<false><<<C / g.G, BG_THREADS, smem, st>>>(x, y, g, fin);
+    if (fin.mode == 0 || !aligned16(x) || (y != nullptr && !aligned16(y)) || (add != nullptr && (y == nullptr || !aligned16(add))) ||
+        !bg_plan(N, C, HW, 1, &g, &smem))
+        return DK_ERR_UNSUPPORTED;
+    if (relu) bn_group_fwd_kernel<true><<<C / g.G, BG_THREADS, smem, st>>>(x, y, add, g, fin);
+    else bn_group_fwd_kernel<false><<<C / g.G, BG_THREADS, smem, st>>>(x, y, add, g, fin);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }

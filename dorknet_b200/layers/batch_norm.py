@@ -69,6 +69,16 @@ class BatchNormLayer(Layer):
         pending(y, 1)
         self._relu_fused = True
 
+    def fused_add_relu_apply(self, y, skip):
+        """y = relu(batchnorm(x) + skip) in the SAME kernel as the statistics: the join of a ResidualBlock whose branch
+        ends in this layer (residual_block.py:75).  The mask of that ReLU depends on `skip`, so backward stays unfused:
+        the block's ReLu masks dY with its own output and this layer's backward sees a plain gradient."""
+        pending, self._pending = self._pending, None
+        if pending is None:
+            raise RuntimeError("BatchNormLayer {}: output already materialised".format(self.layer_name))
+        pending(y, 1, skip)
+        self._relu_fused = False
+
     def _flush(self):
         """Run a still-deferred training forward (somebody needs the statistics before any consumer used y)."""
         if self._pending is not None:
@@ -117,9 +127,14 @@ class BatchNormLayer(Layer):
             self._relu_fused = False
             mom, eps = float(self.run_momentum), float(self.eps)
 
-            def run(out, relu):
+            def run(out, relu, add=None):
                 # statistics + running mean/std + normalisation (+ReLU) in one call: a cluster kernel that keeps the
                 # channel in shared memory between the two passes (bn_fused.cu), or the split kernels
+                if add is not None:
+                    api.dk_bn_fwd_train_add(X.ptr, add.ptr, out.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first), mom,
+                                            eps, base, base + 4 * C, base + 8 * C, base + 12 * C, relu, N, C, HW, ws, wsn,
+                                            runtime.stream())
+                    return
                 api.dk_bn_fwd_train(X.ptr, out.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first), mom, eps,
                                     base, base + 4 * C, base + 8 * C, base + 12 * C, relu, N, C, HW, ws, wsn,
                                     runtime.stream())

@@ -2,6 +2,7 @@
 from .layer import Layer, api, runtime, asarray
 from .activations import ReLu
 from .depthwise_convolution import DepthwiseConvLayer
+from ..array import LazyBNOutput
 
 
 class ResidualBlock(Layer):
@@ -15,6 +16,7 @@ class ResidualBlock(Layer):
         self.layer_list = layer_list
         self.skip_projection = skip_projection
         self.post_skip_activation = post_skip_activation
+        self.fuse_join = True  # fold `X_tmp + skippee` + ReLU into the branch's last BatchNorm when it is still deferred
         if layer_list is None:
             self.layer_list = []
 
@@ -47,7 +49,13 @@ class ResidualBlock(Layer):
                 raise ValueError("operands could not be broadcast together with shapes {} {}".format(
                     X_tmp.shape, skippee.shape))
             y = act._buf("y", X_tmp.shape)
-            api.dk_add_relu_fwd(X_tmp.ptr, skippee.ptr, y.ptr, y.size, runtime.stream())
+            if (isinstance(X_tmp, LazyBNOutput) and not X_tmp.is_materialised and not test_mode and self.fuse_join):
+                # the branch ends in a BatchNorm whose normalisation pass has not run: it adds the skip and applies
+                # the ReLU itself (one pass over the activation instead of three)
+                X_tmp.bn.fused_add_relu_apply(y, skippee)  # (a lazy skip output materialises on .ptr)
+                X_tmp.consume()
+            else:
+                api.dk_add_relu_fwd(X_tmp.ptr, skippee.ptr, y.ptr, y.size, runtime.stream())
             act._y = y  # the reference calls the activation without test_mode, so it always records (:75)
             return y
         return act.forward(X_tmp + skippee)

@@ -87,6 +87,14 @@ int dk_bn_fwd_train(const float *x, float *y, const float *gamma, const float *b
                     float *running_mean, float *running_std, int first_batch, float momentum, float eps,
                     float *save_mean, float *save_invstd, float *save_scale, float *save_shift,
                     int fuse_relu, int N, int C, int HW, void *ws, size_t ws_bytes, dk_stream_t stream);
+/* The same with the residual join of a ResidualBlock folded into the normalisation pass:
+ * y = relu?(batchnorm(x) + add)  (residual_block.py:75: post_skip_activation(X_tmp + skippee), X_tmp the output of the
+ * branch's last BatchNormLayer).  Statistics and saved values are those of dk_bn_fwd_train; the backward of the join
+ * stays with the caller (dk_relu_bwd on y, then dk_bn_bwd with fuse_relu = 0). */
+int dk_bn_fwd_train_add(const float *x, const float *add, float *y, const float *gamma, const float *beta,
+                        float *running_mean, float *running_std, int first_batch, float momentum, float eps,
+                        float *save_mean, float *save_invstd, float *save_scale, float *save_shift,
+                        int fuse_relu, int N, int C, int HW, void *ws, size_t ws_bytes, dk_stream_t stream);
 /* Test mode: y = gamma*(x - running_mean)/running_std + beta (batch_norm.py:112-115). */
 int dk_bn_fwd_infer(const float *x, float *y, const float *gamma, const float *beta,
                     const float *running_mean, const float *running_std, int fuse_relu,

@@ -300,3 +300,35 @@ def test_batchnorm_vs_oracle(O, case, relu, fused):
         assert_close(bn.non_learned_params["running_std"].get(), rs2, FP32, "running_std 2")
     finally:
         api.dk_tc_debug_set(9, 1)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("case", [(8, 64, 56, 56), (64, 128, 28, 28), (8, 256, 14, 14), (6, 512, 7, 7), (3, 5, 9, 11), (2, 3, 300, 300)])
+def test_residual_join_folded_into_batchnorm(O, case, fuse):
+    """ResidualBlock whose branch ends in a BatchNorm: relu(bn(x) + skip) as ONE pass of the BatchNorm kernel
+    (cluster / channel-group kernels; split-kernel fallback for odd shapes) against the oracle, forward and backward."""
+    from dorknet_b200.layers.batch_norm import BatchNormLayer
+    from dorknet_b200.layers.activations import ReLu
+    from dorknet_b200.layers.residual_block import ResidualBlock
+    N, C, H, W = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = (rng.standard_normal((N, C, H, W)) * 2.0 + 0.5).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, (1, C, 1, 1)).astype(np.float32)
+    beta = rng.uniform(-0.5, 0.5, (1, C, 1, 1)).astype(np.float32)
+    dY = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    bn = BatchNormLayer("bn", input_dimension=4, incoming_chans=C)
+    bn.learned_params["gamma"], bn.learned_params["beta"] = gamma, beta
+    blk = ResidualBlock("blk", [bn], None, ReLu("r"))
+    blk.fuse_join = fuse
+    Y = blk.forward(X)
+    Yo, cache, rm, rs = O.bn_fwd_train(X, gamma, beta, None, None)
+    pre = Yo + X
+    safe = np.abs(pre) > 1e-5 * np.max(np.abs(pre))
+    assert_close(np.where(safe, Y.get(), 0), np.where(safe, np.maximum(pre, 0), 0), FP32, "relu(bn(x) + x)")
+    assert_close(bn.non_learned_params["running_mean"].get(), rm, FP32, "running_mean")
+    d = dY * (Y.get() > 0)
+    dXo, g = O.bn_bwd(d.astype(np.float32), gamma, cache)
+    dX = blk.backward(dY)
+    assert_close(dX.get(), dXo + d, FP32_RED, "dX", atol=1e-6)
+    assert_close(bn.grads["gamma"].get(), g["gamma"], FP32_RED, "dgamma", atol=1e-5)
+    assert_close(bn.grads["beta"].get(), g["beta"], FP32_RED, "dbeta", atol=1e-5)
