@@ -349,8 +349,19 @@ def _conv_dgrad_bytes(a):
     return 4 * N * (C * H * W + F * OH * OW)
 
 
+def _bn_fwd_add_bytes(a):
+    N, C, HW = a[15], a[16], a[17]
+    return 4 * 6 * N * C * HW  # BatchNorm forward (3n) + the residual join it absorbed (3n), SURVEY 8(d)
+
+
+def _bn_apply_strided_bytes(a):
+    N, C, H, W, s = a[5:10]
+    return 4 * 2 * N * C * ((H - 1) // s + 1) * ((W - 1) // s + 1)
+
+
 BYTES_FN = {
     "dk_bn_fwd_train": _bn_fwd_bytes, "dk_bn_bwd": _bn_bwd_bytes, "dk_bn_apply": _bn_apply_bytes,
+    "dk_bn_fwd_train_add": _bn_fwd_add_bytes, "dk_bn_apply_strided": _bn_apply_strided_bytes,
     "dk_dwconv_fwd": _dw_fwd_bytes, "dk_dwconv_bwd": _dw_bwd_bytes,
     "dk_pwconv_fwd": _pw_fwd_bytes, "dk_pwconv_dgrad": _pw_dgrad_bytes, "dk_pwconv_wgrad": _pw_wgrad_bytes,
     "dk_conv2d_fwd": _conv_fwd_bytes, "dk_conv2d_wgrad": _conv_wgrad_bytes, "dk_conv2d_dgrad": _conv_dgrad_bytes,

@@ -169,6 +169,24 @@ class LazyBNOutput(LazyDeviceArray):
         self._thunk = None
 
 
+class LazyReluOutput(LazyDeviceArray):
+    """Output of a ReLu that follows a training-mode BatchNorm whose normalisation pass is still deferred: nothing has
+    been launched yet.  Any consumer that reads it gets relu(batchnorm(x)) from ONE fused pass, as before; a
+    PointwiseConvLayer with stride s > 1 instead asks the BatchNorm for just the pixels it reads
+    (`bn.fused_relu_apply_strided`) and re-points the thunk to a plain apply from the saved statistics, so the
+    full-size activation is only ever produced if somebody else wants it."""
+
+    __slots__ = ("bn", "relu")
+
+    def __init__(self, buf, thunk, bn, relu):
+        super().__init__(buf, thunk)
+        self.bn = bn
+        self.relu = relu
+
+    def replace_thunk(self, thunk):
+        self._thunk = thunk
+
+
 def empty(shape, dtype=np.float32):
     torch = _torch()
     runtime.ensure_init()

@@ -178,6 +178,49 @@ bn_apply_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
     }
 }
 
+// y[n,c,oh,ow] = relu?(x[n,c,oh*s,ow*s]*scale[c] + shift[c]): the normalisation pass restricted to the pixels a following
+// stride-s pointwise convolution reads (X[:, :, ::s, ::s], pointwise_convolution.py:48), written compactly.  In
+// ResNet-18-depsep conv0_bn -> ReLU -> pw0 (stride 2) uses one pixel in four: the full-size apply wrote 205 MB per
+// step that nobody read.  VEC: stride 2, W % 8 == 0: a thread turns 8 consecutive inputs into 4 consecutive outputs.
+template <bool VEC, bool RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_apply_strided_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ scale,
+                        const float *__restrict__ shift, int64_t total_out, int C, int H, int W, int OH, int OW, int s) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC) {
+        const int ow4 = OW >> 2;
+        const int64_t nvec = total_out >> 2;
+        for (int64_t i = tid; i < nvec; i += nthreads) {
+            const int q = (int)(i % ow4);
+            const int64_t r = i / ow4;  // (n*C + c)*OH + oh
+            const int oh = (int)(r % OH);
+            const int64_t plane = r / OH;
+            const int c = (int)(plane % C);
+            const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+            const float *src = x + (plane * H + (int64_t)oh * 2) * W + 8 * q;
+            const float4 a = ld_stream4(src), b = ld_stream4(src + 4);
+            float4 v = make_float4(fmaf(a.x, sc, sh), fmaf(a.z, sc, sh), fmaf(b.x, sc, sh), fmaf(b.z, sc, sh));
+            if (RELU) {
+                v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+                v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+            }
+            st_stream4(y + 4 * i, v);
+        }
+    } else {
+        for (int64_t i = tid; i < total_out; i += nthreads) {
+            const int ow = (int)(i % OW);
+            const int64_t r = i / OW;
+            const int oh = (int)(r % OH);
+            const int64_t plane = r / OH;
+            const int c = (int)(plane % C);
+            float v = fmaf(x[(plane * H + (int64_t)oh * s) * W + (int64_t)ow * s], __ldg(scale + c), __ldg(shift + c));
+            if (RELU) v = v > 0.f ? v : 0.f;
+            y[i] = v;
+        }
+    }
+}
+
 // test mode: y = gamma*((x - rm)/rs) + beta, evaluated as the reference does (batch_norm.py:112-115)
 template <bool RELU>
 __global__ void __launch_bounds__(BN_THREADS)
@@ -479,6 +522,25 @@ int dk_bn_apply(const float *x, float *y, const float *scale, const float *shift
                 int HW, dk_stream_t stream) {
     DK_REQUIRE(N > 0 && C > 0 && HW > 0 && x && y && scale && shift, "dk_bn_apply: bad arguments");
     return launch_apply(x, y, scale, shift, fuse_relu, N, C, HW, as_stream(stream));
+}
+
+int dk_bn_apply_strided(const float *x, float *y, const float *scale, const float *shift, int fuse_relu, int N, int C,
+                        int H, int W, int stride, dk_stream_t stream) {
+    DK_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && stride >= 1 && x && y && scale && shift, "dk_bn_apply_strided: bad arguments");
+    const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+    const int64_t total = (int64_t)N * C * OH * OW;
+    const bool vec = stride == 2 && (W % 8 == 0) && aligned16(x) && aligned16(y);
+    const int grid = stream_grid(vec ? total / 4 : total, BN_THREADS * 2);
+    cudaStream_t st = as_stream(stream);
+    if (vec) {
+        if (fuse_relu) bn_apply_strided_kernel<true, true><<<grid, BN_THREADS, 0, st>>>(x, y, scale, shift, total, C, H, W, OH, OW, stride);
+        else bn_apply_strided_kernel<true, false><<<grid, BN_THREADS, 0, st>>>(x, y, scale, shift, total, C, H, W, OH, OW, stride);
+    } else {
+        if (fuse_relu) bn_apply_strided_kernel<false, true><<<grid, BN_THREADS, 0, st>>>(x, y, scale, shift, total, C, H, W, OH, OW, stride);
+        else bn_apply_strided_kernel<false, false><<<grid, BN_THREADS, 0, st>>>(x, y, scale, shift, total, C, H, W, OH, OW, stride);
+    }
+    DK_LAUNCH_CHECK();
+    return DK_OK;
 }
 
 int dk_bn_fwd_infer(const float *x, float *y, const float *gamma, const float *beta, const float *running_mean,

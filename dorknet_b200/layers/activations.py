@@ -1,6 +1,6 @@
 """ReLu (reference: layers/activations.py:6-53, layers/relu_cy.pyx)."""
 from .layer import Layer, api, runtime, asarray
-from ..array import LazyBNOutput
+from ..array import LazyBNOutput, LazyDeviceArray, LazyReluOutput
 
 
 class ReLu(Layer):
@@ -22,12 +22,15 @@ class ReLu(Layer):
         y = self._buf("y", X.shape)
         self._fused_bn = None
         if isinstance(X, LazyBNOutput) and not X.is_materialised and not test_mode:
-            # BatchNorm -> ReLU: one pass y = relu(x*scale + shift); backward: the BatchNorm masks dY itself
-            X.bn.fused_relu_apply(y)
+            # BatchNorm -> ReLU: one pass y = relu(x*scale + shift); backward: the BatchNorm masks dY itself.  The pass
+            # is launched when the consumer reads the result (a strided pointwise consumer asks for less: LazyReluOutput)
+            bn = X.bn
             X.consume()
-            self._fused_bn = X.bn
-            self._y = y
-            return y
+            self._fused_bn = bn
+            bn.expect_fused_relu(y)
+            out = LazyReluOutput(y, lambda: bn.fused_relu_apply(y), bn, self)
+            self._y = out
+            return out
         api.dk_relu_fwd(X.ptr, y.ptr, None, X.size, runtime.stream())
         if not test_mode:
             self._y = y
@@ -46,6 +49,8 @@ class ReLu(Layer):
         """dY * mask (activations.py:44-47)"""
         upstream_dx = asarray(upstream_dx)
         if self._fused_bn is not None:
+            if isinstance(self._y, LazyDeviceArray):
+                self._y.materialise()  # (nobody read the output: the deferred BatchNorm pass still has to run)
             return upstream_dx  # the fused BatchNorm's backward applies the (x_hat*gamma+beta > 0) mask
         dx = self._buf("dx", upstream_dx.shape)
         api.dk_relu_bwd(upstream_dx.ptr, self._y.ptr, dx.ptr, upstream_dx.size, runtime.stream())

@@ -58,6 +58,9 @@ class BatchNormLayer(Layer):
         self._x = None
         self._relu_fused = False
         self._pending = None
+        self._relu_claimed = False
+        self._relu_done = False
+        self._relu_out = None
         self.defer_apply = True  # return a lazy output so that a following ReLu can fuse (False: run the kernel now)
 
     def fused_relu_apply(self, y):
@@ -65,9 +68,38 @@ class BatchNormLayer(Layer):
         output); the mask is re-derived from x in backward, so this layer's backward must start with it."""
         pending, self._pending = self._pending, None
         if pending is None:
+            if self._relu_done:  # _flush already ran the fused pass into the ReLu's buffer
+                return
             raise RuntimeError("BatchNormLayer {}: output already materialised".format(self.layer_name))
         pending(y, 1)
         self._relu_fused = True
+
+    def expect_fused_relu(self, relu_out):
+        """A ReLu took our deferred output (and will write into `relu_out`): whatever ends up running the normalisation
+        pass, it is the fused one and backward masks dY."""
+        self._relu_claimed = True
+        self._relu_out = relu_out
+
+    def fused_relu_apply_strided(self, out, stride):
+        """out[n,c,oh,ow] = relu(batchnorm(x))[n,c,oh*s,ow*s] only (what a stride-s PointwiseConvLayer reads): the
+        statistics pass, then a normalisation pass over one pixel in s*s.  The full-size output is not produced."""
+        pending, self._pending = self._pending, None
+        if pending is None:
+            raise RuntimeError("BatchNormLayer {}: output already materialised".format(self.layer_name))
+        pending(None, 0)  # statistics, running mean / std, saved scale / shift
+        self._relu_fused = True
+        N, C, HW = self._dims(self.input_shape)
+        H, W = self.input_shape[2], self.input_shape[3]
+        base = self._bufs["saved"].ptr
+        api.dk_bn_apply_strided(self._x.ptr, out.ptr, base + 8 * C, base + 12 * C, 1, N, C, H, W, int(stride),
+                                runtime.stream())
+
+    def apply_saved(self, y, relu):
+        """y = relu?(x*scale + shift) from the statistics of the last training forward (a late reader of an output
+        whose full-size pass was skipped)."""
+        N, C, HW = self._dims(self.input_shape)
+        base = self._bufs["saved"].ptr
+        api.dk_bn_apply(self._x.ptr, y.ptr, base + 8 * C, base + 12 * C, int(relu), N, C, HW, runtime.stream())
 
     def fused_add_relu_apply(self, y, skip):
         """y = relu(batchnorm(x) + skip) in the SAME kernel as the statistics: the join of a ResidualBlock whose branch
@@ -83,7 +115,13 @@ class BatchNormLayer(Layer):
         """Run a still-deferred training forward (somebody needs the statistics before any consumer used y)."""
         if self._pending is not None:
             pending, self._pending = self._pending, None
-            pending(self._bufs["y"], 0)
+            if self._relu_claimed:
+                # a ReLu holds the (still unread) output: run the fused pass into its buffer now
+                pending(self._relu_out, 1)
+                self._relu_fused = True
+                self._relu_done = True
+            else:
+                pending(self._bufs["y"], 0)
 
     def __repr__(self):
         return "BatchNormLayer({}, input_dimension={}, incoming_chans={}, run_momentum={})".format(
@@ -125,17 +163,20 @@ class BatchNormLayer(Layer):
             self._flush()
             self._x = X
             self._relu_fused = False
+            self._relu_claimed = False
+            self._relu_done = False
             mom, eps = float(self.run_momentum), float(self.eps)
 
             def run(out, relu, add=None):
                 # statistics + running mean/std + normalisation (+ReLU) in one call: a cluster kernel that keeps the
                 # channel in shared memory between the two passes (bn_fused.cu), or the split kernels
+                out_ptr = out.ptr if out is not None else None
                 if add is not None:
-                    api.dk_bn_fwd_train_add(X.ptr, add.ptr, out.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first), mom,
+                    api.dk_bn_fwd_train_add(X.ptr, add.ptr, out_ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first), mom,
                                             eps, base, base + 4 * C, base + 8 * C, base + 12 * C, relu, N, C, HW, ws, wsn,
                                             runtime.stream())
                     return
-                api.dk_bn_fwd_train(X.ptr, out.ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first), mom, eps,
+                api.dk_bn_fwd_train(X.ptr, out_ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first), mom, eps,
                                     base, base + 4 * C, base + 8 * C, base + 12 * C, relu, N, C, HW, ws, wsn,
                                     runtime.stream())
             if self.defer_apply:

@@ -2,6 +2,7 @@
 import numpy as np
 
 from .layer import Layer, api, runtime, asarray
+from ..array import LazyReluOutput
 
 
 class PointwiseConvLayer(Layer):
@@ -36,6 +37,8 @@ class PointwiseConvLayer(Layer):
             self.learned_params = {}
             self.grads = {}
         self._x = None
+        self._xgeom = None
+        self.fuse_strided_input = True  # BatchNorm -> ReLU -> stride-s input: normalise only the pixels this layer reads
 
     def __repr__(self):
         out = "PointwiseConvLayer({}, ".format(self.layer_name)
@@ -57,10 +60,21 @@ class PointwiseConvLayer(Layer):
         self.input_shape = X.shape
         y = self._buf("y", (N, self.num_filters, OH, OW))
         bias = self._param("bias").ptr if self.with_bias else None
-        ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, H, W, self.num_filters, s))
-        api.dk_pwconv_fwd(X.ptr, self._param("weights").ptr, bias, y.ptr, N, C, H, W, self.num_filters, s,
+        if (s > 1 and self.fuse_strided_input and not test_mode and isinstance(X, LazyReluOutput)
+                and not X.is_materialised and X.bn._pending is not None):
+            # BatchNorm -> ReLU -> X[:, :, ::s, ::s]: only the pixels this layer reads are normalised, into a compact
+            # [N, C, OH, OW] operand that both the forward and the wgrad GEMM take through TMA with stride 1
+            xc = self._buf("x_sub", (N, C, OH, OW))
+            bn = X.bn
+            bn.fused_relu_apply_strided(xc, s)
+            X.replace_thunk(lambda: bn.apply_saved(X._buf, 1))  # the full-size output, only if somebody else reads it
+            self._x, self._xgeom = xc, (OH, OW, 1)
+        else:
+            self._x, self._xgeom = X, (H, W, s)
+        xh, xw, xs = self._xgeom
+        ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, xh, xw, self.num_filters, xs))
+        api.dk_pwconv_fwd(self._x.ptr, self._param("weights").ptr, bias, y.ptr, N, C, xh, xw, self.num_filters, xs,
                           ws, wsn, runtime.stream())
-        self._x = X
         return y
 
     def backward(self, upstream_dx):
@@ -72,8 +86,9 @@ class PointwiseConvLayer(Layer):
         st = runtime.stream()
         ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, max(H, OH * s), max(W, OW * s), F, s))
         dbias = self._grad("bias").ptr if self.with_bias else None
+        xh, xw, xs = self._xgeom  # (a compact, already subsampled operand has stride 1)
         api.dk_pwconv_wgrad(dY.ptr, self._x.ptr, w.ptr, self._grad("weights").ptr, dbias, self._l2_strength(),
-                            N, C, H, W, F, s, ws, wsn, st)
+                            N, C, xh, xw, F, xs, ws, wsn, st)
         # zero-stuffed dx of shape (OH*s, OW*s): for odd H this is NOT the input shape
         # (pointwise_convolution.py:68-72) -- reproduced on purpose
         dx = self._buf("dx", (N, C, OH * s, OW * s))

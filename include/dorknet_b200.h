@@ -102,6 +102,11 @@ int dk_bn_fwd_infer(const float *x, float *y, const float *gamma, const float *b
 /* y = x*scale[c] + shift[c] (+ReLU): materialises a deferred BN apply. */
 int dk_bn_apply(const float *x, float *y, const float *scale, const float *shift, int fuse_relu,
                 int N, int C, int HW, dk_stream_t stream);
+/* The same restricted to the pixels a following stride-s pointwise convolution reads, written compactly:
+ * y[n,c,oh,ow] = x[n,c,oh*s,ow*s]*scale[c] + shift[c] (+ReLU), y of shape [N, C, (H-1)/s+1, (W-1)/s+1]
+ * (= BN output [:, :, ::s, ::s], pointwise_convolution.py:48). */
+int dk_bn_apply_strided(const float *x, float *y, const float *scale, const float *shift, int fuse_relu,
+                        int N, int C, int H, int W, int stride, dk_stream_t stream);
 /* Backward (batch_norm.py:118-174): dgamma = sum(dy*x_hat), dbeta = sum(dy),
  * dx = gamma*invstd*(dy - mean(dy) - x_hat*mean(dy*x_hat)).  With fuse_relu != 0 the incoming
  * dy is first masked by (x*scale+shift > 0), i.e. the backward of a fused BN+ReLU. */

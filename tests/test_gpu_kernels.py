@@ -332,3 +332,46 @@ def test_residual_join_folded_into_batchnorm(O, case, fuse):
     assert_close(dX.get(), dXo + d, FP32_RED, "dX", atol=1e-6)
     assert_close(bn.grads["gamma"].get(), g["gamma"], FP32_RED, "dgamma", atol=1e-5)
     assert_close(bn.grads["beta"].get(), g["beta"], FP32_RED, "dbeta", atol=1e-5)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("case", [(4, 16, 16, 16, 24, 2), (64, 64, 112, 112, 64, 2), (3, 8, 15, 15, 12, 2), (2, 8, 12, 12, 8, 3)])
+def test_batchnorm_relu_into_strided_pointwise(O, case, fuse):
+    """BatchNorm -> ReLU -> PointwiseConvLayer(stride s): only the pixels the pointwise layer reads are normalised
+    (dk_bn_apply_strided into a compact operand); forward, backward and a late read of the full-size ReLU output."""
+    from dorknet_b200.layers.batch_norm import BatchNormLayer
+    from dorknet_b200.layers.activations import ReLu
+    from dorknet_b200.layers.pointwise_convolution import PointwiseConvLayer
+    N, C, H, W, F, s = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = (rng.standard_normal((N, C, H, W)) * 1.5 + 0.3).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, (1, C, 1, 1)).astype(np.float32)
+    beta = rng.uniform(-0.5, 0.5, (1, C, 1, 1)).astype(np.float32)
+    Wt = (rng.standard_normal((F, C)) / np.sqrt(C)).astype(np.float32)
+    bn = BatchNormLayer("bn", input_dimension=4, incoming_chans=C)
+    bn.learned_params["gamma"], bn.learned_params["beta"] = gamma, beta
+    act = ReLu("r")
+    pw = PointwiseConvLayer("p", stride=s, filter_block_shape=(F, C), with_bias=False)
+    pw.learned_params["weights"] = Wt
+    pw.fuse_strided_input = fuse
+    A = act.forward(bn.forward(X))
+    Y = pw.forward(A)
+    Yb, cache, rm, rs = O.bn_fwd_train(X, gamma, beta, None, None)
+    Ao, _ = O.relu_fwd(Yb)
+    Yo, pcache = O.pointwise_fwd(Ao, Wt, None, s)
+    assert_close(Y.get(), Yo, GEMM, "Y")
+    assert_close(bn.non_learned_params["running_std"].get(), rs, FP32, "running_std")
+    dY = rng.standard_normal(Yo.shape).astype(np.float32)
+    dAo, g = O.pointwise_bwd(dY, Wt, pcache, s, 0.0, False)
+    dA = pw.backward(dY)
+    assert_close(dA.get(), dAo, GEMM, "dA")
+    assert_close(pw.grads["weights"].get(), g["weights"], GEMM_W, "dW")
+    if dAo.shape == X.shape:  # (odd H: the reference's zero-stuffed dX is larger than X and its own backward fails)
+        ours_mask = (np.asarray(A.get()) > 0).astype(np.float32)  # late read of the full-size output
+        # (the oracle's BatchNorm backward is fed OUR dA: the TF32 rounding of the dgrad GEMM is checked above, not here)
+        dXo, gb = O.bn_bwd(O.relu_bwd(np.asarray(dA.get()), ours_mask), gamma, cache)
+        dX = bn.backward(act.backward(dA))
+        assert_close(dX.get(), dXo, 5 * FP32_RED, "dX", atol=1e-6)
+        assert_close(bn.grads["gamma"].get(), gb["gamma"], 5 * FP32_RED, "dgamma", atol=1e-5)
+    safe = np.abs(Yb) > 1e-5 * np.max(np.abs(Yb))
+    assert_close(np.where(safe, A.get(), 0), np.where(safe, Ao, 0), FP32, "full-size relu(bn(x)) read late")
