@@ -49,7 +49,7 @@ class ReLu(Layer):
         """dY * mask (activations.py:44-47)"""
         upstream_dx = asarray(upstream_dx)
         if self._fused_bn is not None:
-            if isinstance(self._y, LazyDeviceArray):
+            if isinstance(self._y, LazyDeviceArray) and self._fused_bn._pending is not None:
                 self._y.materialise()  # (nobody read the output: the deferred BatchNorm pass still has to run)
             return upstream_dx  # the fused BatchNorm's backward applies the (x_hat*gamma+beta > 0) mask
         dx = self._buf("dx", upstream_dx.shape)
