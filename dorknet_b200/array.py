@@ -187,6 +187,26 @@ class LazyReluOutput(LazyDeviceArray):
         self._thunk = thunk
 
 
+class LazyStridedGrad(LazyDeviceArray):
+    """Input gradient of a stride-s PointwiseConvLayer: zero except at [:, :, ::s, ::s] (pointwise_convolution.py:68-72).
+    Reading it (`.ptr`, `.get()`, `+`) produces the reference's zero-stuffed full-size tensor.  A consumer that can use
+    the non-zero entries alone calls compact() instead and gets them as a dense [N, C, OH, OW] array -- the dgrad GEMM
+    then writes a quarter of the bytes (stride 2) and the zeros are never stored or read."""
+
+    __slots__ = ("stride", "_compact_fn", "_compact")
+
+    def __init__(self, buf, thunk, stride, compact_fn):
+        super().__init__(buf, thunk)
+        self.stride = stride
+        self._compact_fn = compact_fn
+        self._compact = None
+
+    def compact(self):
+        if self._compact is None:
+            self._compact = self._compact_fn()
+        return self._compact
+
+
 def empty(shape, dtype=np.float32):
     torch = _torch()
     runtime.ensure_init()

@@ -373,6 +373,123 @@ bn_bwd_dx_kernel(const float *__restrict__ dy, const float *__restrict__ x, floa
     }
 }
 
+// ---- backward with a stride-2 COMPACT upstream gradient ------------------------------------------------------------------
+// The gradient a stride-2 pointwise convolution sends back is zero except at (even row, even column) pixels
+// (pointwise_convolution.py:68-72 zero-stuffs it to full size).  Taking it in its compact [N, C, H/2, W/2] form, pass 1
+// only visits those pixels (a quarter of dY, half of X's sectors) and pass 2 reads a quarter of the dY bytes; nobody
+// writes or reads the 3/4 zeros (154 MB each way for conv0_bn at batch 64).  Requires W % 8 == 0, H % 2 == 0.
+template <bool RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_reduce_sub_kernel(const float *__restrict__ dys, const float *__restrict__ x, int N, int C, int H, int W, int S,
+                         int64_t per_split, const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+                         const float *__restrict__ save_scale, const float *__restrict__ save_shift,
+                         float *__restrict__ ws_part, unsigned int *__restrict__ ws_count, float *__restrict__ coef,
+                         float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const int c = blockIdx.x, s = blockIdx.y;
+    const int OH = H >> 1, OW = W >> 1, ow4 = OW >> 2;
+    const int64_t total4 = (int64_t)N * OH * ow4;  // float4 groups of the compact gradient of this channel
+    const int64_t v0 = (int64_t)s * per_split;
+    const int64_t v1 = v0 + per_split < total4 ? v0 + per_split : total4;
+    const float mean = save_mean[c], invstd = save_invstd[c];
+    const float sc = RELU ? save_scale[c] : 0.f, sh = RELU ? save_shift[c] : 0.f;
+    float sg = 0.0f, sgx = 0.0f;
+    constexpr int U = 2;
+    for (int64_t v = v0 + threadIdx.x; v < v1; v += U * BN_THREADS) {
+        float4 gq[U], ta[U], tb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t vv = v + (int64_t)u * BN_THREADS;
+            if (vv < v1) {
+                const int q = (int)(vv % ow4);
+                const int64_t r = vv / ow4;
+                const int oh = (int)(r % OH);
+                const int64_t n = r / OH;
+                gq[u] = ld_stream4(dys + ((n * C + c) * OH + oh) * OW + 4 * q);
+                const float *xp = x + ((n * C + c) * H + 2 * oh) * (int64_t)W + 8 * q;
+                ta[u] = ld_stream4(xp);
+                tb[u] = ld_stream4(xp + 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (v + (int64_t)u * BN_THREADS < v1) {
+                float g[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+                const float t[4] = {ta[u].x, ta[u].z, tb[u].x, tb[u].z};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (RELU) g[e] = fmaf(t[e], sc, sh) > 0.f ? g[e] : 0.f;
+                    sg += g[e];
+                    sgx = fmaf(g[e], (t[e] - mean) * invstd, sgx);
+                }
+            }
+        }
+    }
+    __shared__ float red[33];
+    sg = block_sum(sg, red);
+    sgx = block_sum(sgx, red);
+    if (threadIdx.x == 0) {
+        float *p = ws_part + ((size_t)c * BN_MAX_SPLITS + s) * BN_WS_FLOATS_PER_SPLIT;
+        p[0] = sg;
+        p[1] = sgx;
+        __threadfence();
+        const unsigned int prev = atomicAdd(&ws_count[c], 1u);
+        if (prev == (unsigned int)(S - 1)) {
+            __threadfence();
+            const volatile float *vp = ws_part + (size_t)c * BN_MAX_SPLITS * BN_WS_FLOATS_PER_SPLIT;
+            float a = 0.0f, b = 0.0f;
+            for (int k = 0; k < S; ++k) {
+                a += vp[k * BN_WS_FLOATS_PER_SPLIT + 0];
+                b += vp[k * BN_WS_FLOATS_PER_SPLIT + 1];
+            }
+            dbeta[c] = a;
+            dgamma[c] = b;
+            const float inv_n = 1.0f / (float)((int64_t)N * H * W);  // means over ALL pixels (the others contribute 0)
+            coef[2 * c + 0] = a * inv_n;
+            coef[2 * c + 1] = b * inv_n;
+            ws_count[c] = 0;
+        }
+    }
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_bwd_dx_sub_kernel(const float *__restrict__ dys, const float *__restrict__ x, float *__restrict__ dx,
+                     const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+                     const float *__restrict__ save_scale, const float *__restrict__ save_shift,
+                     const float *__restrict__ coef, int64_t total, int C, int H, int W) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w4 = W >> 2, OW = W >> 1, OH = H >> 1;
+    const int64_t nvec = total >> 2;
+    for (int64_t i = tid; i < nvec; i += nthreads) {
+        const int q = (int)(i % w4);
+        const int64_t r = i / w4;  // (n*C + c)*H + h
+        const int h = (int)(r % H);
+        const int64_t plane = r / H;
+        const int c = (int)(plane % C);
+        const float mean = __ldg(save_mean + c), invstd = __ldg(save_invstd + c), sc = __ldg(save_scale + c);
+        const float k1 = __ldg(coef + 2 * c), k2 = __ldg(coef + 2 * c + 1);
+        const float4 t = ld_stream4(x + 4 * i);
+        float g0 = 0.0f, g2 = 0.0f;
+        if ((h & 1) == 0) {
+            const float2 gg = __ldg(reinterpret_cast<const float2 *>(dys + (plane * OH + (h >> 1)) * OW + 2 * q));
+            g0 = gg.x;
+            g2 = gg.y;
+            if (RELU) {
+                const float sh = __ldg(save_shift + c);
+                g0 = fmaf(t.x, sc, sh) > 0.f ? g0 : 0.f;
+                g2 = fmaf(t.z, sc, sh) > 0.f ? g2 : 0.f;
+            }
+        }
+        float4 o;
+        o.x = sc * (g0 - k1 - ((t.x - mean) * invstd) * k2);
+        o.y = sc * (0.f - k1 - ((t.y - mean) * invstd) * k2);
+        o.z = sc * (g2 - k1 - ((t.z - mean) * invstd) * k2);
+        o.w = sc * (0.f - k1 - ((t.w - mean) * invstd) * k2);
+        st_stream4(dx + 4 * i, o);
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 struct BnWs {
     float *part;          // [C][BN_MAX_SPLITS][4]
@@ -590,6 +707,48 @@ int dk_bn_bwd(const float *dy, const float *x, const float *gamma, const float *
         if (fuse_relu) DK_BN_BWD(false, true); else DK_BN_BWD(false, false);
     }
 #undef DK_BN_BWD
+    return DK_OK;
+}
+
+int dk_bn_bwd_strided(const float *dy_sub, const float *x, const float *gamma, const float *save_mean,
+                      const float *save_invstd, const float *save_scale, const float *save_shift, float *dx, float *dgamma,
+                      float *dbeta, int fuse_relu, int N, int C, int H, int W, int stride, void *ws, size_t ws_bytes,
+                      dk_stream_t stream) {
+    int rc = bn_check("dk_bn_bwd_strided", N, C, H * W, ws, ws_bytes);
+    if (rc) return rc;
+    DK_REQUIRE(dy_sub && x && save_mean && save_invstd && save_scale && save_shift && dx && dgamma && dbeta,
+               "dk_bn_bwd_strided: NULL pointer");
+    DK_REQUIRE(stride == 2 && W % 8 == 0 && H % 2 == 0 && aligned16(dy_sub) && aligned16(x) && aligned16(dx),
+               "dk_bn_bwd_strided: needs stride 2, W %% 8 == 0, H %% 2 == 0 and 16-byte aligned tensors (got stride %d, %dx%d)",
+               stride, H, W);
+    (void)gamma;
+    cudaStream_t st = as_stream(stream);
+    BnWs w = bn_ws_carve(ws, C);
+    const int64_t total4 = (int64_t)N * (H / 2) * (W / 8);
+    int64_t want = ceil_div((int64_t)sm_count() * 8, C);
+    const int64_t max_by_work = ceil_div(total4, 4 * BN_THREADS);
+    if (want > max_by_work) want = max_by_work;
+    if (want > BN_MAX_SPLITS) want = BN_MAX_SPLITS;
+    if (want < 1) want = 1;
+    const int64_t per = ceil_div(total4, want);
+    const int S = (int)ceil_div(total4, per);
+    dim3 grid(C, S);
+    const int64_t total = (int64_t)N * C * H * W;
+    const int grid2 = stream_grid(total / 4, BN_THREADS * 2);
+    if (fuse_relu) {
+        bn_bwd_reduce_sub_kernel<true><<<grid, BN_THREADS, 0, st>>>(dy_sub, x, N, C, H, W, S, per, save_mean, save_invstd, save_scale,
+                                                                    save_shift, w.part, w.count, w.coef, dgamma, dbeta);
+        DK_LAUNCH_CHECK();
+        bn_bwd_dx_sub_kernel<true><<<grid2, BN_THREADS, 0, st>>>(dy_sub, x, dx, save_mean, save_invstd, save_scale, save_shift,
+                                                                 w.coef, total, C, H, W);
+    } else {
+        bn_bwd_reduce_sub_kernel<false><<<grid, BN_THREADS, 0, st>>>(dy_sub, x, N, C, H, W, S, per, save_mean, save_invstd, save_scale,
+                                                                     save_shift, w.part, w.count, w.coef, dgamma, dbeta);
+        DK_LAUNCH_CHECK();
+        bn_bwd_dx_sub_kernel<false><<<grid2, BN_THREADS, 0, st>>>(dy_sub, x, dx, save_mean, save_invstd, save_scale, save_shift,
+                                                                  w.coef, total, C, H, W);
+    }
+    DK_LAUNCH_CHECK();
     return DK_OK;
 }
 

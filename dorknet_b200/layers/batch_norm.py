@@ -2,6 +2,7 @@
 import numpy as np
 
 from .layer import Layer, api, runtime, asarray, empty
+from ..array import LazyStridedGrad
 from ..array import LazyBNOutput
 
 
@@ -208,6 +209,17 @@ class BatchNormLayer(Layer):
         dx = self._buf("dx", self.input_shape)
         dg, db = self._grad("gamma"), self._grad("beta")
         ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
+        if (isinstance(dY, LazyStridedGrad) and not dY.is_materialised and dY.stride == 2 and self.input_dimension == 4
+                and tuple(dY.shape) == tuple(self.input_shape) and self.input_shape[3] % 8 == 0
+                and self.input_shape[2] % 2 == 0):
+            # the gradient of a stride-2 pointwise convolution, taken in its compact form: the 3/4 zeros are neither
+            # written by the dgrad GEMM nor read here
+            H, W = self.input_shape[2], self.input_shape[3]
+            dys = dY.compact()
+            api.dk_bn_bwd_strided(dys.ptr, self._x.ptr, self._param("gamma").ptr, base, base + 4 * C, base + 8 * C,
+                                  base + 12 * C, dx.ptr, dg.ptr, db.ptr, 1 if self._relu_fused else 0, N, C, H, W, 2,
+                                  ws, wsn, runtime.stream())
+            return dx
         api.dk_bn_bwd(dY.ptr, self._x.ptr, self._param("gamma").ptr, base, base + 4 * C, base + 8 * C, base + 12 * C,
                       dx.ptr, dg.ptr, db.ptr, 1 if self._relu_fused else 0, N, C, HW, ws, wsn, runtime.stream())
         return dx

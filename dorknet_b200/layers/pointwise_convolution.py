@@ -2,7 +2,7 @@
 import numpy as np
 
 from .layer import Layer, api, runtime, asarray
-from ..array import LazyReluOutput
+from ..array import LazyReluOutput, LazyStridedGrad
 
 
 class PointwiseConvLayer(Layer):
@@ -38,6 +38,7 @@ class PointwiseConvLayer(Layer):
             self.grads = {}
         self._x = None
         self._xgeom = None
+        self.lazy_strided_dx = True  # stride > 1: return the input gradient as a LazyStridedGrad
         self.fuse_strided_input = True  # BatchNorm -> ReLU -> stride-s input: normalise only the pixels this layer reads
 
     def __repr__(self):
@@ -92,5 +93,18 @@ class PointwiseConvLayer(Layer):
         # zero-stuffed dx of shape (OH*s, OW*s): for odd H this is NOT the input shape
         # (pointwise_convolution.py:68-72) -- reproduced on purpose
         dx = self._buf("dx", (N, C, OH * s, OW * s))
+        if s > 1 and self.lazy_strided_dx:
+            # deferred: a consumer that only needs the non-zero entries (BatchNormLayer.backward) asks for the compact
+            # form; anybody else reads the zero-stuffed tensor as before
+            def full():
+                ws2, wsn2 = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, max(H, OH * s), max(W, OW * s), F, s))
+                api.dk_pwconv_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, OH, OW, F, s, ws2, wsn2, runtime.stream())
+
+            def compact():
+                dxs = self._buf("dx_sub", (N, C, OH, OW))
+                ws2, wsn2 = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, OH, OW, F, 1))
+                api.dk_pwconv_dgrad(dY.ptr, w.ptr, dxs.ptr, N, C, OH, OW, F, 1, ws2, wsn2, runtime.stream())
+                return dxs
+            return LazyStridedGrad(dx, full, s, compact)
         api.dk_pwconv_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, OH, OW, F, s, ws, wsn, st)
         return dx

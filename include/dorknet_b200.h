@@ -114,6 +114,14 @@ int dk_bn_bwd(const float *dy, const float *x, const float *gamma,
               const float *save_mean, const float *save_invstd, const float *save_scale, const float *save_shift,
               float *dx, float *dgamma, float *dbeta, int fuse_relu,
               int N, int C, int HW, void *ws, size_t ws_bytes, dk_stream_t stream);
+/* The same for the upstream gradient of a stride-2 pointwise convolution taken in its COMPACT form
+ * dy_sub[N, C, H/2, W/2] (= the non-zero entries of the zero-stuffed gradient, pointwise_convolution.py:68-72:
+ * dy[n,c,2i,2j] = dy_sub[n,c,i,j], 0 elsewhere).  Results are those of dk_bn_bwd on the zero-stuffed tensor.
+ * Requires stride == 2, W % 8 == 0, H % 2 == 0. */
+int dk_bn_bwd_strided(const float *dy_sub, const float *x, const float *gamma,
+                      const float *save_mean, const float *save_invstd, const float *save_scale,
+                      const float *save_shift, float *dx, float *dgamma, float *dbeta, int fuse_relu,
+                      int N, int C, int H, int W, int stride, void *ws, size_t ws_bytes, dk_stream_t stream);
 
 /* ---- DepthwiseConvLayer: layers/depthwise_convolution.py:72-83,186-196, im2col.pyx:109-178 - */
 size_t dk_dwconv_ws_bytes(int N, int C, int H, int W, int kh, int kw, int stride, int pad);
