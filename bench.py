@@ -77,10 +77,11 @@ class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region through NVML -- as few queries as possible, because a
     query is not free here (measured on B200, 40 steps of 3.95 ms): one NVML call blocks its caller for ~13 ms, so four
     calls made from the timing loop itself starve the GPU (5.29 ms/step); a thread polling every 50 ms costs nothing on
-    one GPU (3.953 vs 3.953) but 0.1-1.4 ms/step on two (the query stalls NCCL's launches); an `nvidia-smi -lms` child
-    is worse still.  Default mode "trigger": a helper thread takes ONE sample when the timing loop signals that half of
-    the steps are enqueued (the loop itself never waits), and the loop takes a second one after the last step is
-    enqueued, while the GPU is still working through its queue.  BENCH_CLOCK_MODE=thread is the old 50 ms poller."""
+    one GPU (3.953 vs 3.953) but 0.1-1.4 ms/step on two (the query stalls the other process's launches); an `nvidia-smi
+    -lms` child is worse still; even ONE query cost ~5 ms of a 2-GPU region when launches were still being enqueued.
+    Default mode "tail": ONE sample, taken by the timing loop after every launch of the region is enqueued and the GPU
+    is one step from the end of it (an event says so): on 2 x B200 that still costs ~3 ms of the region (5 ms mid-region).
+    BENCH_CLOCK_MODE=trigger adds a mid-region sample from a helper thread, =thread is the old 50 ms poller."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
@@ -461,9 +462,10 @@ def run_ours(a, spec):
 
     # ---- timed region: K steps, inputs resident in HBM (one CUDA-graph replay per step) -----------------------
     clocks = ClockSampler(torch.cuda.current_device(), period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.05")),
-                          mode=os.environ.get("BENCH_CLOCK_MODE", "trigger")) if (
+                          mode=os.environ.get("BENCH_CLOCK_MODE", "tail")) if (
         rank == 0 and os.environ.get("BENCH_NO_CLOCKS") != "1") else None
     trigger_at = a.steps // 2 if (clocks and clocks.mode == "trigger") else -1
+    tail_only = bool(clocks and clocks.mode == "tail")
     barrier()
     if clocks:
         clocks.start()
@@ -476,11 +478,18 @@ def run_ours(a, spec):
         loss = train_step(*ring[i % nring][2:])
         if i == trigger_at:
             clocks.trigger()  # half of the steps are enqueued: the helper thread samples now, this loop does not wait
+        if tail_only and i == max(0, a.steps - 2):
+            e_late = torch.cuda.Event()
+            e_late.record()  # one more step follows
         if dbg_sync:
             torch.cuda.current_stream().synchronize()
     e1.record()
-    if trigger_at >= 0:
-        clocks.sample()  # everything is enqueued, the GPU is still inside the last steps
+    if tail_only:
+        # Every launch of the region is enqueued (on every rank: nothing is left that a driver lock could delay); wait
+        # until the GPU is one step from the end, then query NVML while it executes it
+        e_late.synchronize()
+    if trigger_at >= 0 or tail_only:
+        clocks.sample()  # the GPU is still inside the last steps
         tail_under_load = not e1.query()
     barrier()
     t_wall1 = time.time()
@@ -491,6 +500,8 @@ def run_ours(a, spec):
     clock_info = clocks.stop(t_wall0, t_wall1) if clocks else None
     if clock_info is not None and trigger_at >= 0:
         clock_info["mode"] = "one NVML sample mid-region (helper thread) + one after the last enqueue (GPU still busy: %s)" % tail_under_load
+    elif clock_info is not None and tail_only:
+        clock_info["mode"] = "one NVML sample after the last enqueue, inside the timed region (GPU still busy: %s)" % tail_under_load
     # the dominant kernel family, bracketed with CUDA events on the launching stream: the same step, same buffers,
     # launched eagerly right after the timed region (events cannot sit inside a replayed graph)
     dom = CallTimer(torch, BYTES_FN)
@@ -577,7 +588,7 @@ def run_ours(a, spec):
         "config": {"workload": "%s, %s, batch %d per GPU, %s%s" % (spec["name"], spec["note"], B, spec["opt"],
                                                                  ", mixup" if a.mixup else ""),
                    "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "allreduce": ("none" if dp is None else ("nccl, %d buckets captured inside the step's CUDA graph, overlapped with backward"
+                   "allreduce": ("none" if dp is None else "none: gradients summed over NVLink peer memory inside the optimiser kernel (dk_opt_multi_p2p)" if dp.mode == "p2p" else ("nccl, %d buckets captured inside the step's CUDA graph, overlapped with backward"
                                                             % len(dp.buckets) if graphed.dp_in_graph else
                                                             "nccl, issued from backward hooks" if a.no_graph else "nccl, between two graphs")),
                    "l2_flush": "none needed: per-step working set (activations) >> 126 MB L2; inputs rotate over %d batches" % nring},

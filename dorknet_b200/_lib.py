@@ -69,6 +69,12 @@ PROTOS = {
     "dk_opt_sgdm_multi": (I, [P, I, L, F, F, F, P, P]),
     "dk_opt_rmsprop_multi": (I, [P, I, L, F, F, F, P, P]),
     "dk_mixup": (I, [P, P, P, F, L, P]),
+    "dk_p2p_alloc": (I, [Z, P, P]),
+    "dk_p2p_open": (I, [P, P]),
+    "dk_p2p_close": (I, [P]),
+    "dk_p2p_free": (I, [P]),
+    "dk_p2p_wait_done": (I, [P, P]),
+    "dk_opt_multi_p2p": (I, [I, P, I, L, P, P, P]),
 }
 
 # value-returning (not status) functions
@@ -79,6 +85,12 @@ _NO_CHECK = {"dk_version", "dk_last_error", "dk_sm_count", "dk_kernel_launches",
 class OptTensor(ctypes.Structure):
     """mirror of dk_opt_tensor"""
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("state", c_void_p), ("n", c_int64)]
+
+
+class P2PCtx(ctypes.Structure):
+    """mirror of dk_p2p_ctx"""
+    _fields_ = [("world", c_int), ("rank", c_int), ("grad_delta", c_int64 * 8), ("ready", c_void_p * 8),
+                ("done", c_void_p * 8), ("epoch", c_void_p)]
 
 
 class SumsqTask(ctypes.Structure):

@@ -11,7 +11,14 @@ Mechanics
     is issued (async_op): NCCL orders it after the kernels already on the compute stream and runs it
     on its own stream, overlapped with the rest of backward;
   * the fused optimiser kernel multiplies gradients by 1/G (grad_scale), so no separate scaling pass.
+
+Mode "p2p" (default on B200s of one box; DK_DP_MODE=nccl selects the above): no collective launch at all.  The flat
+gradient buffer of every rank is cudaMalloc'ed, exported with cudaIpc and mapped by all peers (P2PExchange); the
+optimiser kernel itself reads element i from every rank's buffer over NVLink, adds them in rank order and applies the
+update (csrc/dp_p2p.cu: dk_opt_multi_p2p), bracketed by two flag handshakes on peer-mapped words.  torch.distributed
+only carries the 64-byte handles at start-up and the initial parameter broadcast.
 """
+import ctypes
 import os
 
 import numpy as np
@@ -68,8 +75,71 @@ def flat_layout(sizes, align=32):
     return offs, cur
 
 
+class _RawCudaArray:
+    """a cudaMalloc'ed range presented through __cuda_array_interface__ (torch.as_tensor wraps it without a copy)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class P2PExchange:
+    """Peer-mapped gradient buffers + flag blocks of all ranks of one box, and the device-side dk_p2p_ctx."""
+
+    FLAG_BYTES = 256  # ready[8], done[8] (uint32, indexed by writer rank), epoch at word 32
+
+    def __init__(self, dist, group, nfloats):
+        import torch
+        from ._lib import api, P2PCtx
+        self.api = api
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("p2p data parallel supports up to 8 ranks")
+        self.nfloats = int(nfloats)
+
+        def alloc(nbytes):
+            ptr, handle = ctypes.c_void_p(0), (ctypes.c_ubyte * 64)()
+            api.dk_p2p_alloc(int(nbytes), ctypes.byref(ptr), handle)
+            return int(ptr.value), bytes(handle)
+        self.grad_ptr, gh = alloc(max(self.nfloats, 1) * 4)
+        self.flag_ptr, fh = alloc(self.FLAG_BYTES)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (gh, fh), group=group)
+        self._opened = []
+        grad_ptrs, flag_ptrs = [0] * self.world, [0] * self.world
+        for p, (pgh, pfh) in enumerate(gathered):
+            if p == self.rank:
+                grad_ptrs[p], flag_ptrs[p] = self.grad_ptr, self.flag_ptr
+                continue
+            for h, out in ((pgh, grad_ptrs), (pfh, flag_ptrs)):
+                q = ctypes.c_void_p(0)
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                api.dk_p2p_open(buf, ctypes.byref(q))
+                out[p] = int(q.value)
+                self._opened.append(int(q.value))
+        ctx = P2PCtx()
+        ctx.world, ctx.rank = self.world, self.rank
+        for p in range(self.world):
+            ctx.grad_delta[p] = grad_ptrs[p] - self.grad_ptr
+            ctx.ready[p] = flag_ptrs[p]
+            ctx.done[p] = flag_ptrs[p] + 32
+        ctx.epoch = self.flag_ptr + 128
+        raw = np.frombuffer(ctypes.string_at(ctypes.addressof(ctx), ctypes.sizeof(ctx)), dtype=np.uint8).copy()
+        self.ctx = torch.from_numpy(raw).to(runtime.device())
+        self.flat = torch.as_tensor(_RawCudaArray(self.grad_ptr, max(self.nfloats, 1)), device=runtime.device())
+        dist.barrier(group=group)  # everybody has mapped everybody before the first handshake
+
+    @property
+    def ctx_ptr(self):
+        return self.ctx.data_ptr()
+
+    def wait_done(self):
+        self.api.dk_p2p_wait_done(self.ctx_ptr, runtime.stream())
+
+
 class DataParallel:
-    def __init__(self, network, optimiser=None, num_buckets=3, overlap=True, process_group=None, device=None):
+    def __init__(self, network, optimiser=None, num_buckets=3, overlap=True, process_group=None, device=None,
+                 mode=None):
         import torch.distributed as dist
         self.dist = dist
         self.network = network
@@ -93,6 +163,20 @@ class DataParallel:
         sizes = [int(np.prod(l.learned_params[k].shape)) for l, k in self.entries]
         self.offsets, self.total = flat_layout(sizes)
         self.sizes = sizes
+        # gradient exchange: "p2p" = fused into the optimiser kernel over NVLink peer memory, "nccl" = all_reduce
+        if mode is None:
+            mode = os.environ.get("DK_DP_MODE", "p2p")
+        self.mode = "nccl"
+        self.p2p = None
+        if (mode == "p2p" and self.world > 1 and device is None and optimiser is not None and self.world <= 8
+                and hasattr(optimiser, "attach_p2p")):
+            try:
+                self.p2p = P2PExchange(dist, process_group, self.total)
+                self.mode = "p2p"
+            except Exception as e:  # noqa: BLE001 -- e.g. no peer access between these GPUs: NCCL still works
+                import sys
+                sys.stderr.write("dorknet_b200: peer-memory gradient exchange unavailable (%s); using NCCL\n" % e)
+                self.p2p = None
         self._flatten_grads()
         self.buckets = []
         for a, b in plan_buckets(sizes, num_buckets):
@@ -102,14 +186,19 @@ class DataParallel:
             self.buckets.append(dict(lo=lo, hi=hi, trigger=last_layer))
         if optimiser is not None:
             optimiser.grad_scale = 1.0 / self.world
-        if self.world > 1 and overlap:
+            if self.p2p is not None:
+                optimiser.attach_p2p(self.p2p)
+        if self.world > 1 and overlap and self.p2p is None:
             self._install_hooks()
 
     # -- flat gradient storage ---------------------------------------------------------------------
     def _flatten_grads(self):
         import torch
         dev = self.device if self.device is not None else runtime.device()
-        self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=dev)
+        if self.p2p is not None:
+            self.flat = self.p2p.flat  # cudaMalloc'ed, mapped by every peer
+        else:
+            self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=dev)
         for (layer, k), off, n in zip(self.entries, self.offsets, self.sizes):
             shape = layer.learned_params[k].shape
             layer.grads[k] = DeviceArray(self.flat[off:off + n], shape)
@@ -144,8 +233,16 @@ class DataParallel:
                                     async_op=True)
         self._pending.append(work)
 
+    def begin_step(self):
+        """Call before the first kernel of a step that writes gradients (p2p mode: wait until every peer has read the
+        previous step's)."""
+        if self.p2p is not None:
+            self.p2p.wait_done()
+
     def finish(self):
         """Call after network.backward(): (issue and) wait for every bucket on the compute stream."""
+        if self.p2p is not None:
+            return  # the optimiser kernel reads the peers' gradients itself
         if self.world <= 1 or os.environ.get("DK_DP_SKIP_ALLREDUCE") == "1":  # (diagnostics knob)
             return
         if not self.overlap or not self.hooks_enabled:

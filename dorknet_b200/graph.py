@@ -39,6 +39,8 @@ class GraphedTrainStep:
         self._opt_graph = None
 
     def _eager(self, X, Y):
+        if self.dp is not None:
+            self.dp.begin_step()
         loss, _ = self.net.forward(X, Y)
         self.net.backward()
         if self.dp is not None:
@@ -83,6 +85,8 @@ class GraphedTrainStep:
                     self.dp.hooks_enabled = False  # fallback: one all-reduce after the graph, not from the hooks
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
+                    if self.dp is not None:
+                        self.dp.begin_step()
                     loss, _ = self.net.forward(X, Y)
                     self.net.backward()
                     if self.dp is None:
@@ -107,9 +111,10 @@ class GraphedTrainStep:
         g = torch.cuda.CUDAGraph()
         self.dp.hooks_enabled = True
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self.dp.begin_step()
             loss, _ = self.net.forward(X, Y)
             self.net.backward()
-            self.dp.finish()  # joins NCCL's stream back into the capture stream
+            self.dp.finish()  # joins NCCL's stream back into the capture stream (nothing to do in p2p mode)
             self.opt.update_weights()
         return (g, loss, X, Y)
 

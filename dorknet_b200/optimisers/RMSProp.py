@@ -16,7 +16,7 @@ class RMSProp(MultiTensorOptimiser):
 
     def update_weights(self):
         """c = d*c + (1-d)*g^2 ; w -= lr*g/sqrt(c + 1e-5) (RMSProp.py:28-36), one launch."""
-        tab, n, max_n = self._args()
-        if n:
+        def plain(tab, n, max_n):
             api.dk_opt_rmsprop_multi(tab, n, max_n, float(self.learning_rate), float(self.decay_rate),
                                      float(self.grad_scale), self.push_hyper(), runtime.stream())
+        self._update(2, plain)

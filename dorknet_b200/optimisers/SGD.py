@@ -13,7 +13,7 @@ class SGD(MultiTensorOptimiser):
 
     def update_weights(self):
         """w += -lr * g for every tensor of the update set, one launch."""
-        tab, n, max_n = self._args()
-        if n:
+        def plain(tab, n, max_n):
             api.dk_opt_sgd_multi(tab, n, max_n, float(self.learning_rate), float(self.grad_scale), self.push_hyper(),
                                  runtime.stream())
+        self._update(0, plain)

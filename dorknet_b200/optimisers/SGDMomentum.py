@@ -16,7 +16,7 @@ class SGDMomentum(MultiTensorOptimiser):
 
     def update_weights(self):
         """v = -lr*g + momentum*v ; w += v (SGDMomentum.py:31-39), one launch."""
-        tab, n, max_n = self._args()
-        if n:
+        def plain(tab, n, max_n):
             api.dk_opt_sgdm_multi(tab, n, max_n, float(self.learning_rate), float(self.momentum),
                                   float(self.grad_scale), self.push_hyper(), runtime.stream())
+        self._update(1, plain)

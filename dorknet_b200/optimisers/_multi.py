@@ -47,6 +47,21 @@ class MultiTensorOptimiser:
         self._hyper = None       # device {lr, momentum/decay, grad_scale}
         self._hyper_host = None  # pinned staging
         self._hyper_vals = None
+        self._p2p = None         # data_parallel.P2PExchange: gradients are summed over the peers inside the update kernel
+
+    def attach_p2p(self, exchange):
+        self._p2p = exchange
+
+    def _update(self, kind, plain):
+        """One launch: `plain()` = the single-GPU kernel, or the peer-memory variant when a P2PExchange is attached."""
+        from .._lib import api
+        tab, n, max_n = self._args()
+        if not n:
+            return
+        if self._p2p is not None:
+            api.dk_opt_multi_p2p(kind, tab, n, max_n, self.push_hyper(), self._p2p.ctx_ptr, runtime.stream())
+        else:
+            plain(tab, n, max_n)
 
     def set_learning_rate(self, new_lr):
         self.learning_rate = new_lr

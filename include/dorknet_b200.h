@@ -235,6 +235,29 @@ int dk_opt_sgdm_multi(const dk_opt_tensor *table, int num_tensors, int64_t max_n
 int dk_opt_rmsprop_multi(const dk_opt_tensor *table, int num_tensors, int64_t max_n,
                          float lr, float decay, float grad_scale, const float *hyper, dk_stream_t stream);
 
+/* ---- data parallel over NVLink peer memory: gradient exchange fused into the optimiser kernel ----
+ * Each rank allocates its flat gradient buffer and a flag block with dk_p2p_alloc, exchanges the 64-byte handles
+ * (any host channel: torch.distributed here), maps the peers' buffers with dk_p2p_open and fills a dk_p2p_ctx in
+ * DEVICE memory.  Per step: dk_p2p_wait_done before the first kernel that writes gradients, dk_opt_multi_p2p in place of
+ * dk_opt_*_multi: "gradients ready" handshake, ONE kernel that sums element i of every rank's gradient buffer in rank
+ * order (peers read over NVLink), scales by hyper[2] and applies optimiser `kind` (0 SGD, 1 SGDMomentum, 2 RMSProp;
+ * hyper = {lr, momentum|decay, grad_scale} in device memory), then the "done reading" handshake. */
+#define DK_P2P_MAX_RANKS 8
+typedef struct {
+    int world, rank;
+    long long grad_delta[DK_P2P_MAX_RANKS]; /* byte offset from MY gradient buffer to rank p's mapping of its own */
+    unsigned int *ready[DK_P2P_MAX_RANKS];  /* rank p's flag block (uint32[8], indexed by writer), as mapped HERE */
+    unsigned int *done[DK_P2P_MAX_RANKS];
+    unsigned int *epoch;                    /* local step counter (device memory) */
+} dk_p2p_ctx;
+int dk_p2p_alloc(size_t bytes, void **ptr, unsigned char *handle64);
+int dk_p2p_open(const unsigned char *handle64, void **ptr);
+int dk_p2p_close(void *ptr);
+int dk_p2p_free(void *ptr);
+int dk_p2p_wait_done(const dk_p2p_ctx *ctx, dk_stream_t stream);
+int dk_opt_multi_p2p(int kind, const dk_opt_tensor *table, int num_tensors, int64_t max_n, const float *hyper,
+                     const dk_p2p_ctx *ctx, dk_stream_t stream);
+
 /* ---- input pipeline (next row): data_loading/image_data_loader.py:100-112 ---- */
 /* out = lam*xb + (1-lam)*xa  (mixup of two batches / label sets) */
 int dk_mixup(const float *xa, const float *xb, float *out, float lam, int64_t n, dk_stream_t stream);
