@@ -489,8 +489,9 @@ def run_ours(a, spec):
         # until the GPU is one step from the end, then query NVML while it executes it
         e_late.synchronize()
     if trigger_at >= 0 or tail_only:
+        busy_at_start = not e1.query()
         clocks.sample()  # the GPU is still inside the last steps
-        tail_under_load = not e1.query()
+        tail_under_load = "%s when the query started, %s when it returned" % (busy_at_start, not e1.query())
     barrier()
     t_wall1 = time.time()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -560,13 +561,18 @@ def run_ours(a, spec):
         w0 = time.perf_counter()
         s0.record()
         up.submit_from_pinned(*host[0])
+        pend = None
         for i in range(a.steps):
             Xd, Yd = up.get()
             loss = train_step(Xd, Yd)
             up.release()
             if i + 1 < a.steps:
                 up.submit_from_pinned(*host[(i + 1) % nring])  # H2D of the next batch overlaps this step
-            lv = float(loss)  # device -> host read of the step's result
+            nxt = loss.fetch_async()  # device -> host copy of THIS step's loss, enqueued behind the step
+            if pend is not None:
+                lv = pend.result()    # ... and the host reads the previous step's while this one runs
+            pend = nxt
+        lv = pend.result()
         s1.record()
         barrier()
         w1 = time.perf_counter()

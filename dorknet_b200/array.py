@@ -277,7 +277,41 @@ class _SlotArena:
         return self.host.numpy()
 
 
+    def read_async(self):
+        """Enqueue a snapshot of all slots into its own pinned buffer on the current stream; returns (host tensor,
+        event).  The host can keep launching: it reads the snapshot once the event has fired."""
+        torch = _torch()
+        n = max(self.used, 1)
+        host = torch.empty(n, dtype=torch.float32).pin_memory() if not self._free_hosts else self._free_hosts.pop()
+        if host.numel() < n:
+            host = torch.empty(n, dtype=torch.float32).pin_memory()
+        host[:n].copy_(self.buf[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev
+
+    _free_hosts = []
+
+
 _arena = _SlotArena()
+
+
+class PendingScalar:
+    """Result of DeviceScalar.fetch_async(): the device -> host copy is in flight; result() waits for it only."""
+
+    __slots__ = ("_terms", "_const", "_host", "_ev")
+
+    def __init__(self, terms, const, host, ev):
+        self._terms, self._const, self._host, self._ev = terms, const, host, ev
+
+    def result(self):
+        self._ev.synchronize()
+        snap = self._host.numpy()
+        total = np.float64(self._const)
+        for slot, coeff in self._terms:
+            total += coeff * float(snap[slot])
+        _SlotArena._free_hosts.append(self._host)
+        return float(total)
 
 
 def alloc_scalar_slot():
@@ -333,6 +367,22 @@ class DeviceScalar:
             else:
                 total += coeff * float(slot.get().reshape(-1)[0])
         return float(total)
+
+    def fetch_async(self):
+        """Start the device -> host read of this value behind whatever is enqueued on the current stream and return a
+        PendingScalar; the caller keeps launching work and calls .result() later (a training loop reads the loss of
+        step i while step i+1 runs, instead of draining the GPU every step)."""
+        from .regularisers.l2 import flush_pending
+        flush_pending()
+        if any(not isinstance(slot, int) for slot, _ in self.terms):
+            v = float(self)
+
+            class _Done:
+                def result(self_inner):
+                    return v
+            return _Done()
+        host, ev = _arena.read_async()
+        return PendingScalar(list(self.terms), self.const, host, ev)
 
     def get(self):
         return np.float32(float(self))
