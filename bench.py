@@ -360,7 +360,13 @@ def _bn_apply_strided_bytes(a):
     return 4 * 2 * N * C * ((H - 1) // s + 1) * ((W - 1) // s + 1)
 
 
+def _bn_bwd_strided_bytes(a):
+    N, C, H, W = a[11:15]
+    return 4 * 5 * N * C * H * W  # what dk_bn_bwd on the zero-stuffed gradient would count
+
+
 BYTES_FN = {
+    "dk_bn_bwd_strided": _bn_bwd_strided_bytes,
     "dk_bn_fwd_train": _bn_fwd_bytes, "dk_bn_bwd": _bn_bwd_bytes, "dk_bn_apply": _bn_apply_bytes,
     "dk_bn_fwd_train_add": _bn_fwd_add_bytes, "dk_bn_apply_strided": _bn_apply_strided_bytes,
     "dk_dwconv_fwd": _dw_fwd_bytes, "dk_dwconv_bwd": _dw_bwd_bytes,

@@ -46,6 +46,7 @@ struct TcParams {
     int bn;          // MMA N (multiple of 32, <= 256)
     int m_blocks, n_blocks, k_blocks;
     int splits, items_per_split, total_items;  // mode 1
+    int kpi;         // mode 1, both operands through TMA: 32-wide k-blocks per pipeline item (k_blocks then counts ITEMS per image)
     int num_tiles;
     int stages;
     int epi;         // 0: out[(b*N + n)*ldo + m] (+bias[n]);  1: out[(split*M + m)*N + n];  2: zero-stuffed strided scatter
@@ -241,7 +242,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // carve: stages first (1024-byte aligned), then barriers
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 4;
-    const uint32_t stage_bytes = TC_A_BYTES + b_bytes;
+    const uint32_t kpi = (uint32_t)p.kpi;  // stage layout: kpi A sub-tiles, then kpi B sub-tiles
+    const uint32_t stage_bytes = kpi * (TC_A_BYTES + b_bytes);
     const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
@@ -308,16 +310,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int iters = tile_iters(tile);
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
+                    const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + kpi * TC_A_BYTES;
                     const uint32_t fb = full_bar(s);
-                    mbar_expect_tx(fb, (AG::kGather ? 0u : p.a_tx) + (BG::kGather ? 0u : b_bytes));
+                    mbar_expect_tx(fb, kpi * ((AG::kGather ? 0u : p.a_tx) + (BG::kGather ? 0u : b_bytes)));
                     int kb = it, bb = b;
                     if (p.mode == 1) {
                         const int kk = item0 + it;
                         bb = kk / p.k_blocks;
                         kb = kk - bb * p.k_blocks;
                     }
-                    const int k0 = kb * TC_BK;
+                    const int k0 = kb * TC_BK * (int)kpi;
+                    if (kpi > 1) {
+                        // wide items (wgrad, K-major operands): kpi consecutive 128-byte k-blocks of every row arrive
+                        // together -- 512 B of each (n, f) plane row per item instead of 128 B, which is what the DRAM pages
+                        // want; k-blocks past the plane are zero-filled by the TMA unit
+                        for (uint32_t j = 0; j < kpi; ++j) {
+                            tma_load_3d(sA + j * TC_A_BYTES, &tmA, fb, k0 + (int)j * TC_BK, m0, bb);
+                            tma_load_3d(sB + j * b_bytes, &tmB, fb, k0 + (int)j * TC_BK, n0, bb);
+                        }
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                        continue;
+                    }
                     if (!AG::kGather) {
                         if (p.a_mn) {
 #pragma unroll
@@ -355,19 +368,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int it = 0; it < iters; ++it) {
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
+                    const uint32_t sA0 = smem_base + (uint32_t)s * stage_bytes, sB0 = sA0 + kpi * TC_A_BYTES;
                     int nks = TC_BK / 8;
                     if (p.mode == 0) {
                         const int rem = p.K - it * TC_BK;
                         if (rem < TC_BK) nks = (rem + 7) / 8;
                     }
 #pragma unroll 1
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint64_t ad = p.a_mn ? smem_desc(sA + ks * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                                   : smem_desc(sA + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                        const uint64_t bd = p.b_mn ? smem_desc(sB + ks * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                                   : smem_desc(sB + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                        mma_tf32(d_tmem, ad, bd, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    for (uint32_t j = 0; j < kpi; ++j) {
+                        const uint32_t sA = sA0 + j * TC_A_BYTES, sB = sB0 + j * b_bytes;
+#pragma unroll 1
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t ad = p.a_mn ? smem_desc(sA + ks * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                       : smem_desc(sA + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                            const uint64_t bd = p.b_mn ? smem_desc(sB + ks * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
+                                                       : smem_desc(sB + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                            mma_tf32(d_tmem, ad, bd, idesc, (it > 0 || j > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
                     mma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -412,7 +429,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     const int k0 = kb * TC_BK;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;
+                    const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + TC_A_BYTES;  // (kpi == 1 with loaders)
                     // Index arithmetic and copies are issued in explicit batches (pointer arrays + fully unrolled
                     // inner loops): the compiler's own unrolling of these loops is not stable across builds, and a
                     // rolled loop serialises address computation behind every single cp.async.
@@ -607,6 +624,7 @@ static int g_mn_layout = LAYOUT_SW128_BASE32B, g_mn_lbo = 4096, g_mn_sbo = 512, 
 static int g_mn_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 static int g_l2_promo = (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
 static int g_smem_budget = TC_SMEM_BUDGET;  // bytes of operand stages per CTA
+static int g_wide_items = 0;                 // wgrad k-blocks per item: 0 = automatic (pw_wgrad), 1 / 2 / 4 = forced
 static int g_two_per_sm = 1;                 // see tc_launch
 static int g_ctas_per_sm = 1;                // persistent CTAs per SM the grids / split plans are sized for
 static int g_tc_disable_mask = 0;  // bit0 fwd, bit1 dgrad, bit2 wgrad (bring-up / tests)
@@ -690,6 +708,7 @@ static void fill_common(TcParams &p) {
     int st = g_smem_budget / stage_bytes;
     if (st > TC_MAX_STAGES) st = TC_MAX_STAGES;
     p.stages = st;
+    p.kpi = 1;
     p.a_tx = TC_A_BYTES;
     p.mn_layout = (uint32_t)g_mn_layout;
     p.mn_lbo = (uint32_t)g_mn_lbo;
@@ -710,7 +729,7 @@ static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, TcParams p, c
                                      TC_SMEM_BUDGET + 2048));
         attr_set = true;
     }
-    const int stage_bytes = TC_A_BYTES + p.bn * TC_BK * 4;
+    const int stage_bytes = p.kpi * (TC_A_BYTES + p.bn * TC_BK * 4);
     int per_sm = g_ctas_per_sm;
     if (two_per_sm && g_two_per_sm && per_sm == 1 && p.num_tiles >= 2 * sm_count() && p.tmem_cols <= 256) {
         const int st2 = (98 * 1024) / stage_bytes;
@@ -762,8 +781,12 @@ size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s
     const ConvGeom g = mk_geom(C, H, W, F, kh, kw, s, p);
     const int64_t P = (int64_t)g.OH * g.OW;
     const int Kf = C * kh * kw;
-    int splits, per;
-    split_plan(F, Kf, (int64_t)N * ceil_div(P, TC_BK), (int64_t)N * P * (F + Kf) * 4, &splits, &per);
+    int splits = 1, per;
+    for (int kpi = 1; kpi <= 4; kpi *= 2) {  // (pw_wgrad may group 2 or 4 k-blocks per item: take the largest plan)
+        int sp;
+        split_plan(F, Kf, (int64_t)N * ceil_div(ceil_div(P, TC_BK), kpi), (int64_t)N * P * (F + Kf) * 4, &sp, &per);
+        if (sp > splits) splits = sp;
+    }
     size_t repack = 0;  // padded copies of dY and X (pointwise only; fwd / dgrad need one of the two)
     if (kh == 1 && kw == 1 && p == 0 && ((P % 4) != 0 || s > 1) && P <= 4 * TC_REPACK_MAX_P)
         repack = repack_bytes((int64_t)N * F, P) + repack_bytes((int64_t)N * C, P) + 512;
@@ -906,6 +929,25 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     q.mode = 1; q.a_mn = 0; q.b_mn = 0; q.b_batched = 1;
     q.M = F; q.N = C; q.K = (int)P; q.batches = N;
     fill_common(q);
+    bool a_tma = tma_ok(dy, P), b_tma = (s == 1) && tma_ok(x, P);
+    if (a_tma && b_tma) {
+        // wide pipeline items for long planes: 4 (or 2) consecutive k-blocks per item, if at least two stages still fit and
+        // the rounding of the plane to whole items wastes little
+        const int kb0 = q.k_blocks, one = TC_A_BYTES + q.bn * TC_BK * 4;
+        int kpi = 1;
+        for (int cand = 4; cand >= 2; cand >>= 1) {
+            const int items = (kb0 + cand - 1) / cand;
+            if (P >= 512 && g_smem_budget / (cand * one) >= 2 && items * cand * 16 <= kb0 * 17) { kpi = cand; break; }
+        }
+        if (g_wide_items == 1 || g_wide_items == 2 || g_wide_items == 4) kpi = g_wide_items;
+        if (g_smem_budget / (kpi * one) < 1) kpi = 1;
+        if (kpi > 1) {
+            q.kpi = kpi;
+            q.k_blocks = (kb0 + kpi - 1) / kpi;
+            int st = g_smem_budget / (kpi * one);
+            q.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+        }
+    }
     q.total_items = N * q.k_blocks;
     split_plan(F, C, q.total_items, (int64_t)N * P * (F + C) * 4, &q.splits, &q.items_per_split);
     q.num_tiles = q.m_blocks * q.n_blocks * q.splits;
@@ -916,7 +958,6 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     }
     q.epi = 1; q.out = reinterpret_cast<float *>(ws); q.bias = nullptr; q.ldo = 0;
     CUtensorMap ta = {}, tb = {};
-    bool a_tma = tma_ok(dy, P), b_tma = (s == 1) && tma_ok(x, P);
     int rc = DK_OK;
     int64_t pa = P, pb = P;  // row pitches of the operands the maps describe
     {
@@ -1134,6 +1175,7 @@ int dk_tc_debug_set(int key, int value) {
             dk::g_ctas_per_sm = value;
             dk::g_smem_budget = value >= 2 ? 98 * 1024 : dk::TC_SMEM_BUDGET;
             break;
+        case 15: dk::g_wide_items = value; break;  // wgrad k-blocks per pipeline item (0 automatic)
         case 14: dk::g_two_per_sm = value; break;  // 0: forward / dgrad GEMMs never run two CTAs per SM
         case 11: dk::g_short_a = value; break;  // 0: wgrad dY boxes always 128 rows
         case 10: dk::g_repack_mask = value; break;  // bit0: pad misaligned planes for TMA, bit1: repack small strided planes
