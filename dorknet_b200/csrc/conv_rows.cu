@@ -197,6 +197,106 @@ __device__ __forceinline__ void cr_expand_tile(const ConvRowsParams &p, const fl
     }
 }
 
+
+// The same expansion with everything that does not depend on the tile hoisted out of the tile loop: a loader warp always
+// expands the same (c, i) rows (r = lw, lw + 8), so their destination addresses, tap indices and edge masks are computed
+// once per kernel; per tile only the row validity, the span misalignment and the source offset change.  (ncu on the first
+// span-staging version: ~480 instructions per loader warp and tile, most of them this index arithmetic.)
+constexpr int CR_ROWS_PER_WARP = 2;  // C*kh <= 16 (conv0: 15, MobileNet conv0: 9, MNIST conv0: 3); else cr_expand_tile
+
+template <int KW>
+struct CrRowPlan {
+    int nrows;                              // rows this warp expands (0 .. CR_ROWS_PER_WARP)
+    int rowconst[CR_ROWS_PER_WARP];         // c*slot + 4 + i*W - pad
+    int chw[CR_ROWS_PER_WARP];              // c*H*W (low bits only matter)
+    int irow[CR_ROWS_PER_WARP];             // i
+    uint32_t dst[CR_ROWS_PER_WARP][KW];     // byte offset of tap j of this lane's 4 pixels inside an operand tile
+    int lo_bad, hi_ok;                      // window elements t < lo_bad or t >= hi_ok are padding columns
+    bool active;                            // this lane's 4 pixels exist (4*lane < OW)
+};
+
+template <int S, int KW, bool WGRAD>
+__device__ __forceinline__ void cr_plan_rows(const ConvRowsParams &p, int lw, int lane, uint32_t chunk_bytes, CrRowPlan<KW> &pl) {
+    const int rows = p.C * p.kh;
+    pl.nrows = 0;
+    const uint32_t l = (uint32_t)lane;
+#pragma unroll
+    for (int u = 0; u < CR_ROWS_PER_WARP; ++u) {
+        const int r = lw + u * CR_LOADER_WARPS;
+        pl.rowconst[u] = 0; pl.chw[u] = 0; pl.irow[u] = 0;
+        if (r < rows) {
+            const int c = r / p.kh, i = r - c * p.kh;
+            pl.nrows = u + 1;
+            pl.rowconst[u] = c * p.slot + 4 + i * p.W - p.p;
+            pl.chw[u] = c * p.H * p.W;
+            pl.irow[u] = i;
+        }
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            const uint32_t k = (uint32_t)(r * KW + j);
+            if (WGRAD) pl.dst[u][j] = (l >> 3) * chunk_bytes + k * 128u + (((l & 7u) ^ (k & 7u)) << 4);
+            else pl.dst[u][j] = (k >> 5) * 16384u + (l >> 3) * 4096u + (k & 31u) * 128u + ((((l & 7u) >> 1) ^ (k & 3u)) << 5) + ((l & 1u) << 4);
+        }
+    }
+    pl.lo_bad = p.p - S * 4 * lane;
+    pl.hi_ok = p.W + p.p - S * 4 * lane;
+    pl.active = 4 * lane < p.OW;
+}
+
+template <int S, int KW>
+__device__ __forceinline__ void cr_expand_planned(const ConvRowsParams &p, const CrRowPlan<KW> &pl, const float *stage, int n,
+                                                  int ih0, int lane, uint32_t tile_base) {
+    if (!pl.active) return;
+    constexpr int WIN = 3 * S + KW;
+    constexpr int NL = (WIN + 3 + 3) / 4;
+    const int lo = ih0 > 0 ? ih0 : 0;
+    const uint32_t nbase = ((uint32_t)n * (uint32_t)(p.C * p.H) + (uint32_t)lo) * (uint32_t)p.W;  // (only the low two bits are used)
+    const int dlo = (ih0 - lo) * p.W;
+#pragma unroll
+    for (int u = 0; u < CR_ROWS_PER_WARP; ++u) {
+        if (u < pl.nrows) {
+            const int ih = ih0 + pl.irow[u];
+            const bool rok = ih >= 0 && ih < p.H;
+            float w[WIN];
+            if (rok) {
+                const int mis = (int)((nbase + (uint32_t)pl.chw[u]) & 3u);
+                const int a = pl.rowconst[u] + mis + dlo + S * 4 * lane;
+                const int R = a & 3;
+                const float4 *src = reinterpret_cast<const float4 *>(stage + (a - R));
+                float r[NL * 4];
+#pragma unroll
+                for (int q = 0; q < NL; ++q) {
+                    const float4 v = src[q];
+                    r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+                }
+                if (R == 0) {
+#pragma unroll
+                    for (int t = 0; t < WIN; ++t) w[t] = r[t];
+                } else if (R == 1) {
+#pragma unroll
+                    for (int t = 0; t < WIN; ++t) w[t] = r[t + 1];
+                } else if (R == 2) {
+#pragma unroll
+                    for (int t = 0; t < WIN; ++t) w[t] = r[t + 2];
+                } else {
+#pragma unroll
+                    for (int t = 0; t < WIN; ++t) w[t] = r[t + 3];
+                }
+                if (pl.lo_bad > 0 || pl.hi_ok < WIN) {
+#pragma unroll
+                    for (int t = 0; t < WIN; ++t)
+                        if (t < pl.lo_bad || t >= pl.hi_ok) w[t] = 0.0f;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < WIN; ++t) w[t] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < KW; ++j) st_shared_v4(tile_base + pl.dst[u][j], w[j], w[S + j], w[2 * S + j], w[3 * S + j]);
+        }
+    }
+}
+
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
@@ -305,6 +405,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
                     }
                 }
             }
+            const bool planned = p.C * p.kh <= CR_ROWS_PER_WARP * CR_LOADER_WARPS;
+            CrRowPlan<KW> pl;
+            cr_plan_rows<S, KW, false>(p, lw, lane, 0u, pl);
+            // (n, oh) of this CTA's tiles advance by gridDim.x rows per iteration: no division in the loop
+            int tn = (int)blockIdx.x / p.OH, toh = (int)blockIdx.x - tn * p.OH;
+            const int dn = (int)gridDim.x / p.OH, doh = (int)gridDim.x - dn * p.OH;
             int it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int stg = it % p.in_stages;
@@ -318,9 +424,15 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
                 }
                 const int a = it & 1;
                 mbar_wait(a_empty(a), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-                tile_coords(tile, n, oh, ow0);
-                cr_expand_tile<S, KW, false>(p, in_f + (size_t)stg * p.in_floats, n, oh * p.s - p.p, lw, lane,
-                                             sA + (uint32_t)a * a_bytes, 0u);
+                if (planned)
+                    cr_expand_planned<S, KW>(p, pl, in_f + (size_t)stg * p.in_floats, tn, toh * p.s - p.p, lane,
+                                             sA + (uint32_t)a * a_bytes);
+                else
+                    cr_expand_tile<S, KW, false>(p, in_f + (size_t)stg * p.in_floats, tn, toh * p.s - p.p, lw, lane,
+                                                 sA + (uint32_t)a * a_bytes, 0u);
+                tn += dn;
+                toh += doh;
+                if (toh >= p.OH) { toh -= p.OH; ++tn; }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full(a));
@@ -528,6 +640,10 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
                     }
                 }
             }
+            const bool planned = p.C * p.kh <= CR_ROWS_PER_WARP * CR_LOADER_WARPS;
+            CrRowPlan<KW> pl;
+            cr_plan_rows<S, KW, true>(p, lw, lane, b_chunk, pl);
+            int tn = r_beg / p.OH, toh = r_beg - tn * p.OH;
             int it = 0;
             for (int r = r_beg; r < r_end; ++r, ++it) {
                 const int stg = it % p.in_stages;
@@ -540,9 +656,13 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
                 }
                 const int sb = it & 1;
                 mbar_wait(b_empty(sb), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-                const int n = r / p.OH, oh = r - n * p.OH;
-                cr_expand_tile<S, KW, true>(p, in_f + (size_t)stg * p.in_floats, n, oh * p.s - p.p, lw, lane,
-                                            sB + (uint32_t)sb * b_bytes, b_chunk);
+                if (planned)
+                    cr_expand_planned<S, KW>(p, pl, in_f + (size_t)stg * p.in_floats, tn, toh * p.s - p.p, lane,
+                                             sB + (uint32_t)sb * b_bytes);
+                else
+                    cr_expand_tile<S, KW, true>(p, in_f + (size_t)stg * p.in_floats, tn, toh * p.s - p.p, lw, lane,
+                                                sB + (uint32_t)sb * b_bytes, b_chunk);
+                if (++toh >= p.OH) { toh = 0; ++tn; }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_full(sb));
