@@ -556,9 +556,17 @@ def run_ours(a, spec):
     e2e = None
     if not a.no_e2e:
         up = HostBatchUploader((B, spec["chans"], spec["size"], spec["size"]), (B, spec["classes"]), slots=2)
-        host = [up.pin(r[0], r[1]) for r in ring]  # the step's inputs live in pinned host memory
+        # The step's inputs as a data loader holds them: decoded uint8 NHWC images (+ the mixup partner batch) and the
+        # label matrix, in pinned host memory.  They cross PCIe as uint8; one device kernel does the reference's
+        # astype(float32).transpose(2,0,1) - 128 (+ mixup) (image_preprocessor.py:36-37, image_data_loader.py:100-110).
+        # Same images as the device-resident ring above.
+        host = []
+        for i in range(nring):
+            raw = W.synthetic_batch_u8(B, spec["chans"], spec["size"], spec["classes"], seed=1000 * rank + i, mixup=a.mixup)
+            ha, hb, hy = up.pin_u8(raw["img"], raw["Y"], raw.get("img_b"))
+            host.append((ha, hb, hy, raw.get("lam", 0.0)))
         for i in range(2):  # warm the pipeline
-            up.submit_from_pinned(*host[i % nring])
+            up.submit_u8_from_pinned(*host[i % nring])
             Xd, Yd = up.get()
             float(train_step(Xd, Yd))
             up.release()
@@ -566,14 +574,14 @@ def run_ours(a, spec):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         s0.record()
-        up.submit_from_pinned(*host[0])
+        h2d = up.submit_u8_from_pinned(*host[0])
         pend = None
         for i in range(a.steps):
             Xd, Yd = up.get()
             loss = train_step(Xd, Yd)
             up.release()
             if i + 1 < a.steps:
-                up.submit_from_pinned(*host[(i + 1) % nring])  # H2D of the next batch overlaps this step
+                up.submit_u8_from_pinned(*host[(i + 1) % nring])  # H2D of the next batch overlaps this step
             nxt = loss.fetch_async()  # device -> host copy of THIS step's loss, enqueued behind the step
             if pend is not None:
                 lv = pend.result()    # ... and the host reads the previous step's while this one runs
@@ -584,7 +592,9 @@ def run_ours(a, spec):
         w1 = time.perf_counter()
         ms_e2e = max_over_ranks(max(s0.elapsed_time(s1), 1e3 * (w1 - w0)))
         e2e = {"value": world * B * a.steps / (ms_e2e / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": up.bytes_per_batch, "d2h_bytes_per_step": 4 * 64,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * 64,
+               "input": "uint8 NHWC images%s + fp32 labels from pinned host memory; transpose / -128%s on the device (dk_input_u8_nhwc)"
+                        % (" (two batches)" if a.mixup else "", " / mixup" if a.mixup else ""),
                "ms_per_step": ms_e2e / a.steps, "last_loss": lv}
 
     if rank != 0:

@@ -69,6 +69,7 @@ PROTOS = {
     "dk_opt_sgdm_multi": (I, [P, I, L, F, F, F, P, P]),
     "dk_opt_rmsprop_multi": (I, [P, I, L, F, F, F, P, P]),
     "dk_mixup": (I, [P, P, P, F, L, P]),
+    "dk_input_u8_nhwc": (I, [P, P, P, F, F, I, I, I, I, P]),
     "dk_p2p_alloc": (I, [Z, P, P]),
     "dk_p2p_open": (I, [P, P]),
     "dk_p2p_close": (I, [P]),

@@ -191,21 +191,39 @@ bn_apply_strided_kernel(const float *__restrict__ x, float *__restrict__ y, cons
     if (VEC) {
         const int ow4 = OW >> 2;
         const int64_t nvec = total_out >> 2;
-        for (int64_t i = tid; i < nvec; i += nthreads) {
-            const int q = (int)(i % ow4);
-            const int64_t r = i / ow4;  // (n*C + c)*OH + oh
-            const int oh = (int)(r % OH);
-            const int64_t plane = r / OH;
-            const int c = (int)(plane % C);
-            const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-            const float *src = x + (plane * H + (int64_t)oh * 2) * W + 8 * q;
-            const float4 a = ld_stream4(src), b = ld_stream4(src + 4);
-            float4 v = make_float4(fmaf(a.x, sc, sh), fmaf(a.z, sc, sh), fmaf(b.x, sc, sh), fmaf(b.z, sc, sh));
-            if (RELU) {
-                v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
-                v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+        constexpr int U = 2;  // 2 x 32 bytes in flight per thread before anything is stored
+        for (int64_t i0 = tid; i0 < nvec; i0 += U * nthreads) {
+            float4 a[U], b[U];
+            float sc[U], sh[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + u * nthreads;
+                if (i < nvec) {
+                    const int q = (int)(i % ow4);
+                    const int64_t r = i / ow4;  // (n*C + c)*OH + oh
+                    const int oh = (int)(r % OH);
+                    const int64_t plane = r / OH;
+                    const int c = (int)(plane % C);
+                    sc[u] = __ldg(scale + c);
+                    sh[u] = __ldg(shift + c);
+                    const float *src = x + (plane * H + (int64_t)oh * 2) * W + 8 * q;
+                    a[u] = ld_stream4(src);
+                    b[u] = ld_stream4(src + 4);
+                }
             }
-            st_stream4(y + 4 * i, v);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + u * nthreads;
+                if (i < nvec) {
+                    float4 v = make_float4(fmaf(a[u].x, sc[u], sh[u]), fmaf(a[u].z, sc[u], sh[u]), fmaf(b[u].x, sc[u], sh[u]),
+                                           fmaf(b[u].z, sc[u], sh[u]));
+                    if (RELU) {
+                        v.x = v.x > 0.f ? v.x : 0.f; v.y = v.y > 0.f ? v.y : 0.f;
+                        v.z = v.z > 0.f ? v.z : 0.f; v.w = v.w > 0.f ? v.w : 0.f;
+                    }
+                    st_stream4(y + 4 * i, v);
+                }
+            }
         }
     } else {
         for (int64_t i = tid; i < total_out; i += nthreads) {

@@ -86,6 +86,29 @@ struct MixupOp {
     __device__ __forceinline__ void apply(float xa, float xb, float &y, float &) const { y = lam * xb + oml * xa; }
 };
 
+// ---- device-side input pipeline -----------------------------------------------------------------------
+// The reference's loader turns every decoded uint8 HWC image into fp32 CHW minus 128 on the host
+// (data_loading/image_preprocessor.py:36-37: astype(float32).transpose(2,0,1); im -= 128) and blends mixup pairs there
+// too (image_data_loader.py:100-110).  Here the batch crosses PCIe as uint8 NHWC (a quarter of the bytes) and ONE kernel
+// does transpose + conversion + offset (+ mixup): out[n,c,h,w] = (1-lam)*(xa[n,h,w,c] - sub) + lam*(xb[n,h,w,c] - sub).
+// A thread owns one pixel: consecutive threads read consecutive C-byte groups and write consecutive floats of each plane.
+__global__ void __launch_bounds__(256)
+input_u8_nhwc_kernel(const unsigned char *__restrict__ xa, const unsigned char *__restrict__ xb, float *__restrict__ out,
+                     float lam, float sub, long long pixels, int C, long long HW) {
+    const float oml = 1.0f - lam;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / HW, hw = i - n * HW;
+        const unsigned char *pa = xa + i * C;
+        float *o = out + n * C * HW + hw;
+        if (xb != nullptr) {
+            const unsigned char *pb = xb + i * C;
+            for (int c = 0; c < C; ++c) o[c * HW] = oml * ((float)pa[c] - sub) + lam * ((float)pb[c] - sub);
+        } else {
+            for (int c = 0; c < C; ++c) o[c * HW] = (float)pa[c] - sub;
+        }
+    }
+}
+
 // ---- global average pooling: one warp per (n, c) plane -----------------------------------------
 __global__ void gap_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int planes, int HW, float inv) {
     const int warps_per_block = blockDim.x >> 5;
@@ -291,6 +314,16 @@ int dk_add(const float *a, const float *b, float *out, int64_t n, dk_stream_t st
 int dk_mixup(const float *xa, const float *xb, float *out, float lam, int64_t n, dk_stream_t stream) {
     DK_REQUIRE(n >= 0 && (n == 0 || (xa && xb && out)), "dk_mixup: bad arguments");
     return launch_map<MixupOp, 2, 1>(xa, xb, out, nullptr, n, MixupOp{lam, 1.0f - lam}, as_stream(stream));
+}
+
+int dk_input_u8_nhwc(const unsigned char *xa, const unsigned char *xb, float *out, float lam, float sub, int N, int C, int H,
+                     int W, dk_stream_t stream) {
+    DK_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && xa && out, "dk_input_u8_nhwc: bad arguments");
+    const long long pixels = (long long)N * H * W;
+    input_u8_nhwc_kernel<<<stream_grid(pixels, 256), 256, 0, as_stream(stream)>>>(xa, xb, out, xb ? lam : 0.0f, sub, pixels, C,
+                                                                                 (long long)H * W);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
 }
 
 int dk_gap_fwd(const float *x, float *y, int N, int C, int HW, dk_stream_t stream) {

@@ -262,7 +262,8 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ partial, const fl
 // Same reduction with the Z partials spread over 8 thread rows (fixed combination order -> deterministic): the
 // split-K GEMMs leave up to 148 partials of a small [M][N] matrix, which a one-thread-per-output loop reads as a
 // serial chain of dependent-latency loads.
-constexpr int SKR_X = 32, SKR_Y = 8;
+constexpr int SKR_X = 32;
+template <int SKR_Y>
 __global__ void __launch_bounds__(SKR_X * SKR_Y)
 splitk_reduce2_kernel(const float *__restrict__ partial, const float *__restrict__ w, float *__restrict__ out, float l2,
                       int64_t mn, int Z) {
@@ -290,7 +291,10 @@ splitk_reduce2_kernel(const float *__restrict__ partial, const float *__restrict
 }
 
 void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st) {
-    if (Z >= 16) splitk_reduce2_kernel<<<(unsigned)ceil_div(mn, SKR_X), SKR_X * SKR_Y, 0, st>>>(partial, w, out, l2, mn, Z);
+    // Z >= 64 (a small [M][N] with ~148 partials: the 56x56 / 28x28 pointwise wgrads): 32 thread rows, so that a thread's
+    // 4-5 loads are one batch in flight instead of a chain of five
+    if (Z >= 64) splitk_reduce2_kernel<32><<<(unsigned)ceil_div(mn, SKR_X), SKR_X * 32, 0, st>>>(partial, w, out, l2, mn, Z);
+    else if (Z >= 16) splitk_reduce2_kernel<8><<<(unsigned)ceil_div(mn, SKR_X), SKR_X * 8, 0, st>>>(partial, w, out, l2, mn, Z);
     else splitk_reduce_kernel<<<stream_grid(mn, 256), 256, 0, st>>>(partial, w, out, l2, mn, Z);
 }
 

@@ -101,22 +101,37 @@ class P2PExchange:
             ptr, handle = ctypes.c_void_p(0), (ctypes.c_ubyte * 64)()
             api.dk_p2p_alloc(int(nbytes), ctypes.byref(ptr), handle)
             return int(ptr.value), bytes(handle)
-        self.grad_ptr, gh = alloc(max(self.nfloats, 1) * 4)
-        self.flag_ptr, fh = alloc(self.FLAG_BYTES)
+        # Every rank takes part in every collective below whatever happened locally, and the outcome is agreed on
+        # (a rank that fell back to NCCL alone would leave the others spinning on its flags).
+        err = None
+        try:
+            self.grad_ptr, gh = alloc(max(self.nfloats, 1) * 4)
+            self.flag_ptr, fh = alloc(self.FLAG_BYTES)
+        except Exception as e:  # noqa: BLE001
+            err, gh, fh = str(e), None, None
         gathered = [None] * self.world
-        dist.all_gather_object(gathered, (gh, fh), group=group)
+        dist.all_gather_object(gathered, (err, gh, fh), group=group)
+        bad = [g[0] for g in gathered if g[0] is not None]
         self._opened = []
         grad_ptrs, flag_ptrs = [0] * self.world, [0] * self.world
-        for p, (pgh, pfh) in enumerate(gathered):
-            if p == self.rank:
-                grad_ptrs[p], flag_ptrs[p] = self.grad_ptr, self.flag_ptr
-                continue
-            for h, out in ((pgh, grad_ptrs), (pfh, flag_ptrs)):
-                q = ctypes.c_void_p(0)
-                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-                api.dk_p2p_open(buf, ctypes.byref(q))
-                out[p] = int(q.value)
-                self._opened.append(int(q.value))
+        if not bad:
+            try:
+                for p, (_, pgh, pfh) in enumerate(gathered):
+                    if p == self.rank:
+                        grad_ptrs[p], flag_ptrs[p] = self.grad_ptr, self.flag_ptr
+                        continue
+                    for h, out in ((pgh, grad_ptrs), (pfh, flag_ptrs)):
+                        q = ctypes.c_void_p(0)
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                        api.dk_p2p_open(buf, ctypes.byref(q))
+                        out[p] = int(q.value)
+                        self._opened.append(int(q.value))
+            except Exception as e:  # noqa: BLE001
+                err = str(e)
+        ok = torch.tensor([0 if (bad or err) else 1], dtype=torch.int32, device=runtime.device())
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise RuntimeError("peer mapping failed on at least one rank: %s" % (bad[0] if bad else err))
         ctx = P2PCtx()
         ctx.world, ctx.rank = self.world, self.rank
         for p in range(self.world):

@@ -84,6 +84,40 @@ class HostBatchUploader:
             s["ready"].record(self.stream)
         self._inflight += 1
 
+    # ---- uint8 NHWC batches: a quarter of the PCIe bytes, converted on the device ---------------------------------
+    def pin_u8(self, img, Y, img_b=None):
+        """Pinned copies of decoded uint8 NHWC batch(es) and the label matrix (a loader's output buffers)."""
+        torch = self.torch
+        def pin(a, dt):
+            t = torch.empty(a.size, dtype=dt).pin_memory()
+            t.copy_(torch.from_numpy(np.ascontiguousarray(a).reshape(-1)))
+            return t
+        hb = pin(img_b, torch.uint8) if img_b is not None else None
+        return pin(img, torch.uint8), hb, pin(np.asarray(Y, np.float32), torch.float32)
+
+    def submit_u8_from_pinned(self, ha, hb, hy, lam=0.0, sub=128.0):
+        """H2D of uint8 NHWC image batch(es) + labels on the side stream, then ONE kernel there turns them into the fp32
+        NCHW network input (dk_input_u8_nhwc: transpose, - 128, mixup with `lam` when a second batch is given)."""
+        torch = self.torch
+        s = self.slots[self._w % len(self.slots)]
+        self._w += 1
+        N, C, H, W = self.x_shape
+        if "ua" not in s:
+            s["ua"] = torch.empty(N * H * W * C, dtype=torch.uint8, device=runtime.device())
+        if hb is not None and "ub" not in s:
+            s["ub"] = torch.empty(N * H * W * C, dtype=torch.uint8, device=runtime.device())
+        self.stream.wait_event(s["free"])
+        with torch.cuda.stream(self.stream):
+            s["ua"].copy_(ha, non_blocking=True)
+            if hb is not None:
+                s["ub"].copy_(hb, non_blocking=True)
+            s["dy"].t.copy_(hy, non_blocking=True)
+            api.dk_input_u8_nhwc(s["ua"].data_ptr(), s["ub"].data_ptr() if hb is not None else None, s["dx"].ptr,
+                                 float(lam), float(sub), N, C, H, W, self.stream.cuda_stream)
+            s["ready"].record(self.stream)
+        self._inflight += 1
+        return ha.numel() + (hb.numel() if hb is not None else 0) + 4 * hy.numel()
+
     def get(self):
         """(X, Y) DeviceArrays of the oldest submitted batch; valid until release()."""
         if self._inflight <= 0:

@@ -142,23 +142,39 @@ def iter_param_layers(net, include_skip=True):
                 yield l.skip_projection
 
 
-def synthetic_batch(batch, channels, size, classes, seed=0, mixup=False):
-    """images U[0,255)-128 fp32 NCHW, one-hot labels; with mixup two batches are blended with
-    lam ~ U(0, 0.3) as data_loading/image_data_loader.py:100-112 does."""
+def synthetic_batch_u8(batch, channels, size, classes, seed=0, mixup=False):
+    """The synthetic batch as a data loader would hold it: decoded images, uint8 NHWC in [0, 255] (cv2 order), one-hot
+    labels, and for mixup a second batch + lam ~ U(0, 0.3) (data_loading/image_data_loader.py:100-112).
+    Returns dict(img, y, Y[, img_b, y_b, Y_b, lam]); Y is the (blended) label matrix the loss sees."""
     rng = np.random.default_rng(seed)
-    X = (rng.uniform(0.0, 255.0, size=(batch, channels, size, size)) - 128.0).astype(np.float32)
+    out = {"img": rng.integers(0, 256, size=(batch, size, size, channels), dtype=np.uint8)}
     y = rng.integers(0, classes, size=batch)
     Y = np.zeros((batch, classes), np.float32)
     Y[np.arange(batch), y] = 1.0
+    out["y"] = y
     if mixup:
-        Xb = (rng.uniform(0.0, 255.0, size=X.shape) - 128.0).astype(np.float32)
+        out["img_b"] = rng.integers(0, 256, size=(batch, size, size, channels), dtype=np.uint8)
         yb = rng.integers(0, classes, size=batch)
         Yb = np.zeros_like(Y)
         Yb[np.arange(batch), yb] = 1.0
         lam = np.float32(rng.uniform(0.0, 0.3))
-        X = lam * Xb + (1 - lam) * X
+        out["lam"] = float(lam)
         Y = lam * Yb + (1 - lam) * Y
-    return X, y, Y
+    out["Y"] = Y.astype(np.float32)
+    return out
+
+
+def synthetic_batch(batch, channels, size, classes, seed=0, mixup=False):
+    """images in [0,255] - 128 as fp32 NCHW (image_preprocessor.py:36-37 on the uint8 images of
+    synthetic_batch_u8), one-hot labels; with mixup two batches are blended with lam ~ U(0, 0.3) as
+    data_loading/image_data_loader.py:100-112 does."""
+    raw = synthetic_batch_u8(batch, channels, size, classes, seed=seed, mixup=mixup)
+    X = raw["img"].transpose(0, 3, 1, 2).astype(np.float32) - np.float32(128.0)
+    if mixup:
+        Xb = raw["img_b"].transpose(0, 3, 1, 2).astype(np.float32) - np.float32(128.0)
+        lam = np.float32(raw["lam"])
+        X = (np.float32(1.0) - lam) * X + lam * Xb
+    return np.ascontiguousarray(X, np.float32), raw["y"], raw["Y"]
 
 
 # ---- algorithmic bytes / flops (SURVEY.md §8(d), fp32, unfused per-layer minimum) ------------------------

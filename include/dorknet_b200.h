@@ -261,6 +261,10 @@ int dk_opt_multi_p2p(int kind, const dk_opt_tensor *table, int num_tensors, int6
 /* ---- input pipeline (next row): data_loading/image_data_loader.py:100-112 ---- */
 /* out = lam*xb + (1-lam)*xa  (mixup of two batches / label sets) */
 int dk_mixup(const float *xa, const float *xb, float *out, float lam, int64_t n, dk_stream_t stream);
+/* uint8 NHWC batch(es) as decoded -> fp32 NCHW network input, one kernel (image_preprocessor.py:36-37 + mixup):
+ * out[n,c,h,w] = (1-lam)*(xa[n,h,w,c] - sub) + lam*(xb[n,h,w,c] - sub); xb may be NULL (no mixup, lam ignored). */
+int dk_input_u8_nhwc(const unsigned char *xa, const unsigned char *xb, float *out, float lam, float sub,
+                     int N, int C, int H, int W, dk_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -382,3 +382,22 @@ def test_batchnorm_relu_into_strided_pointwise(O, case, fuse):
         assert_close(dA.get(), dAo, GEMM, "dA")
     safe = np.abs(Yb) > 1e-5 * np.max(np.abs(Yb))
     assert_close(np.where(safe, A.get(), 0), np.where(safe, Ao, 0), FP32, "full-size relu(bn(x)) read late")
+
+
+@pytest.mark.parametrize("mixup", [False, True])
+def test_input_pipeline_u8_nhwc(mixup):
+    """uint8 NHWC batches -> fp32 NCHW - 128 (+ mixup) on the device (dk_input_u8_nhwc through HostBatchUploader)
+    against the host arithmetic of the reference's loader (image_preprocessor.py:36-37, image_data_loader.py:100-110)."""
+    from dorknet_b200 import workloads as W
+    from dorknet_b200.input_pipeline import HostBatchUploader
+    N, C, S, K = 5, 3, 33, 7
+    raw = W.synthetic_batch_u8(N, C, S, K, seed=9, mixup=mixup)
+    Xref, _, Yref = W.synthetic_batch(N, C, S, K, seed=9, mixup=mixup)
+    up = HostBatchUploader((N, C, S, S), (N, K), slots=2)
+    ha, hb, hy = up.pin_u8(raw["img"], raw["Y"], raw.get("img_b"))
+    nbytes = up.submit_u8_from_pinned(ha, hb, hy, raw.get("lam", 0.0))
+    Xd, Yd = up.get()
+    assert nbytes == (2 if mixup else 1) * N * C * S * S + 4 * N * K
+    assert_close(Xd.get(), Xref, 1e-6 if mixup else 0.0, "X")
+    assert np.array_equal(Yd.get(), Yref)
+    up.release()

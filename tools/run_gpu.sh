@@ -1,7 +1,8 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_golden.py -m gpu -x -q -k "conv or mini" > gpurun_out/t35.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t35.log
-tail -4 gpurun_out/t35.log
-timeout 300 python tests/conv0_bench.py > gpurun_out/conv0_planned.log 2>&1; tail -3 gpurun_out/conv0_planned.log
-timeout 300 python tests/conv0_bench.py --hw 224 --k 3 --filters 32 > gpurun_out/conv0_planned_mb.log 2>&1; tail -2 gpurun_out/conv0_planned_mb.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t36.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t36.log
+tail -6 gpurun_out/t36.log
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r1ax.json 2> gpurun_out/bench_r1ax.err; tail -3 gpurun_out/bench_r1ax.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_r1ax.json')); print(round(d['value']), d['ms_per_step'], d['e2e'], d['final_loss'])"
