@@ -74,14 +74,14 @@ def build_net(M, spec, seed=0):
 
 # ------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region through NVML -- as few queries as possible, because a
-    query is not free here (measured on B200, 40 steps of 3.95 ms): one NVML call blocks its caller for ~13 ms, so four
-    calls made from the timing loop itself starve the GPU (5.29 ms/step); a thread polling every 50 ms costs nothing on
-    one GPU (3.953 vs 3.953) but 0.1-1.4 ms/step on two (the query stalls the other process's launches); an `nvidia-smi
-    -lms` child is worse still; even ONE query cost ~5 ms of a 2-GPU region when launches were still being enqueued.
-    Default mode "tail": ONE sample, taken by the timing loop after every launch of the region is enqueued and the GPU
-    is one step from the end of it (an event says so): on 2 x B200 that still costs ~3 ms of the region (5 ms mid-region).
-    BENCH_CLOCK_MODE=trigger adds a mid-region sample from a helper thread, =thread is the old 50 ms poller."""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML -- one sample, placed with care, because
+    none of this is free on a B200 box (measured, 40 steps of 3.95 ms): a query blocks its caller for ~13 ms, so queries made
+    by the timing loop mid-region starve the GPU (5.29 ms/step); a thread polling every 50 ms costs nothing on one GPU but
+    0.1-1.4 ms/step on two; `nvmlInit` right before the region cost a 2-GPU region 3-9 ms (it attaches to every GPU of
+    the box); an `nvidia-smi -lms` child is worse still.  So: open() attaches NVML at process start, and the default mode
+    "tail" takes ONE sample from the timing loop after every launch of the region is enqueued and the GPU is two steps
+    from the end of it (an event says so): nothing measurable on 1, 2 or 4 GPUs.  BENCH_CLOCK_MODE=trigger adds a
+    mid-region sample from a helper thread, =thread is the old 50 ms poller."""
 
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
