@@ -39,6 +39,7 @@ PROTOS = {
     "dk_bn_apply": (I, [P, P, P, P, I, I, I, I, P]),
     "dk_bn_apply_strided": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "dk_bn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P, Z, P]),
+    "dk_bn_bwd_join": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P, Z, P]),
     "dk_bn_bwd_strided": (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, Z, P]),
     "dk_dwconv_ws_bytes": (Z, [I, I, I, I, I, I, I, I]),
     "dk_dwconv_fwd": (I, [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),

@@ -728,6 +728,23 @@ int dk_bn_bwd(const float *dy, const float *x, const float *gamma, const float *
     return DK_OK;
 }
 
+int dk_bn_bwd_join(const float *dout, const float *out, const float *x, const float *gamma, const float *save_mean,
+                   const float *save_invstd, const float *save_scale, const float *save_shift, float *dx, float *d_join,
+                   float *dgamma, float *dbeta, int N, int C, int HW, void *ws, size_t ws_bytes, dk_stream_t stream) {
+    int rc = bn_check("dk_bn_bwd_join", N, C, HW, ws, ws_bytes);
+    if (rc) return rc;
+    DK_REQUIRE(dout && out && x && save_mean && save_invstd && save_scale && save_shift && dx && d_join && dgamma && dbeta,
+               "dk_bn_bwd_join: NULL pointer");
+    rc = bn_fused_bwd(dout, x, save_mean, save_invstd, save_scale, save_shift, dx, dgamma, dbeta, 0, N, C, HW, as_stream(stream),
+                      out, d_join);
+    if (rc != DK_ERR_UNSUPPORTED) return rc;
+    // shapes the resident kernels do not take: the two passes the fusion replaces
+    rc = dk_relu_bwd(dout, out, d_join, (int64_t)N * C * HW, stream);
+    if (rc) return rc;
+    return dk_bn_bwd(d_join, x, gamma, save_mean, save_invstd, save_scale, save_shift, dx, dgamma, dbeta, 0, N, C, HW, ws, ws_bytes,
+                     stream);
+}
+
 int dk_bn_bwd_strided(const float *dy_sub, const float *x, const float *gamma, const float *save_mean,
                       const float *save_invstd, const float *save_scale, const float *save_shift, float *dx, float *dgamma,
                       float *dbeta, int fuse_relu, int N, int C, int H, int W, int stride, void *ws, size_t ws_bytes,

@@ -126,9 +126,11 @@ int bn_fused_init();
 // add != nullptr: y = relu?(x*scale + shift + add) -- the residual join folded into the normalisation pass
 int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int N, int C, int HW, cudaStream_t st,
                  const float *add = nullptr);
+// join_out != nullptr: the gradient is first masked by a ResidualBlock's ReLU, g = dy * (join_out > 0), and g is also written
+// to join_g (the skip path's gradient); relu must be 0 then
 int bn_fused_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
                  const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
-                 cudaStream_t st);
+                 cudaStream_t st, const float *join_out = nullptr, float *join_g = nullptr);
 extern int g_bn_fused_enabled;  // 0: split kernels only; 1: group kernels (small planes) and cluster kernels; 2: cluster kernels only
 
 // bn_group.cu: channel-group kernels for small planes (same contract: DK_ERR_UNSUPPORTED when the shape does not fit)
@@ -137,6 +139,6 @@ int bn_group_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int 
                  const float *add = nullptr);
 int bn_group_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
                  const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
-                 cudaStream_t st);
+                 cudaStream_t st, const float *join_out = nullptr, float *join_g = nullptr);
 
 }  // namespace dk

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(BF_THREADS)
 bn_fused_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dx, const BfGeom g,
                     const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
                     const float *__restrict__ save_scale, const float *__restrict__ save_shift, float *__restrict__ dgamma,
-                    float *__restrict__ dbeta) {
+                    float *__restrict__ dbeta, const float *__restrict__ join_out, float *__restrict__ join_g) {
     extern __shared__ __align__(16) float slice[];
     __shared__ __align__(8) uint64_t bar_mem;
     __shared__ float red[18];
@@ -305,6 +305,51 @@ bn_fused_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, f
     // pass 1: sum(g), sum(g * x_hat); with a fused ReLU the masked gradient is written back for pass 2
     float a = 0.0f, b = 0.0f;
     const int len4 = len & ~3;
+    if (join_out != nullptr) {
+        // ResidualBlock join folded in (host side: bulk planes only, RELU = false): the incoming gradient is first masked by
+        // the block's ReLU, g = dY * (out > 0) with `out` the block's output streamed from global memory (four loads in
+        // flight per thread), kept in the shared-memory slice for pass 2 and written out once for the skip path
+        for (int i0 = 4 * threadIdx.x; i0 < len4; i0 += 16 * BF_THREADS) {
+            float4 m[4];
+            long long goff[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 4 * BF_THREADS;
+                if (i < len4) {
+                    const int v = v0 + i;
+                    const int n = v / g.HW, off = v - n * g.HW;
+                    goff[u] = ((long long)n * g.C + c) * g.HW + off;
+                    m[u] = ld_stream4(join_out + goff[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 4 * BF_THREADS;
+                if (i < len4) {
+                    float4 gq = *reinterpret_cast<const float4 *>(sg + i);
+                    const float4 t = *reinterpret_cast<const float4 *>(sx + i);
+                    gq.x = m[u].x > 0.f ? gq.x : 0.f; gq.y = m[u].y > 0.f ? gq.y : 0.f;
+                    gq.z = m[u].z > 0.f ? gq.z : 0.f; gq.w = m[u].w > 0.f ? gq.w : 0.f;
+                    *reinterpret_cast<float4 *>(sg + i) = gq;
+                    st_stream4(join_g + goff[u], gq);
+                    a += (gq.x + gq.y) + (gq.z + gq.w);
+                    b += (gq.x * ((t.x - mean) * invstd) + gq.y * ((t.y - mean) * invstd)) +
+                         (gq.z * ((t.z - mean) * invstd) + gq.w * ((t.w - mean) * invstd));
+                }
+            }
+        }
+        if ((int)threadIdx.x < len - len4) {
+            const int i = len4 + threadIdx.x;
+            const int v = v0 + i;
+            const int n = v / g.HW, off = v - n * g.HW;
+            const long long goff = ((long long)n * g.C + c) * g.HW + off;
+            const float gv = __ldg(join_out + goff) > 0.f ? sg[i] : 0.f;
+            sg[i] = gv;
+            join_g[goff] = gv;
+            a += gv;
+            b += gv * ((sx[i] - mean) * invstd);
+        }
+    } else {
     for (int i = 4 * threadIdx.x; i < len4; i += 4 * BF_THREADS) {
         float4 gq = *reinterpret_cast<const float4 *>(sg + i);
         const float4 t = *reinterpret_cast<const float4 *>(sx + i);
@@ -327,6 +372,7 @@ bn_fused_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, f
         }
         a += gv;
         b += gv * ((t - mean) * invstd);
+    }
     }
     bf_block_sum2(a, b, red);
     if (threadIdx.x == 0) {
@@ -489,20 +535,23 @@ int bn_fused_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int 
 
 int bn_fused_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
                  const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float *join_out, float *join_g) {
+    if (join_out != nullptr && (relu || join_g == nullptr)) return DK_ERR_UNSUPPORTED;
     {
-        const int rc = bn_group_bwd(dy, x, save_mean, save_invstd, save_scale, save_shift, dx, dgamma, dbeta, relu, N, C, HW, st);
+        const int rc = bn_group_bwd(dy, x, save_mean, save_invstd, save_scale, save_shift, dx, dgamma, dbeta, relu, N, C, HW, st,
+                                    join_out, join_g);
         if (rc != DK_ERR_UNSUPPORTED) return rc;
     }
     const bool bulk = (HW % 4 == 0) && aligned16(x) && aligned16(dy) && aligned16(dx);
+    if (join_out != nullptr && (!bulk || !aligned16(join_out) || !aligned16(join_g))) return DK_ERR_UNSUPPORTED;
     BfGeom g;
     if (!bf_plan(N, C, HW, 2, bulk, &g)) return DK_ERR_UNSUPPORTED;
     const size_t smem = (size_t)((g.per + 3) & ~3) * 8;
     if (relu)
         return bf_launch(bn_fused_bwd_kernel<true>, g, smem, st, dy, x, dx, g, save_mean, save_invstd, save_scale, save_shift,
-                         dgamma, dbeta);
+                         dgamma, dbeta, join_out, join_g);
     return bf_launch(bn_fused_bwd_kernel<false>, g, smem, st, dy, x, dx, g, save_mean, save_invstd, save_scale, save_shift,
-                     dgamma, dbeta);
+                     dgamma, dbeta, join_out, join_g);
 }
 
 }  // namespace dk

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(BG_THREADS)
 bn_group_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, float *__restrict__ dx, const BgGeom g,
                     const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
                     const float *__restrict__ save_scale, const float *__restrict__ save_shift, float *__restrict__ dgamma,
-                    float *__restrict__ dbeta) {
+                    float *__restrict__ dbeta, const float *__restrict__ join_out, float *__restrict__ join_g) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar_mem;
     __shared__ float tot[2 * BG_MAX_G];
@@ -210,7 +210,35 @@ bn_group_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, f
     // pass 1: sum(g), sum(g * x_hat) per column (g = dY, masked by the recomputed ReLU when fused)
     float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
     const int n0 = rg * g.rows, n1 = (n0 + g.rows < g.N) ? n0 + g.rows : g.N;
-    if (active) {
+    if (active && join_out != nullptr) {
+        // ResidualBlock join folded in (RELU = false): g = dY * (out > 0), `out` streamed from global memory four rows
+        // ahead; g replaces dY in the tile (pass 2) and is written out once for the skip path
+        for (int nb = n0; nb < n1; nb += 4) {
+            float4 m[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (nb + u < n1) m[u] = ld_stream4(join_out + ((long long)(nb + u) * g.C + c0) * g.HW + 4 * q);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int n = nb + u;
+                if (n < n1) {
+                    float4 gq = *reinterpret_cast<const float4 *>(tg + (size_t)n * L + 4 * q);
+                    const float4 t = *reinterpret_cast<const float4 *>(tx + (size_t)n * L + 4 * q);
+                    gq.x = m[u].x > 0.f ? gq.x : 0.f; gq.y = m[u].y > 0.f ? gq.y : 0.f;
+                    gq.z = m[u].z > 0.f ? gq.z : 0.f; gq.w = m[u].w > 0.f ? gq.w : 0.f;
+                    *reinterpret_cast<float4 *>(tg + (size_t)n * L + 4 * q) = gq;
+                    st_stream4(join_g + ((long long)n * g.C + c0) * g.HW + 4 * q, gq);
+                    const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+                    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a[e] += gv[e];
+                        b[e] = fmaf(gv[e], (tv[e] - mean[e]) * invstd[e], b[e]);
+                    }
+                }
+            }
+        }
+    } else if (active) {
         for (int n = n0; n < n1; ++n) {
             const float4 gq = *reinterpret_cast<const float4 *>(tg + (size_t)n * L + 4 * q);
             const float4 t = *reinterpret_cast<const float4 *>(tx + (size_t)n * L + 4 * q);
@@ -300,16 +328,17 @@ int bn_group_fwd(const float *x, float *y, const BnFinalize &fin, int relu, int 
 
 int bn_group_bwd(const float *dy, const float *x, const float *save_mean, const float *save_invstd, const float *save_scale,
                  const float *save_shift, float *dx, float *dgamma, float *dbeta, int relu, int N, int C, int HW,
-                 cudaStream_t st) {
+                 cudaStream_t st, const float *join_out, float *join_g) {
     BgGeom g;
     size_t smem;
     if (!aligned16(x) || !aligned16(dy) || !aligned16(dx) || !bg_plan(N, C, HW, 2, &g, &smem)) return DK_ERR_UNSUPPORTED;
+    if (join_out != nullptr && (relu || join_g == nullptr || !aligned16(join_out) || !aligned16(join_g))) return DK_ERR_UNSUPPORTED;
     if (relu)
         bn_group_bwd_kernel<true><<<C / g.G, BG_THREADS, smem, st>>>(dy, x, dx, g, save_mean, save_invstd, save_scale, save_shift,
-                                                                     dgamma, dbeta);
+                                                                     dgamma, dbeta, join_out, join_g);
     else
         bn_group_bwd_kernel<false><<<C / g.G, BG_THREADS, smem, st>>>(dy, x, dx, g, save_mean, save_invstd, save_scale,
-                                                                      save_shift, dgamma, dbeta);
+                                                                      save_shift, dgamma, dbeta, join_out, join_g);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }

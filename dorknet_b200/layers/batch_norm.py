@@ -224,6 +224,20 @@ class BatchNormLayer(Layer):
                       dx.ptr, dg.ptr, db.ptr, 1 if self._relu_fused else 0, N, C, HW, ws, wsn, runtime.stream())
         return dx
 
+    def backward_join(self, upstream_dx, block_out, joined_dx):
+        """ResidualBlock whose branch ends here: joined_dx = upstream_dx * (block_out > 0) (the block's ReLU backward,
+        activations.py:44-47), kept for the skip path, and this layer's backward of it -- in one kernel."""
+        dY = asarray(upstream_dx)
+        self._flush()
+        N, C, HW = self._dims(self.input_shape)
+        base = self._bufs["saved"].ptr
+        dx = self._buf("dx", self.input_shape)
+        dg, db = self._grad("gamma"), self._grad("beta")
+        ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
+        api.dk_bn_bwd_join(dY.ptr, block_out.ptr, self._x.ptr, self._param("gamma").ptr, base, base + 4 * C, base + 8 * C,
+                           base + 12 * C, dx.ptr, joined_dx.ptr, dg.ptr, db.ptr, N, C, HW, ws, wsn, runtime.stream())
+        return dx
+
     # the reference exposes these pieces separately (batch_norm.py:124-174)
     @property
     def std(self):

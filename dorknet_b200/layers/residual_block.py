@@ -3,6 +3,7 @@ from .layer import Layer, api, runtime, asarray
 from .activations import ReLu
 from .depthwise_convolution import DepthwiseConvLayer
 from ..array import LazyBNOutput
+from .batch_norm import BatchNormLayer
 
 
 class ResidualBlock(Layer):
@@ -70,8 +71,18 @@ class ResidualBlock(Layer):
         return regularisation
 
     def backward(self, upstream_dx):
-        joined_dx = self.post_skip_activation.backward(upstream_dx)
-        dx = self.layer_list[-1].backward(joined_dx)
+        act, last = self.post_skip_activation, self.layer_list[-1]
+        if (self.fuse_join and type(act) is ReLu and act._fused_bn is None and type(last) is BatchNormLayer
+                and last.input_dimension == 4 and not last._relu_fused and act._y is not None
+                and tuple(act._y.shape) == tuple(last.input_shape)):
+            # the block's ReLU backward and the last BatchNorm's backward in one kernel; joined_dx is still produced
+            # (the skip path needs it)
+            upstream_dx = asarray(upstream_dx)
+            joined_dx = act._buf("dx", upstream_dx.shape)
+            dx = last.backward_join(upstream_dx, act._y, joined_dx)
+        else:
+            joined_dx = act.backward(upstream_dx)
+            dx = last.backward(joined_dx)
         first = self.layer_list[0]
         for l in self.layer_list[-2:0:-1]:
             dx = l.backward(dx)

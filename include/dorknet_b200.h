@@ -114,6 +114,14 @@ int dk_bn_bwd(const float *dy, const float *x, const float *gamma,
               const float *save_mean, const float *save_invstd, const float *save_scale, const float *save_shift,
               float *dx, float *dgamma, float *dbeta, int fuse_relu,
               int N, int C, int HW, void *ws, size_t ws_bytes, dk_stream_t stream);
+/* Backward of a ResidualBlock join folded into the backward of the branch's last BatchNorm
+ * (residual_block.py:86-88: joined_dx = post_skip_activation.backward(upstream_dx); layer_list[-1].backward(joined_dx)):
+ * d_join = dout * (out > 0) with `out` the block's output (activations.py:44-47), written once for the skip path, and
+ * (dx, dgamma, dbeta) = BatchNorm backward of d_join -- one pass over (dout, out, x) instead of two kernels. */
+int dk_bn_bwd_join(const float *dout, const float *out, const float *x, const float *gamma,
+                   const float *save_mean, const float *save_invstd, const float *save_scale,
+                   const float *save_shift, float *dx, float *d_join, float *dgamma, float *dbeta,
+                   int N, int C, int HW, void *ws, size_t ws_bytes, dk_stream_t stream);
 /* The same for the upstream gradient of a stride-2 pointwise convolution taken in its COMPACT form
  * dy_sub[N, C, H/2, W/2] (= the non-zero entries of the zero-stuffed gradient, pointwise_convolution.py:68-72:
  * dy[n,c,2i,2j] = dy_sub[n,c,i,j], 0 elsewhere).  Results are those of dk_bn_bwd on the zero-stuffed tensor.
