@@ -347,6 +347,18 @@ def rmsprop_update(w, g, c, lr, decay):
 
 
 # ----------------------------------------------------------------------------- data (next row, §8f-1)
+def input_u8_nhwc(img, img_b=None, lam=0.0, sub=128.0):
+    """Decoded uint8 NHWC batch -> the fp32 NCHW network input: data_loading/image_preprocessor.py:36-37
+    (`im.astype(np.float32).transpose(2,0,1); im -= 128.0` per image), and with a second batch the loader's mixup
+    X = lam*X_b + (1-lam)*X_a (data_loading/image_data_loader.py:100-105).  What dk_input_u8_nhwc does on the device."""
+    Xa = np.ascontiguousarray(np.asarray(img).astype(np.float32).transpose(0, 3, 1, 2)) - np.float32(sub)
+    if img_b is None:
+        return Xa
+    Xb = np.ascontiguousarray(np.asarray(img_b).astype(np.float32).transpose(0, 3, 1, 2)) - np.float32(sub)
+    lam = np.float32(lam)
+    return lam * Xb + (1 - lam) * Xa
+
+
 def mixup(Xa, Xb, ya, yb, lam):
     """data_loading/image_data_loader.py:100-112: X = lam*X_b + (1-lam)*X_a (same for labels)."""
     return lam * Xb + (1 - lam) * Xa, lam * yb + (1 - lam) * ya

@@ -290,7 +290,28 @@ def _net_case_body(name):
     save(name, **out)
 
 
+def input_case():
+    """The reference loader's per-image arithmetic after decoding (data_loading/image_preprocessor.py:16-39 with
+    crop_mode=None on images that already have the target size: cv2.resize to the same size is the identity, then
+    astype(float32).transpose(2,0,1) - 128) and its mixup (image_data_loader.py:100-110), from the live reference."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_image_preprocessor", "/root/reference/data_loading/image_preprocessor.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = rng(90)
+    N, S, C = 3, 17, 3
+    pre = mod.ImagePreprocessor(image_size=(S, S), crop_mode=None)
+    img_a = g.integers(0, 256, size=(N, S, S, C), dtype=np.uint8)
+    img_b = g.integers(0, 256, size=(N, S, S, C), dtype=np.uint8)
+    Xa = np.stack([pre.preprocess_image(im.copy()) for im in img_a], axis=0)
+    Xb = np.stack([pre.preprocess_image(im.copy()) for im in img_b], axis=0)
+    lam = np.float32(0.2173)
+    mixed = lam * Xb + (1 - lam) * Xa  # image_data_loader.py:105 with mixup_prop = lam
+    save("input_pipeline", img_a=img_a, img_b=img_b, Xa=f32(Xa), lam=np.float32(lam), X_mixed=f32(mixed))
+
+
 def main():
+    input_case()
     conv_case("conv_k3s1p1", 2, 3, 9, 10, 4, 3, 1, 1, False, 0.0, 1)
     conv_case("conv_k5s2p1_half", 2, 3, 10, 12, 5, 5, 2, 1, True, 0.01, 2)   # (10+2-5)/2 = 3.5 -> floor
     conv_case("conv_k4s2p1", 2, 4, 8, 8, 6, 4, 2, 1, False, 1e-4, 3)         # MNIST 4x4 s2

@@ -67,3 +67,35 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the structs that cross the C ABI have the header's size and field offsets (checked with
+    gcc on include/dorknet_b200.h: no GPU, no CUDA toolkit needed)."""
+    import shutil
+    import subprocess
+    from dorknet_b200 import _lib
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    fields = {"dk_opt_tensor": (_lib.OptTensor, ["param", "grad", "state", "n"]),
+              "dk_p2p_ctx": (_lib.P2PCtx, ["world", "rank", "grad_delta", "ready", "done", "epoch"])}
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "dorknet_b200.h"', "int main(void) {"]
+    for name, (_, fl) in fields.items():
+        src.append('printf("%s %%zu", sizeof(%s));' % (name, name))
+        for f in fl:
+            src.append('printf(" %%zu", offsetof(%s, %s));' % (name, f))
+        src.append('printf("\\n");')
+    src += ["return 0;", "}"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    for line in out:
+        if not line.strip():
+            continue
+        name, size, *offs = line.split()
+        cls, fl = fields[name]
+        assert ctypes.sizeof(cls) == int(size), name
+        assert [getattr(cls, f).offset for f in fl] == [int(o) for o in offs], name

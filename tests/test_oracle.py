@@ -1,6 +1,8 @@
 """The oracle (oracle/oracle.py + oracle/dk_oracle.c) against the golden vectors generated
 from the live reference (tests/golden/make_golden.py) and, when oracle/_ref is built, against
 the reference's own compiled kernels directly.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -130,6 +132,25 @@ def test_optimisers(golden):
                 else:
                     w, state = O.rmsprop_update(w, g, state, 0.01, 0.9)
                 close(w, d["%s%d" % (key, i + 1)])
+
+
+def test_input_pipeline_golden(golden):
+    """uint8 NHWC -> fp32 NCHW - 128 (+ mixup) against the live reference's ImagePreprocessor / loader arithmetic."""
+    d = golden("input_pipeline")
+    assert np.array_equal(O.input_u8_nhwc(d["img_a"]), d["Xa"])
+    close(O.input_u8_nhwc(d["img_a"], d["img_b"], float(d["lam"])), d["X_mixed"], rtol=1e-6, atol=1e-5)
+
+
+def test_synthetic_batches_are_the_oracle_of_their_uint8_form():
+    """bench.py's device-resident fp32 batches and its uint8 host batches (e2e) describe the same images."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from dorknet_b200 import workloads as W
+    for mix in (False, True):
+        raw = W.synthetic_batch_u8(3, 3, 11, 7, seed=4, mixup=mix)
+        X, y, Y = W.synthetic_batch(3, 3, 11, 7, seed=4, mixup=mix)
+        close(X, O.input_u8_nhwc(raw["img"], raw.get("img_b"), raw.get("lam", 0.0)), rtol=1e-6, atol=1e-5)
+        assert np.array_equal(Y, raw["Y"]) and np.array_equal(y, raw["y"])
 
 
 def test_mixup_identity():
