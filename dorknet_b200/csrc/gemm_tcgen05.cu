@@ -230,6 +230,23 @@ struct MatrixTransposedKM {
     __device__ __forceinline__ const float *ptr(int r, const KCol &c) const { return (c.ok && r < R) ? w + c.off + r : nullptr; }
 };
 
+// Rows of a dense [B][R][P] tensor (P % 4 == 0, 16-byte aligned) as a K-major operand, copied by the loader warps with
+// 16-byte cp.async -- not because TMA could not describe it, but to take this operand OFF the TMA unit: with 128-byte box
+// rows the TMA stream of a CTA tops out near 25 GB/s per SM, and a wgrad whose two operands both stream from HBM is bound
+// by it.  One operand through TMA, the other through the LSU path lets the two engines share the load.
+struct RowsVecKM {
+    static constexpr bool kGather = true;
+    static constexpr bool kMN = false;
+    static constexpr bool kVec16 = true;
+    const float *src;
+    int R, P;
+    struct KCol { long long off; bool ok; };
+    __device__ __forceinline__ KCol kcol(int b, int k) const { return KCol{(long long)b * R * P + k, k < P}; }
+    __device__ __forceinline__ const float *ptr(int r, const KCol &c) const { return (c.ok && r < R) ? src + c.off + (long long)r * P : nullptr; }
+};
+template <class G, class = void> struct is_vec16 { static constexpr bool value = false; };
+template <class G> struct is_vec16<G, decltype((void)G::kVec16)> { static constexpr bool value = G::kVec16; };
+
 constexpr int TC_GATHER_THREADS = TC_THREADS + 128;
 
 template <class AG, class BG>
@@ -465,7 +482,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
-                    if constexpr (BG::kGather) {
+                    if constexpr (is_vec16<BG>::value) {
+                        // 16-byte chunks: lane & 7 = chunk of the 128-byte row, (lw, lane >> 3) = row within 16
+                        const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
+                        const int j = lane & 7, rb = lw * 4 + (lane >> 3);
+                        const auto kc = bg.kcol(bbB, k0 + 4 * j);
+                        for (int r = rb; r < p.bn; r += 16)
+                            cp_async_16(sB + (uint32_t)r * 128u + ((uint32_t)(j ^ (r & 7)) << 4), bg.ptr(n0 + r, kc), safe);
+                    } else if constexpr (BG::kGather) {
                         static_assert(!BG::kMN, "gathered B operands are K-major");
                         const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
                         const auto kc = bg.kcol(bbB, k0 + lane);
@@ -624,6 +648,7 @@ static int g_mn_layout = LAYOUT_SW128_BASE32B, g_mn_lbo = 4096, g_mn_sbo = 512, 
 static int g_mn_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
 static int g_l2_promo = (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
 static int g_smem_budget = TC_SMEM_BUDGET;  // bytes of operand stages per CTA
+static int g_hybrid_wgrad = 0;               // 1: pointwise wgrad takes X through 16-byte cp.async loaders, dY through TMA
 static int g_wide_items = 0;                 // wgrad k-blocks per item: 0 = automatic (pw_wgrad), 1 / 2 / 4 = forced
 static int g_two_per_sm = 1;                 // see tc_launch
 static int g_ctas_per_sm = 1;                // persistent CTAs per SM the grids / split plans are sized for
@@ -640,6 +665,7 @@ int init_gemm_tcgen05() {
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     if (const char *m = getenv("DK_TC_DISABLE_MASK")) g_tc_disable_mask = atoi(m);  // diagnostics
+    if (const char *m = getenv("DK_HYBRID_WGRAD")) g_hybrid_wgrad = atoi(m);
     g_tc_ready = true;
     return DK_OK;
 }
@@ -930,7 +956,8 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     q.M = F; q.N = C; q.K = (int)P; q.batches = N;
     fill_common(q);
     bool a_tma = tma_ok(dy, P), b_tma = (s == 1) && tma_ok(x, P);
-    if (a_tma && b_tma) {
+    const bool hybrid = g_hybrid_wgrad && a_tma && b_tma;
+    if (a_tma && b_tma && !hybrid) {
         // wide pipeline items for long planes: 4 (or 2) consecutive k-blocks per item, if at least two stages still fit and
         // the rounding of the plane to whole items wastes little
         const int kb0 = q.k_blocks, one = TC_A_BYTES + q.bn * TC_BK * 4;
@@ -989,7 +1016,8 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     if (b_tma) rc = make_map(&tb, x, pb, C, N, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const PixelGatherKM ga{dy, F, OH, OW, OW, (int)P, 1}, gb{x, C, H, W, OW, (int)P, s};
-    if (a_tma && b_tma) rc = tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+    if (hybrid) rc = tc_launch(ta, tb, q, NoGather{}, RowsVecKM{x, C, (int)P}, st);
+    else if (a_tma && b_tma) rc = tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
     else if (a_tma) rc = tc_launch(ta, tb, q, NoGather{}, gb, st);
     else rc = tc_launch(ta, tb, q, ga, gb, st);
     if (rc) return rc;
@@ -1175,6 +1203,7 @@ int dk_tc_debug_set(int key, int value) {
             dk::g_ctas_per_sm = value;
             dk::g_smem_budget = value >= 2 ? 98 * 1024 : dk::TC_SMEM_BUDGET;
             break;
+        case 16: dk::g_hybrid_wgrad = value; break;  // pointwise wgrad: X through the LSU path (16-byte cp.async), dY through TMA
         case 15: dk::g_wide_items = value; break;  // wgrad k-blocks per pipeline item (0 automatic)
         case 14: dk::g_two_per_sm = value; break;  // 0: forward / dgrad GEMMs never run two CTAs per SM
         case 11: dk::g_short_a = value; break;  // 0: wgrad dY boxes always 128 rows

@@ -159,6 +159,12 @@ __device__ __forceinline__ void cp_async_f32(uint32_t dst, const float *src, con
     const float *q = src ? src : safe;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
 }
+// asynchronous 16-byte global -> shared copy, L2 only; src == nullptr writes zeros
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const float *src, const float *safe) {
+    const uint32_t n = src ? 16u : 0u;
+    const float *q = src ? src : safe;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(q), "r"(n) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_pending(int n) {  // wait until at most n groups are still in flight
     switch (n) {

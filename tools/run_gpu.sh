@@ -1,8 +1,6 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t37.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t37.log
-tail -8 gpurun_out/t37.log
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r1ba.json 2> gpurun_out/bench_r1ba.err; tail -3 gpurun_out/bench_r1ba.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_r1ba.json')); print(round(d['value']), d['ms_per_step'], round(d['e2e']['value']), d['final_loss'], d['gpu_launches'])"
+DK_HYBRID_WGRAD=1 timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_golden.py -m gpu -x -q -k "pointwise or mini" > gpurun_out/t38.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t38.log
+tail -4 gpurun_out/t38.log
+timeout 200 python tests/pw_sweep.py 64 16=0,1 wgrad > gpurun_out/pw_sweep_hybrid.log 2>&1; grep "s=1" gpurun_out/pw_sweep_hybrid.log
