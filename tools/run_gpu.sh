@@ -1,6 +1,4 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/t39.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t39.log
-tail -3 gpurun_out/t39.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 300 python bench.py > gpurun_out/r01bc_bench.json 2> gpurun_out/r01bc_bench.err; tail -2 gpurun_out/r01bc_bench.err; cut -c1-200 gpurun_out/r01bc_bench.json
