@@ -94,6 +94,8 @@ PW_CASES = [
     (2, 64, 64, 8, 16, 1), (3, 64, 128, 28, 28, 1), (2, 256, 256, 14, 14, 1), (2, 40, 48, 10, 10, 1),
     (2, 64, 64, 14, 14, 2), (2, 64, 128, 15, 15, 2), (2, 256, 512, 7, 7, 1), (3, 512, 512, 7, 7, 1),
     (2, 64, 64, 112, 112, 2), (2, 24, 40, 9, 7, 3), (2, 6, 10, 5, 5, 1),
+    # cfg5 (MobileNet stack) channel counts: 512 -> 1024 and 1024 -> 1024 at 7x7, and 1024 at 14x14 planes
+    (2, 512, 1024, 7, 7, 1), (3, 1024, 1024, 7, 7, 1), (2, 1024, 512, 14, 14, 1),
 ]
 
 
@@ -136,6 +138,9 @@ CONV_CASES = [
     # stride 1 with 5 columns, clipped top / bottom rows, OW not a multiple of 4 (forward only takes it)
     (4, 3, 225, 225, 64, 5, 2, 1), (4, 3, 224, 224, 16, 5, 2, 2), (4, 2, 30, 30, 8, 5, 1, 2), (4, 3, 19, 19, 8, 3, 1, 0),
     (8, 3, 31, 31, 40, 3, 2, 1),
+    # cfg2's layer at its real plane size (3x3 64 -> 64 at 56x56), the MNIST stack's layers at theirs (cfg1)
+    (2, 64, 56, 56, 64, 3, 1, 1), (3, 32, 28, 28, 32, 3, 1, 1), (3, 32, 28, 28, 64, 4, 2, 1), (3, 64, 14, 14, 64, 3, 1, 1),
+    (3, 64, 14, 14, 128, 4, 2, 1),
 ]
 
 
@@ -210,7 +215,7 @@ def test_full_size_properties_resnet_shapes():
     assert abs(lhs - rhs) <= 2e-3 * abs(rhs)
 
 
-@pytest.mark.parametrize("case", [(64, 512, 120), (8, 128, 12), (130, 64, 300)])
+@pytest.mark.parametrize("case", [(64, 512, 120), (8, 128, 12), (130, 64, 300), (16, 1024, 120)])
 def test_dense_tcgen05_vs_oracle(O, case):
     """DenseLayer on the tensor-core path (in/out multiples of 4): fwd, dX, dW (+l2), db."""
     from dorknet_b200 import _lib
