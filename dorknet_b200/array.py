@@ -158,15 +158,30 @@ class LazyBNOutput(LazyDeviceArray):
     apply+ReLU pass instead of two (and tells the BatchNorm to mask its backward); any other consumer materialises
     the plain y = x*scale + shift on first use."""
 
-    __slots__ = ("bn",)
+    __slots__ = ("bn", "_consumed")
 
     def __init__(self, buf, thunk, bn):
         super().__init__(buf, thunk)
         self.bn = bn
+        self._consumed = False
+
+    @property
+    def fusable(self):
+        """True while nothing has been launched for this output and no fused consumer has taken it."""
+        return self._thunk is not None and not self._consumed
 
     def consume(self):
-        """Mark as consumed by a fused kernel: the plain y will never be produced."""
-        self._thunk = None
+        """A fused kernel (BatchNorm+ReLU, BatchNorm+join) took this output and writes its own buffer.  The plain
+        y = x*scale + shift is still owed to any OTHER reader -- an identity skip of a ResidualBlock whose branch starts
+        with a ReLu, a user calling .get() -- as the reference returns a real array there: on first read the statistics
+        pass runs if it has not (flushing the fused consumer into its buffer), then y is applied from the saved values."""
+        self._consumed = True
+        bn, buf = self.bn, self._buf
+
+        def late_reader():
+            bn._flush()
+            bn.apply_saved(buf, 0)
+        self._thunk = late_reader
 
 
 class LazyReluOutput(LazyDeviceArray):
@@ -245,16 +260,48 @@ def asnumpy(a):
     return np.asarray(a)
 
 
+class _Epoch:
+    """The lifetime of one set of values in the slot arena: from the first l2 / loss kernel of a step until the next
+    step overwrites them.  sealed = a snapshot of the arena (pinned host copy + event) was enqueued right after the
+    step's loss kernel; DeviceScalars of a sealed epoch read THAT copy, so they keep their value for ever."""
+
+    __slots__ = ("seq", "host", "ev")
+    _count = 0
+
+    def __init__(self):
+        _Epoch._count += 1
+        self.seq = _Epoch._count
+        self.host = None
+        self.ev = None
+
+    @property
+    def sealed(self):
+        return self.host is not None
+
+    def values(self):
+        self.ev.synchronize()
+        return self.host.numpy()
+
+    def __del__(self):
+        try:
+            if self.host is not None:
+                _SlotArena._free_hosts.append(self.host)
+        except Exception:  # interpreter shutdown
+            pass
+
+
 class _SlotArena:
     """One small device buffer holding every one-float result slot (loss, l2 terms), so reading a
     DeviceScalar is ONE device->host copy however many terms it has."""
 
     SIZE = 4096
+    _free_hosts = []
 
     def __init__(self):
         self.buf = None
         self.used = 0
         self.host = None
+        self.epoch = _Epoch()
 
     def alloc(self):
         torch = _torch()
@@ -276,21 +323,28 @@ class _SlotArena:
         torch.cuda.current_stream().synchronize()
         return self.host.numpy()
 
-
     def read_async(self):
         """Enqueue a snapshot of all slots into its own pinned buffer on the current stream; returns (host tensor,
         event).  The host can keep launching: it reads the snapshot once the event has fired."""
         torch = _torch()
         n = max(self.used, 1)
-        host = torch.empty(n, dtype=torch.float32).pin_memory() if not self._free_hosts else self._free_hosts.pop()
-        if host.numel() < n:
-            host = torch.empty(n, dtype=torch.float32).pin_memory()
+        host = self._free_hosts.pop() if self._free_hosts else None
+        if host is None or host.numel() < n:
+            host = torch.empty(max(n, 256), dtype=torch.float32).pin_memory()
         host[:n].copy_(self.buf[:n], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         return host, ev
 
-    _free_hosts = []
+    def seal(self):
+        """End the current epoch: snapshot the arena behind everything enqueued so far and open a new epoch (called by
+        the loss layer after its kernel, and by GraphedTrainStep after a replay).  Returns the sealed epoch.  Not legal
+        while the stream is being captured (events recorded there never fire): callers check."""
+        ep = self.epoch
+        if self.buf is not None:
+            ep.host, ep.ev = self.read_async()
+            self.epoch = _Epoch()
+        return ep
 
 
 _arena = _SlotArena()
@@ -299,19 +353,13 @@ _arena = _SlotArena()
 class PendingScalar:
     """Result of DeviceScalar.fetch_async(): the device -> host copy is in flight; result() waits for it only."""
 
-    __slots__ = ("_terms", "_const", "_host", "_ev")
+    __slots__ = ("_scalar",)
 
-    def __init__(self, terms, const, host, ev):
-        self._terms, self._const, self._host, self._ev = terms, const, host, ev
+    def __init__(self, scalar):
+        self._scalar = scalar
 
     def result(self):
-        self._ev.synchronize()
-        snap = self._host.numpy()
-        total = np.float64(self._const)
-        for slot, coeff in self._terms:
-            total += coeff * float(snap[slot])
-        _SlotArena._free_hosts.append(self._host)
-        return float(total)
+        return float(self._scalar)
 
 
 def alloc_scalar_slot():
@@ -319,26 +367,66 @@ def alloc_scalar_slot():
     return _arena.alloc()
 
 
-class DeviceScalar:
-    """A lazily-evaluated float living on the device: sum_i coeff_i * slot_i + const.
+def current_epoch():
+    return _arena.epoch
 
-    The loss (losses.py:23-27) and every layer's l2 term (regularisers/l2.py:12-14) are produced by
-    kernels into one-float device slots; `network.forward` adds them up with Python `+`
-    (feed_forward_network.py:59-60), which here only concatenates term lists -- no kernel, no sync.
-    float(x) synchronises once and reads the slots.
+
+def seal_epoch():
+    return _arena.seal()
+
+
+class DeviceScalar:
+    """A float produced on the device: sum_i coeff_i * slot_i + const.
+
+    The loss (losses.py:23-27) and every layer's l2 term (regularisers/l2.py:12-14) are produced by kernels into
+    one-float device slots; `network.forward` adds them up with Python `+` (feed_forward_network.py:59-60), which
+    here only concatenates term lists -- no kernel, no sync.
+
+    VALUE SEMANTICS.  The slots are rewritten by every step, so a scalar belongs to an epoch of the arena (_Epoch).
+    The loss layer seals the epoch right after its kernel (an asynchronous 16 KB device -> host snapshot + event), so
+    the loss a training loop holds keeps the value of ITS step: float(x) waits for that snapshot only (never for later
+    steps), and arithmetic between scalars of different steps -- the reference loop's
+    `running = 0.9*running + 0.1*loss` (examples/imagenet_dogs_225_resnet_18_depsep.py:222-226) -- folds the older
+    one into the constant, so term lists do not grow.  Scalars of a still-open epoch (a regulariser term read on its
+    own, anything created under CUDA-graph capture) read the device when converted.
     """
 
-    __slots__ = ("terms", "const")
+    __slots__ = ("terms", "const", "epoch")
     __array_priority__ = 100.0
 
-    def __init__(self, terms=(), const=0.0):
+    def __init__(self, terms=(), const=0.0, epoch=None):
         self.terms = list(terms)  # [(slot, coeff)]: slot = arena index (int) or any object with .get()
         self.const = float(const)
+        self.epoch = epoch if epoch is not None else (_arena.epoch if any(isinstance(s, int) for s, _ in self.terms) else None)
+
+    def _resolved(self):
+        """(const, non-arena terms) with every arena term of a SEALED epoch folded into the constant."""
+        vals = self.epoch.values()
+        c = np.float64(self.const)
+        rest = []
+        for slot, coeff in self.terms:
+            if isinstance(slot, int):
+                c += coeff * float(vals[slot])
+            else:
+                rest.append((slot, coeff))
+        return float(c), rest
 
     def _combine(self, other, sign=1.0):
-        if isinstance(other, DeviceScalar):
-            return DeviceScalar(self.terms + [(s, sign * c) for s, c in other.terms], self.const + sign * other.const)
-        return DeviceScalar(self.terms, self.const + sign * float(other))
+        if not isinstance(other, DeviceScalar):
+            return DeviceScalar(self.terms, self.const + sign * float(other), self.epoch)
+        a_terms, a_const, a_ep = self.terms, self.const, self.epoch
+        b_terms, b_const, b_ep = [(s, sign * c) for s, c in other.terms], sign * other.const, other.epoch
+        if a_ep is not None and b_ep is not None and a_ep is not b_ep:
+            # two different steps: the older (sealed) one becomes a number
+            if a_ep.sealed and (not b_ep.sealed or a_ep.seq < b_ep.seq):
+                a_const, a_terms = self._resolved()
+                a_ep = None
+            elif b_ep.sealed:
+                c, rest = other._resolved()
+                b_const, b_terms, b_ep = sign * c, [(s, sign * k) for s, k in rest], None
+            else:
+                raise RuntimeError("DeviceScalars of two open epochs cannot be combined")
+        return DeviceScalar(a_terms + b_terms, a_const + b_const, a_ep if a_ep is not None else b_ep)
 
     def __add__(self, other):
         return self._combine(other)
@@ -348,17 +436,30 @@ class DeviceScalar:
     def __sub__(self, other):
         return self._combine(other, -1.0)
 
+    def __rsub__(self, other):
+        return (self * -1.0)._combine(other)
+
     def __mul__(self, k):
         k = float(k)
-        return DeviceScalar([(s, c * k) for s, c in self.terms], self.const * k)
+        return DeviceScalar([(s, c * k) for s, c in self.terms], self.const * k, self.epoch)
 
     __rmul__ = __mul__
 
+    def __truediv__(self, k):
+        return self * (1.0 / float(k))
+
+    def rebind(self, epoch):
+        """The same expression over another epoch's values (GraphedTrainStep: one captured loss, one epoch per replay)."""
+        return DeviceScalar(self.terms, self.const, epoch)
+
     def __float__(self):
-        from .regularisers.l2 import flush_pending
-        flush_pending()
         total = np.float64(self.const)
         snap = None
+        if self.epoch is not None and self.epoch.sealed:
+            snap = self.epoch.values()
+        else:
+            from .regularisers.l2 import flush_pending
+            flush_pending()
         for slot, coeff in self.terms:
             if isinstance(slot, int):
                 if snap is None:
@@ -371,18 +472,15 @@ class DeviceScalar:
     def fetch_async(self):
         """Start the device -> host read of this value behind whatever is enqueued on the current stream and return a
         PendingScalar; the caller keeps launching work and calls .result() later (a training loop reads the loss of
-        step i while step i+1 runs, instead of draining the GPU every step)."""
-        from .regularisers.l2 import flush_pending
-        flush_pending()
-        if any(not isinstance(slot, int) for slot, _ in self.terms):
-            v = float(self)
-
-            class _Done:
-                def result(self_inner):
-                    return v
-            return _Done()
-        host, ev = _arena.read_async()
-        return PendingScalar(list(self.terms), self.const, host, ev)
+        step i while step i+1 runs, instead of draining the GPU every step).  A scalar of a sealed epoch already has
+        its snapshot in flight: nothing more is enqueued."""
+        if self.epoch is not None and not self.epoch.sealed and self.epoch is _arena.epoch:
+            import torch
+            if not torch.cuda.is_current_stream_capturing():
+                from .regularisers.l2 import flush_pending
+                flush_pending()
+                return PendingScalar(self.rebind(_arena.seal()))
+        return PendingScalar(self)
 
     def get(self):
         return np.float32(float(self))
@@ -395,3 +493,16 @@ class DeviceScalar:
 
     def __format__(self, spec):
         return format(float(self), spec)
+
+    # comparisons / printing in user loops (`if loss < best:`) resolve to the value
+    def __lt__(self, o):
+        return float(self) < float(o)
+
+    def __gt__(self, o):
+        return float(self) > float(o)
+
+    def __le__(self, o):
+        return float(self) <= float(o)
+
+    def __ge__(self, o):
+        return float(self) >= float(o)

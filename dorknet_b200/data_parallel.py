@@ -46,6 +46,25 @@ def init_process_group(backend=None):
     return dist.get_rank(), dist.get_world_size()
 
 
+def backward_order(network):
+    """Parameter layers in the order their backward() RUNS (and so writes gradients): top-level layers last to first; inside
+    a ResidualBlock layer_list[-1] ... layer_list[1], THEN the skip projection, then layer_list[0]
+    (layers/residual_block.py backward: the skip path is taken before the first branch layer so that its gradient can be
+    folded into that layer's kernel; a one-layer branch runs before the skip).  A bucket may only be exchanged once the LAST
+    layer in this order that writes into it has been enqueued."""
+    out = []
+    for l in reversed(list(network.layers)):
+        if hasattr(l, "layer_list"):
+            ll = [m for m in l.layer_list]
+            skip = getattr(l, "skip_projection", None)
+            seq = list(reversed(ll[1:])) + ([skip] if skip is not None else []) + ll[:1] if len(ll) > 1 else ll + (
+                [skip] if skip is not None else [])
+            out.extend(m for m in seq if getattr(m, "learned_params", None))
+        elif getattr(l, "learned_params", None):
+            out.append(l)
+    return out
+
+
 def plan_buckets(sizes, num_buckets):
     """Cut a list of tensor sizes (already in reverse execution order) into <= num_buckets contiguous
     groups of roughly equal bytes.  Returns a list of (first_index, last_index_exclusive)."""
@@ -165,10 +184,10 @@ class DataParallel:
         self._pending = []
         self.hooks_enabled = True  # GraphedTrainStep switches the backward hooks off for its between-graphs fallback
         self.device = device  # None: the process's B200; tests pass torch.device("cpu") with the gloo backend
-        # parameter layers in REVERSE execution order = the order backward produces gradients
-        layers = list(iter_param_layers(network, include_skip=True))
+        # parameter layers in the order backward produces their gradients (skip projections where they really run)
+        assert {id(l) for l in backward_order(network)} == {id(l) for l in iter_param_layers(network, include_skip=True)}
         self.entries = []  # (layer, key)
-        for layer in reversed(layers):
+        for layer in backward_order(network):
             if hasattr(layer, "_ensure_gpu") and device is None:
                 layer._ensure_gpu()
             for k in layer.learned_params.keys():
@@ -224,6 +243,15 @@ class DataParallel:
             return
         for layer, k in self.entries:
             self.dist.broadcast(layer.learned_params[k].t, src=src, group=self.group)
+        seen = set()
+        for layer, _ in self.entries:
+            nl = getattr(layer, "non_learned_params", None)
+            if nl and id(layer) not in seen:
+                seen.add(id(layer))
+                for k in ("running_mean", "running_std"):
+                    v = dict.get(nl, k)  # (no flush of a deferred forward: plain dict access)
+                    if v is not None and hasattr(v, "t"):
+                        self.dist.broadcast(v.t, src=src, group=self.group)
 
     # -- overlap: all-reduce a bucket as soon as its last gradient has been enqueued -------------------
     def _install_hooks(self):
@@ -249,8 +277,9 @@ class DataParallel:
         self._pending.append(work)
 
     def begin_step(self):
-        """Call before the first kernel of a step that writes gradients (p2p mode: wait until every peer has read the
-        previous step's)."""
+        """Kept for callers of the first release: the "every peer has read my gradients" wait is now enqueued by the
+        optimiser right behind the exchange kernel (optimisers/_multi.py), so a plain loop `forward; backward; dp.step()`
+        is safe without it.  Calling it is harmless (the flags already carry the current epoch: no spin)."""
         if self.p2p is not None:
             self.p2p.wait_done()
 

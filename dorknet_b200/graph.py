@@ -103,7 +103,11 @@ class GraphedTrainStep:
         if self.dp is not None and not self.dp_in_graph:
             self.dp.finish()
             self._opt_graph.replay()
-        return entry[1]
+        # the captured loss names arena slots that every replay rewrites: hand out THIS step's values (an asynchronous
+        # 16 KB snapshot right behind the replay; array.DeviceScalar), so a held loss keeps its value
+        from .array import DeviceScalar, seal_epoch
+        loss = entry[1]
+        return loss.rebind(seal_epoch()) if isinstance(loss, DeviceScalar) else loss
 
     def _capture_whole(self, X, Y):
         """forward + backward (+ bucketed all-reduces on NCCL's stream) + optimiser in ONE graph"""

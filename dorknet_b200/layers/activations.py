@@ -21,7 +21,7 @@ class ReLu(Layer):
         X = asarray(X)
         y = self._buf("y", X.shape)
         self._fused_bn = None
-        if isinstance(X, LazyBNOutput) and not X.is_materialised and not test_mode:
+        if isinstance(X, LazyBNOutput) and X.fusable and not test_mode:
             # BatchNorm -> ReLU: one pass y = relu(x*scale + shift); backward: the BatchNorm masks dY itself.  The pass
             # is launched when the consumer reads the result (a strided pointwise consumer asks for less: LazyReluOutput)
             bn = X.bn

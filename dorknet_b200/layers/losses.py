@@ -1,6 +1,6 @@
 """SoftmaxWithCrossEntropy (reference: layers/losses.py:5-41)."""
 from .layer import Layer, api, runtime, asarray, DeviceScalar
-from ..array import alloc_scalar_slot
+from ..array import alloc_scalar_slot, current_epoch, seal_epoch
 from ..regularisers.l2 import flush_pending
 
 
@@ -34,7 +34,12 @@ class SoftmaxWithCrossEntropy(Layer):
         loss, idx = self._loss_slot
         api.dk_softmax_xent_fwd(X.ptr, self.y_one_hot.ptr, p.ptr, loss.ptr, B, K, runtime.stream())
         self.downstream_x = p
-        return DeviceScalar([(idx, 1.0)]), p
+        # the step's scalar results (this loss + the l2 terms flushed above) are complete: snapshot them, so that the
+        # value the caller holds is the value of THIS step (array.DeviceScalar).  Under stream capture nothing can be
+        # snapshotted (GraphedTrainStep seals after every replay instead).
+        import torch
+        ep = current_epoch() if torch.cuda.is_current_stream_capturing() else seal_epoch()
+        return DeviceScalar([(idx, 1.0)], 0.0, ep), p
 
     def backward(self, upstream_dx=None):
         """(p - y)/B (losses.py:29-34); upstream_dx is not used."""

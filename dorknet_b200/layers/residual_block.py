@@ -50,7 +50,7 @@ class ResidualBlock(Layer):
                 raise ValueError("operands could not be broadcast together with shapes {} {}".format(
                     X_tmp.shape, skippee.shape))
             y = act._buf("y", X_tmp.shape)
-            if (isinstance(X_tmp, LazyBNOutput) and not X_tmp.is_materialised and not test_mode and self.fuse_join):
+            if (isinstance(X_tmp, LazyBNOutput) and X_tmp.fusable and not test_mode and self.fuse_join):
                 # the branch ends in a BatchNorm whose normalisation pass has not run: it adds the skip and applies
                 # the ReLU itself (one pass over the activation instead of three)
                 X_tmp.bn.fused_add_relu_apply(y, skippee)  # (a lazy skip output materialises on .ptr)

@@ -60,6 +60,10 @@ class MultiTensorOptimiser:
             return
         if self._p2p is not None:
             api.dk_opt_multi_p2p(kind, tab, n, max_n, self.push_hyper(), self._p2p.ctx_ptr, runtime.stream())
+            # nobody may overwrite gradients a peer is still reading over NVLink: the "all peers have read mine" wait
+            # belongs to the exchange, not to the caller's loop -- enqueued here, right behind the kernel, it orders
+            # every later backward of this stream whatever loop drives the step
+            self._p2p.wait_done()
         else:
             plain(tab, n, max_n)
 
@@ -113,9 +117,14 @@ class MultiTensorOptimiser:
         vals = (float(self.learning_rate), float(self._second_hyper()), float(self.grad_scale))
         if self._hyper is None:
             self._hyper = torch.zeros(4, dtype=torch.float32, device=runtime.device())
-            self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._hyper_host = []
         if vals != self._hyper_vals:
-            self._hyper_host[0], self._hyper_host[1], self._hyper_host[2] = vals
-            self._hyper.copy_(self._hyper_host, non_blocking=True)
+            # a FRESH pinned staging buffer per change: an earlier non_blocking copy may still be queued, and rewriting
+            # the buffer it reads from would let a learning-rate change land one step early.  Changes are rare (per
+            # epoch); the last few buffers are kept alive until their copies have certainly drained.
+            host = torch.tensor([vals[0], vals[1], vals[2], 0.0], dtype=torch.float32).pin_memory()
+            self._hyper_host.append(host)
+            del self._hyper_host[:-8]
+            self._hyper.copy_(host, non_blocking=True)
             self._hyper_vals = vals
         return self._hyper.data_ptr()

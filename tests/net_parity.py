@@ -7,11 +7,17 @@ the same test run in a subprocess on top of the REFERENCE'S UNCHANGED container 
                                                              # not one line changed) driving dorknet_b200's layers
     python tests/net_parity.py --net r18 --container ours
 
-Tolerances (normalised max-abs error max|a-b| / max|b| per tensor).  The product default runs the conv /
-pointwise / dense GEMMs on tcgen05 kind::tf32 (operands truncated to 10 mantissa bits) under fp32 accumulation, the
-reference in fp32 throughout; everything else is fp32 on both sides.  Per layer the TF32 gates are 2e-3 (fwd / dgrad)
-and 5e-3 (wgrad); through the 21 GEMM layers + 34 BatchNorms of ResNet-18-depsep the independent truncation errors add
-in quadrature, so the network-level gates are a small multiple of those (stated below, measured values are printed):
+What is compared with what.  The forward pass (loss, scores, BatchNorm running statistics) is compared with the
+reference directly.  The reference's fp32 GRADIENTS are themselves up to 9.5 % away from the exact gradients of the same
+step (float64 evaluation, tests/golden/fp64_net.py; measured per tensor by tests/golden/make_golden_r18.py and stored
+as referr/*: its per-channel fp32 sums lose the terms that cancel), so every gradient is held to the EXACT gradient
+(grad64/*) with the gates below, and in addition must be at least as close to it as the reference is (x1.5 + gate
+floor).  The distance to the reference's own gradient is printed next to it.
+
+Gates (normalised max-abs error max|a-b| / max|b| per tensor; gradients whose exact value cancels to ~0 --
+dbeta of a BatchNorm that feeds a linear layer + BatchNorm -- are normalised by 1 % of the largest gradient of the same
+kind in the net instead of by their own noise).  The product default runs conv / pointwise / dense GEMMs on tcgen05
+kind::tf32 (operands truncated to 10 mantissa bits, fp32 accumulation), everything else in fp32:
 """
 import argparse
 import os
@@ -25,17 +31,17 @@ if ROOT not in sys.path:
 
 # network-level gates, product default backend (TF32 tcgen05 GEMMs + fused cluster BatchNorm)
 TOL = {
-    "loss": 2e-4,         # relative, loss + l2 terms
-    "scores": 5e-3,       # softmax probabilities of the batch
-    "grad_gemm": 1.5e-2,  # conv / pointwise / dense weight gradients (per tensor, relative to that tensor's max)
+    "loss": 2e-4,         # relative, loss + l2 terms, vs the reference
+    "scores": 5e-3,       # softmax probabilities of the batch, vs the reference
+    "grad_gemm": 1.5e-2,  # conv / pointwise / dense weight gradients vs the exact gradient
     "grad_dw": 1.5e-2,    # depthwise weight gradients (fp32 kernels fed by TF32-perturbed activations / gradients)
     "grad_bn": 1.5e-2,    # gamma / beta gradients
-    "running": 1e-3,      # BatchNorm running mean / std after the step
-    "scores_test": 2e-2,  # test-mode scores after the SGDMomentum update
+    "running": 1e-3,      # BatchNorm batch mean / std of the step (running statistics after the first batch), vs float64
+    "scores_test": 2e-2,  # test-mode scores after the SGDMomentum update, vs the reference
 }
-# fp32 SIMT GEMM backend (GPU-side cross-check): fp32 against fp32, only summation order differs
-TOL_FP32 = {"loss": 2e-6, "scores": 2e-5, "grad_gemm": 5e-4, "grad_dw": 5e-4, "grad_bn": 5e-4, "running": 2e-5,
-            "scores_test": 1e-4}
+# fp32 SIMT GEMM backend (GPU-side cross-check): fp32 against float64
+TOL_FP32 = {"loss": 2e-6, "scores": 2e-5, "grad_gemm": 2e-4, "grad_dw": 2e-4, "grad_bn": 2e-4, "running": 2e-5,
+            "scores_test": 5e-3}
 
 
 def nerr(a, b, floor=0.0):
@@ -88,7 +94,7 @@ def run(net_name="r18", container="ours", backend=0, verbose=True):
         n0 = launch_count()
         loss, scores = net.forward(X, Y)
         net.backward()
-        worst, failures = {}, []
+        worst, failures, ref_worst, vs_ref = {}, [], [0.0], [0.0]
 
         def check(cat, what, e):
             if e >= worst.get(cat, (-1.0, ""))[0]:
@@ -103,22 +109,31 @@ def run(net_name="r18", container="ours", backend=0, verbose=True):
         kinds = {}
         for l in workloads.iter_param_layers(net):
             for k in l.grads.keys():
-                g = d["grad/%s/%s" % (l.layer_name, k)]
+                g = d["grad64/%s/%s" % (l.layer_name, k)]
                 kk = (type(l).__name__, k)
                 kinds[kk] = max(kinds.get(kk, 0.0), float(np.max(np.abs(g))))
         for l in workloads.iter_param_layers(net):
             tname = type(l).__name__
             cat = {"BatchNormLayer": "grad_bn", "DepthwiseConvLayer": "grad_dw"}.get(tname, "grad_gemm")
             for k in l.grads.keys():
-                g = d["grad/%s/%s" % (l.layer_name, k)]
+                nm = "%s/%s" % (l.layer_name, k)
+                g, gref = d["grad64/" + nm], d["grad/" + nm]
                 floor = 1e-2 * kinds[(tname, k)]
-                check(cat, "grad %s/%s" % (l.layer_name, k), nerr(l.grads[k].get(), g, floor))
+                mine = l.grads[k].get()
+                e = nerr(mine, g, floor)
+                check(cat, "grad " + nm, e)
+                eref = nerr(gref, g, floor)  # the reference's own distance to the exact gradient
+                ref_worst[0] = max(ref_worst[0], eref)
+                vs_ref[0] = max(vs_ref[0], nerr(mine, gref, floor))
+                if backend != 0 and not e <= 1.5 * eref + tol[cat]:
+                    failures.append("grad %s: %.3e from the exact gradient, the reference is at %.3e" % (nm, e, eref))
             nl = getattr(l, "non_learned_params", None)
             if nl and "rm/%s" % l.layer_name in d.files:
+                # first training batch: running statistics are assigned the batch mean / std (batch_norm.py:76-89)
                 check("running", "running_mean %s" % l.layer_name,
-                      nerr(np.asarray(nl["running_mean"].get()).reshape(-1), d["rm/%s" % l.layer_name], 1e-3))
+                      nerr(np.asarray(nl["running_mean"].get()).reshape(-1), d["mean64/%s" % l.layer_name], 1e-3))
                 check("running", "running_std %s" % l.layer_name,
-                      nerr(np.asarray(nl["running_std"].get()).reshape(-1), d["rs/%s" % l.layer_name]))
+                      nerr(np.asarray(nl["running_std"].get()).reshape(-1), d["std64/%s" % l.layer_name]))
         opt.update_weights()
         _, st = net.forward(X, None, test_mode=True)
         check("scores_test", "scores_test", nerr(st.get(), d["scores_test"]))
@@ -131,6 +146,8 @@ def run(net_name="r18", container="ours", backend=0, verbose=True):
                 net_name, container, type(net).__module__, backend, launches, tc, simt))
             for cat in sorted(worst):
                 print("  %-12s worst %.3e (gate %.1e) at %s" % (cat, worst[cat][0], tol[cat], worst[cat][1]))
+            print("  gradients: the reference's own worst distance to the exact gradient %.3e; ours to the reference's %.3e"
+                  % (ref_worst[0], vs_ref[0]))
         assert not failures, "\n".join(failures)
         return worst
     finally:

@@ -121,3 +121,76 @@ def test_two_rank_gradient_allreduce_gloo(overlap):
             assert ar[0] < log.index("bwd a")
         else:
             assert ar[0] > log.index("bwd a")
+
+
+class _FakeBlock:
+    """ResidualBlock stand-in with the product's real backward order: layer_list[-1..1], skip projection, layer_list[0]"""
+
+    def __init__(self, name, layer_list, skip):
+        self.layer_name = name
+        self.layer_list = layer_list
+        self.skip_projection = skip
+        self.learned_params = None
+        self.grads = None
+
+    def backward(self, upstream):
+        for l in self.layer_list[:0:-1]:
+            l.backward(upstream)
+        if self.skip_projection is not None:
+            self.skip_projection.backward(upstream)
+        self.layer_list[0].backward(upstream)
+        return upstream
+
+
+def _worker_block(rank, world, port, num_buckets, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dorknet_b200.data_parallel import DataParallel, backward_order
+        log = []
+        mk = lambda n, shp: _FakeLayer(n, {"weights": shp}, log)  # noqa: E731
+        # sized so that with 2..4 buckets a cut falls between the skip projection and the branch layers around it
+        blk = _FakeBlock("res", [mk("b0", (64, 9)), mk("b1", (300, 64)), mk("b2", (64, 9)), mk("b3", (300, 64))],
+                         mk("skip", (700, 64)))
+        layers = [mk("stem", (64, 75)), blk, mk("head", (10, 300))]
+        net, opt = _FakeNet(layers), _FakeOpt()
+        assert [l.layer_name for l in backward_order(net)] == ["head", "b3", "b2", "b1", "skip", "b0", "stem"]
+        dp = DataParallel(net, opt, num_buckets=num_buckets, overlap=True, device=torch.device("cpu"))
+        assert [l.layer_name for l, _ in dp.entries] == ["head", "b3", "b2", "b1", "skip", "b0", "stem"]
+        written = set()
+        orig_launch = dp._launch
+        bad = []
+
+        def logged(b):
+            # every tensor inside the bucket must have been written by now
+            for (l, k), off, n in zip(dp.entries, dp.offsets, dp.sizes):
+                if off >= b["lo"] and off + n <= b["hi"] and ("bwd " + l.layer_name) not in log:
+                    bad.append((l.layer_name, b["lo"], b["hi"]))
+            orig_launch(b)
+        dp._launch = logged
+        for layer in reversed(layers):
+            layer.backward(float(rank + 1))
+        dp.finish()
+        expect = sum(float(r + 1) + len("weights") for r in range(world))
+        ok = all(torch.all(l.grads["weights"].t == expect).item() for l, _ in dp.entries)
+        q.put((rank, ok and not bad, bad))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_buckets", [2, 3, 4])
+def test_skip_projection_gradient_is_written_before_its_bucket_is_reduced(num_buckets):
+    """a block's skip projection runs AFTER layer_list[-1..1]; a bucket holding its gradient must not be
+    all-reduced from an earlier layer's hook (include_skip_projections=True would train on un-reduced gradients)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_block, args=(r, 2, port, num_buckets, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, bad in res:
+        assert ok, (rank, bad)
