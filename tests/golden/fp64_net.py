@@ -11,6 +11,17 @@ import numpy as np
 
 F8 = np.float64
 
+# Arithmetic model of the tensor-core path: tcgen05 kind::tf32 reads fp32 operands and ignores the 13 low mantissa
+# bits (round toward zero); products are exact, accumulation here is float64.  Off by default (exact evaluation).
+TF32_OPERANDS = False
+
+
+def _t(a):
+    if not TF32_OPERANDS:
+        return a
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)
+    return u.view(np.float32).astype(F8)
+
 
 def _pad(X, p):
     return np.pad(X, ((0, 0), (0, 0), (p, p), (p, p))) if p else X
@@ -35,7 +46,7 @@ def conv_fwd(L, X):  # layers/convolution.py:58-87, im2col.pyx:16-36
     for i in range(kh):
         for j in range(kw):
             patch = Xp[:, :, i:i + s * (OH - 1) + 1:s, j:j + s * (OW - 1) + 1:s]
-            Y += np.einsum("nchw,fc->nfhw", patch, W[:, :, i, j], optimize=True)
+            Y += np.einsum("nchw,fc->nfhw", _t(patch), _t(W[:, :, i, j]), optimize=True)
     if "bias" in L.learned_params:
         Y += np.asarray(L.learned_params["bias"], F8)[None, :, None, None]
     return Y, (Xp, W, s, p, OH, OW, X.shape)
@@ -49,8 +60,8 @@ def conv_bwd(L, dY, cache, grads):  # convolution.py:90-126, im2col.pyx:209-234
     for i in range(kh):
         for j in range(kw):
             sl = (slice(None), slice(None), slice(i, i + s * (OH - 1) + 1, s), slice(j, j + s * (OW - 1) + 1, s))
-            dW[:, :, i, j] = np.einsum("nfhw,nchw->fc", dY, Xp[sl], optimize=True)
-            dXp[sl] += np.einsum("nfhw,fc->nchw", dY, W[:, :, i, j], optimize=True)
+            dW[:, :, i, j] = np.einsum("nfhw,nchw->fc", _t(dY), _t(Xp[sl]), optimize=True)
+            dXp[sl] += np.einsum("nfhw,fc->nchw", _t(dY), _t(W[:, :, i, j]), optimize=True)
     if L.weight_regulariser is not None:
         dW += float(L.weight_regulariser.strength) * W
     grads[(L.layer_name, "weights")] = dW
@@ -64,7 +75,7 @@ def pw_fwd(L, X):  # layers/pointwise_convolution.py:46-55
     W = np.asarray(L.learned_params["weights"], F8)
     s = int(L.stride)
     Xs = X[:, :, ::s, ::s]
-    Y = np.einsum("nchw,fc->nfhw", Xs, W, optimize=True)
+    Y = np.einsum("nchw,fc->nfhw", _t(Xs), _t(W), optimize=True)
     if "bias" in L.learned_params:
         Y += np.asarray(L.learned_params["bias"], F8)[None, :, None, None]
     return Y, (Xs, W, s)
@@ -72,13 +83,13 @@ def pw_fwd(L, X):  # layers/pointwise_convolution.py:46-55
 
 def pw_bwd(L, dY, cache, grads):  # pointwise_convolution.py:57-75 (zero-stuffed dX of shape OH*s)
     Xs, W, s = cache
-    dW = np.einsum("nfhw,nchw->fc", dY, Xs, optimize=True)
+    dW = np.einsum("nfhw,nchw->fc", _t(dY), _t(Xs), optimize=True)
     if L.weight_regulariser is not None:
         dW += float(L.weight_regulariser.strength) * W
     grads[(L.layer_name, "weights")] = dW
     if "bias" in L.learned_params:
         grads[(L.layer_name, "bias")] = dY.sum((0, 2, 3))
-    dXs = np.einsum("nfhw,fc->nchw", dY, W, optimize=True)
+    dXs = np.einsum("nfhw,fc->nchw", _t(dY), _t(W), optimize=True)
     if s == 1:
         return dXs
     N, C, OH, OW = dXs.shape
@@ -168,7 +179,7 @@ class Evaluator:
             Y, c = X.mean((2, 3)), X.shape
         elif t == "DenseLayer":  # layers/dense_layer.py:46-51
             W = np.asarray(L.learned_params["weights"], F8)
-            Y = X @ W
+            Y = _t(X) @ _t(W)
             if "bias" in L.learned_params:
                 Y = Y + np.asarray(L.learned_params["bias"], F8)
             c = (X, W)
@@ -224,13 +235,13 @@ class Evaluator:
             return np.broadcast_to(dY[:, :, None, None] / (H * W), c).copy()
         if t == "DenseLayer":  # dense_layer.py:54-67
             X, W = c
-            dW = X.T @ dY
+            dW = _t(X).T @ _t(dY)
             if L.weight_regulariser is not None:
                 dW += float(L.weight_regulariser.strength) * W
             self.grads[(L.layer_name, "weights")] = dW
             if "bias" in L.learned_params:
                 self.grads[(L.layer_name, "bias")] = dY.sum(0)
-            return dY @ W.T
+            return _t(dY) @ _t(W).T
         if t == "ResidualBlock":  # residual_block.py:86-97
             joined = self._bwd(L.post_skip_activation, dY)
             dx = joined
