@@ -25,6 +25,7 @@ void count_launch() { ++g_launches; }
 int init_gemm_tcgen05();  // gemm_tcgen05.cu: opt-in shared memory sizes
 int init_depthwise();     // depthwise.cu
 int init_conv_rows();     // conv_rows.cu
+int init_conv_tma();      // conv_tma.cu
 int bn_fused_init();      // bn_fused.cu
 
 }  // namespace dk
@@ -50,6 +51,8 @@ int dk_init(int device) {
     rc = dk::init_gemm_tcgen05();
     if (rc) return rc;
     rc = dk::init_conv_rows();
+    if (rc) return rc;
+    rc = dk::init_conv_tma();
     if (rc) return rc;
     rc = dk::bn_fused_init();
     if (rc) return rc;

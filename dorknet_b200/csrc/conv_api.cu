@@ -21,7 +21,8 @@ static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 static size_t conv_ws(int N, int C, int H, int W, int F, int kh, int kw, int s, int p) {
     const int OH = (H + 2 * p - kh) / s + 1, OW = (W + 2 * p - kw) / s + 1;
     const size_t simt = simt_wgrad_ws_bytes(F, C * kh * kw, (int64_t)N * OH * OW);
-    const size_t tc = max_sz(tc_conv_ws_bytes(N, C, H, W, F, kh, kw, s, p), conv_rows_ws_bytes(N, C, H, W, F, kh, kw, s, p));
+    const size_t tc = max_sz(max_sz(tc_conv_ws_bytes(N, C, H, W, F, kh, kw, s, p), conv_rows_ws_bytes(N, C, H, W, F, kh, kw, s, p)),
+                             conv_tma_ws_bytes(N, C, H, W, F, kh, kw, s, p));
     return max_sz(simt, tc) + 256;
 }
 
@@ -57,6 +58,7 @@ int dk_conv2d_fwd(const float *x, const float *w, const float *bias, float *y, i
     if (rc) return rc;
     DK_REQUIRE(x && w && y, "dk_conv2d_fwd: NULL pointer");
     DK_TRY_TC(conv_rows_fwd(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad, as_stream(stream)));
+    DK_TRY_TC(conv_tma_fwd(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
     DK_TRY_TC(tc_conv_fwd(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
     ++g_simt_calls;
     return simt_conv_fwd(x, w, bias, y, N, C, H, W, F, kh, kw, stride, pad, as_stream(stream));
@@ -68,6 +70,7 @@ int dk_conv2d_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     if (rc) return rc;
     DK_REQUIRE(dy && w && dx, "dk_conv2d_dgrad: NULL pointer");
     const int OH = (H + 2 * pad - kh) / stride + 1, OW = (W + 2 * pad - kw) / stride + 1;
+    DK_TRY_TC(conv_tma_dgrad(dy, w, dx, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
     DK_TRY_TC(tc_conv_dgrad(dy, w, dx, N, C, H, W, F, kh, kw, stride, pad, OH, OW, ws, ws_bytes, as_stream(stream)));
     ++g_simt_calls;
     return simt_conv_dgrad(dy, w, dx, N, C, H, W, F, kh, kw, stride, pad, OH, OW, as_stream(stream));
@@ -85,6 +88,7 @@ int dk_conv2d_wgrad(const float *dy, const float *x, const float *w, float *dw, 
         if (rc) return rc;
     }
     DK_TRY_TC(conv_rows_wgrad(dy, x, w, dw, l2, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
+    DK_TRY_TC(conv_tma_wgrad(dy, x, w, dw, l2, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
     DK_TRY_TC(tc_conv_wgrad(dy, x, w, dw, l2, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream)));
     ++g_simt_calls;
     return simt_conv_wgrad(dy, x, w, dw, l2, N, C, H, W, F, kh, kw, stride, pad, ws, ws_bytes, as_stream(stream));

@@ -1,0 +1,685 @@
+// conv_tma.cu -- stride-1 k x k convolutions (ConvLayer: layers/convolution.py:58-126, layers/im2col.pyx:16-36,209-234) as
+// TMA-fed tcgen05 implicit GEMMs directly on the NCHW tensors: the kernels for the one tensor-bound shape of the
+// baseline (cfg2: 3x3, 64 -> 64 at 56x56) and the MNIST stack's 3x3 layers.
+//
+// The patch matrix of the reference never exists.  A 4-D tensor map (W, H, C, N) with a (32, 1, rows, 1) box delivers
+// 32 consecutive pixels of ONE image row for 32 (or up to 128) channels as a ready-made swizzled operand tile, and a
+// filter tap (i, j) is nothing but a coordinate shift (w + j - p, h + i - p): TMA's out-of-bounds zero fill IS the
+// padding -- no index arithmetic, no gather warps, no padded copies.
+//
+//   forward / dgrad (conv_s1_kernel): tile = 4 output rows x 32 columns of one image (M = 128 pixels: TMEM lane =
+//       pixel, so the epilogue stores 128-byte runs of NCHW), N = output channels (<= 256), K loop over (channel block
+//       of 32, tap column j): ONE pipeline stage = the kh + 3 input-row boxes that serve all kh taps of that column
+//       (tap i = boxes i..i+3 of the stage: an MN-major operand is a sequence of 4 KB 32-pixel blocks, so the A
+//       descriptor simply starts i blocks later) -- input traffic from L2 is (kh+3)/4 * kw instead of kh * kw times
+//       the tensor.  The permuted filters stay RESIDENT in shared memory for the whole persistent CTA when they fit
+//       (147 KB for 64 x 64 x 3 x 3), else they stream next to the input boxes.
+//       dgrad is the same kernel on dY with the flipped / transposed filters and padding k - 1 - p.
+//   wgrad (conv_s1_wgrad_kernel): dW[f][c][i][j] = sum over pixels of dY[f][px] * X[c][px shifted by the tap]: M = F,
+//       N = C, K = pixels (both operands K-major: 32 pixels of an image row are contiguous).  A CTA owns one tap column
+//       j and a range of (image, 32-column strip) pairs and walks down the rows: each step loads ONE dY row box and
+//       ONE new X row box; the X boxes of the last kh steps are the kh row taps (accumulator i in TMEM columns
+//       i*stride), so every byte fetched feeds kh MMAs.  Partials per (split, j) go to the workspace, the existing
+//       deterministic split-K reduce adds them (+ l2 * W).
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "tc_ptx.cuh"
+
+namespace dk {
+
+using namespace tc;
+
+constexpr int CT_THREADS = 192;
+constexpr int CT_BOX = 4096;           // one (32 pixels x 32 channels) fp32 box
+constexpr int CT_MAX_STAGES = 8;
+constexpr int CT_SMEM_MAX = 227 * 1024 - 2048;
+constexpr uint32_t CT_MN_LBO = 4096, CT_MN_SBO = 512, CT_MN_KSTEP = 1024;
+
+int g_conv_tma_enabled = 1;  // dk_tc_debug_set(17, 0) switches these kernels off (the gather variants take over)
+
+struct CsParams {
+    int N, Cin, H, W, Nout, OH, OW, kh, kw, ph, pw;
+    int bnF;            // output channels rounded up to 32: one tap column's accumulator width
+    int cblocks;        // input-channel blocks of 32
+    int nb, nr;         // a tile = nr output rows x nb 32-column blocks (nb * nr = 4: M = 128 pixels)
+    int rgroups, num_tiles;
+    int stages, nbox;   // nbox = (nr + kh - 1) * nb input boxes per stage (one stage = one channel block)
+    int w_resident;
+    int jchunk;         // tap columns per MMA (N = jchunk * bnF <= 256)
+    int nacc;           // accumulator sets in TMEM (2 = the epilogue overlaps the next tile)
+    uint32_t b_bytes;   // one filter tile: bnF x 32 floats
+    uint32_t stage_bytes, wres_bytes, xch_bytes;
+    uint32_t tmem_cols, acc_stride;
+    float *out;
+    const float *bias;
+};
+
+// Forward-form kernel.  Only ALIGNED boxes can be fetched (a TMA box whose innermost coordinate is not a multiple of
+// 16 bytes traps on this hardware: profiles/r01r_tma_alignment_probe.log), so the +-1 pixel shifts of the filter's
+// columns cannot be loads.  They are not needed: with Z_j[f][r][c] = sum_{i, ch} W[f][ch][i][j] * X[ch][r + i - p][c]
+// (vertical taps only -- whole-row shifts, always aligned) the convolution is Y[f][r][c] = sum_j Z_j[f][r][c + j - p], a
+// shift of the RESULT by j - p columns.  The kw partial results Z_j are kw accumulators side by side in TMEM (one
+// MMA of N = kw * F columns per (channel block, row tap) computes all of them from ONE read of the input boxes), and
+// TMEM lane = pixel, so the epilogue adds them up with warp shuffles (+ a shared-memory hand-over of the edge lanes
+// between the 32-column blocks of a row).  Columns outside the image are zero in X, hence in Z: padding again costs
+// nothing.
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const CsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t wres = smem_base;                       // resident filter tiles [cblock][i][j][bnF x 128 B]
+    const uint32_t stage0 = smem_base + p.wres_bytes;
+    const uint32_t xch_base = stage0 + (uint32_t)p.stages * p.stage_bytes;   // edge-lane hand-over [4 warps][kw][4][32]
+    const uint32_t bar_base = xch_base + p.xch_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (CT_MAX_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * CT_MAX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * CT_MAX_STAGES + 2 + a); };
+    const uint32_t wfull_bar = bar_base + 8u * (2 * CT_MAX_STAGES + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * CT_MAX_STAGES + 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        mbar_init(wfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int taps = p.kh * p.kw;
+    const int rows_in = p.nr + p.kh - 1;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            if (p.w_resident) {
+                mbar_expect_tx(wfull_bar, (uint32_t)(taps * p.cblocks) * p.b_bytes);
+                for (int cb = 0; cb < p.cblocks; ++cb)
+                    for (int t = 0; t < taps; ++t)
+                        tma_load_3d(wres + (uint32_t)(cb * taps + t) * p.b_bytes, &tmW, wfull_bar, cb * 32, 0, t);
+            }
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t tx = (uint32_t)p.nbox * CT_BOX + (p.w_resident ? 0u : (uint32_t)taps * p.b_bytes);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int n = tile / p.rgroups, r0 = (tile - n * p.rgroups) * p.nr;
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sA = stage0 + (uint32_t)s * p.stage_bytes, fb = full_bar(s);
+                    mbar_expect_tx(fb, tx);
+                    for (int rr = 0; rr < rows_in; ++rr)
+                        for (int b = 0; b < p.nb; ++b)
+                            tma_load_4d(sA + (uint32_t)(rr * p.nb + b) * CT_BOX, &tmX, fb, 32 * b, r0 + rr - p.ph, cb * 32, n);
+                    if (!p.w_resident) {
+                        const uint32_t sB = sA + (uint32_t)p.nbox * CT_BOX;
+                        for (int t = 0; t < taps; ++t)
+                            tma_load_3d(sB + (uint32_t)t * p.b_bytes, &tmW, fb, cb * 32, 0, t);
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            if (p.w_resident) {
+                mbar_wait(wfull_bar, 0);
+                tc_fence_after();
+            }
+            int s = 0, local = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+                const int acc = p.nacc == 2 ? (local & 1) : 0;
+                const uint32_t aph = p.nacc == 2 ? (((uint32_t)(local >> 1)) & 1u) : ((uint32_t)local & 1u);
+                mbar_wait(tempty_bar(acc), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.acc_stride;
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    int nks = 4;
+                    const int rem = p.Cin - cb * 32;
+                    if (rem < 32) nks = (rem + 7) / 8;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sA = stage0 + (uint32_t)s * p.stage_bytes;
+                    const uint32_t wt = p.w_resident ? wres + (uint32_t)(cb * taps) * p.b_bytes : sA + (uint32_t)p.nbox * CT_BOX;
+#pragma unroll 1
+                    for (int i = 0; i < p.kh; ++i) {
+                        const uint32_t a0 = sA + (uint32_t)(i * p.nb) * CT_BOX;
+#pragma unroll 1
+                        for (int j0 = 0; j0 < p.kw; j0 += p.jchunk) {
+                            const int nj = p.kw - j0 < p.jchunk ? p.kw - j0 : p.jchunk;
+                            const uint32_t idesc = idesc_tf32(128, nj * p.bnF, 1, 0);
+                            const uint32_t b0 = wt + (uint32_t)(i * p.kw + j0) * p.b_bytes;
+                            const uint32_t dd = d_tmem + (uint32_t)(j0 * p.bnF);
+#pragma unroll 1
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint64_t ad = smem_desc(a0 + ks * CT_MN_KSTEP, CT_MN_LBO, CT_MN_SBO, LAYOUT_SW128_BASE32B);
+                                const uint64_t bd = smem_desc(b0 + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                                mma_tf32(dd, ad, bd, idesc, (cb > 0 || i > 0 || ks > 0) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    mma_commit(empty_bar(s));
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+                mma_commit(tfull_bar(acc));
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 2..5) ========================
+        const int q = warp & 3;                      // TMEM lane quadrant = block (row q / nb, column block q % nb)
+        const int trow = q / p.nb, cblk = q - trow * p.nb;
+        const int col = 32 * cblk + lane;
+        float *xch = reinterpret_cast<float *>(smem_raw + (xch_base - smem_u32(smem_raw)));  // [4][kw][4][32]
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+            const int acc = p.nacc == 2 ? (local & 1) : 0;
+            const uint32_t aph = p.nacc == 2 ? (((uint32_t)(local >> 1)) & 1u) : ((uint32_t)local & 1u);
+            const int n = tile / p.rgroups, row = (tile - n * p.rgroups) * p.nr + trow;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const bool ok = row < p.OH && col < p.OW;
+            const long long plane = (long long)p.OH * p.OW;
+            float *o = p.out + (long long)n * p.Nout * plane + (long long)row * p.OW + col;
+            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * p.acc_stride;
+            for (int c = 0; c < p.bnF; c += 32) {
+                float y[32];
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) y[jj] = 0.0f;
+                // pass 1 (several column blocks per row): publish the edge lanes every tap column will hand to its neighbour
+                if (p.nb > 1) {
+                    for (int j = 0; j < p.kw; ++j) {
+                        const int d = j - p.pw;  // Y[col] += Z_j[col + d]
+                        if (d == 0) continue;
+                        uint32_t v[32];
+                        tmem_ld32(t_row + (uint32_t)(j * p.bnF + c), v);
+                        tmem_ld_wait();
+                        // d > 0: the block to the LEFT needs my lanes 0 .. d-1;  d < 0: the block to the RIGHT needs my lanes 32+d .. 31
+                        const int e = d > 0 ? lane : lane - (32 + d);
+                        const int ne = d > 0 ? d : -d;
+                        if (e >= 0 && e < ne) {
+                            float *dst = xch + ((q * p.kw + j) * 4 + e) * 32;
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) dst[jj] = __uint_as_float(v[jj]);
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                for (int j = 0; j < p.kw; ++j) {
+                    const int d = j - p.pw;
+                    uint32_t v[32];
+                    tmem_ld32(t_row + (uint32_t)(j * p.bnF + c), v);
+                    tmem_ld_wait();
+                    const int src = lane + d;
+                    const bool inside = src >= 0 && src < 32;
+                    // neighbour block of the same tile row that owns column col + d (if any)
+                    const int nq = src < 0 ? q - 1 : q + 1;
+                    const bool has_nb = !inside && (src < 0 ? cblk > 0 : cblk + 1 < p.nb);
+                    // the neighbour published exactly the lanes this block misses: index = lane (d < 0) or src - 32 (d > 0)
+                    const float *nsrc = xch + ((nq * p.kw + j) * 4 + (src < 0 ? lane : src - 32)) * 32;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        float t = __shfl_sync(0xffffffffu, __uint_as_float(v[jj]), src & 31);
+                        if (!inside) t = has_nb ? nsrc[jj] : 0.0f;
+                        y[jj] += t;
+                    }
+                }
+                if (ok) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        if (c + jj < p.Nout) {
+                            float rr = y[jj];
+                            if (p.bias) rr += __ldg(p.bias + c + jj);
+                            o[(long long)(c + jj) * plane] = rr;
+                        }
+                    }
+                }
+                if (p.nb > 1) asm volatile("bar.sync 1, 128;" ::: "memory");  // the hand-over buffer is free again
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---- wgrad ------------------------------------------------------------------------------------------------------------
+struct CwParams {
+    int N, C, H, W, F, OH, OW, kh, kw, p;
+    int bnC;            // MMA N = round_up(C, 32)
+    int a_rows;         // rows of the dY box (F rounded up to 8, <= 128)
+    int csegs, strips;  // 32-column strips per image row, N * csegs strips in total
+    int splits, strips_per_split;
+    int stages;
+    uint32_t a_bytes, b_bytes, stage_bytes;
+    uint32_t tmem_cols, acc_stride;
+    float *partial;     // [splits][F][C][kh][kw]
+};
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_s1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                     const __grid_constant__ CUtensorMap tmXS, const CwParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + (uint32_t)p.stages * p.stage_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (CT_MAX_STAGES + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * CT_MAX_STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * CT_MAX_STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDY);
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmXS);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int j = blockIdx.x % p.kw, split = blockIdx.x / p.kw;
+    const int sb = split * p.strips_per_split;
+    int se = sb + p.strips_per_split;
+    if (se > p.strips) se = p.strips;
+    const int steps = p.OH + p.kh - 1;  // per strip: kh - 1 rows of run-in, then one output row per step
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int strip = sb; strip < se; ++strip) {
+                const int n = strip / p.csegs, c0 = (strip - n * p.csegs) * 32;
+                for (int t = 0; t < steps; ++t) {
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sA = smem_base + (uint32_t)s * p.stage_bytes, sB = sA + p.a_bytes, fb = full_bar(s);
+                    const int oh = t - (p.kh - 1);
+                    mbar_expect_tx(fb, p.b_bytes + (oh >= 0 ? (uint32_t)p.a_rows * 128u : 0u));
+                    // X row t - p (zero rows above / below) of the copy shifted by j - p columns: aligned boxes only (a box
+                    // starting at an odd column traps); the unshifted tap column reads X itself
+                    if (j == p.p) tma_load_4d(sB, &tmX, fb, c0, t - p.p, 0, n);
+                    else tma_load_4d(sB, &tmXS, fb, c0, t - p.p, 0, (j < p.p ? j : j - 1) * p.N + n);
+                    if (oh >= 0) tma_load_4d(sA, &tmDY, fb, c0, oh, 0, n);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(128, p.bnC, 0, 0);
+            int s = 0;
+            uint32_t ph = 0;
+            bool first = true;
+            for (int strip = sb; strip < se; ++strip) {
+                for (int t = 0; t < steps; ++t) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    if (t >= p.kh - 1) {
+                        const uint32_t sA = smem_base + (uint32_t)s * p.stage_bytes;
+#pragma unroll 1
+                        for (int i = 0; i < p.kh; ++i) {
+                            // X row oh + i - p was loaded kh - 1 - i steps ago
+                            int sx = s - (p.kh - 1 - i);
+                            if (sx < 0) sx += p.stages;
+                            const uint32_t sB = smem_base + (uint32_t)sx * p.stage_bytes + p.a_bytes;
+                            const uint32_t d_tmem = tmem_base + (uint32_t)i * p.acc_stride;
+#pragma unroll 1
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = smem_desc(sA + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                                const uint64_t bd = smem_desc(sB + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                                mma_tf32(d_tmem, ad, bd, idesc, (!first || ks > 0) ? 1u : 0u);
+                            }
+                        }
+                        first = false;
+                        // the oldest X row of this step is not needed again
+                        int so = s - (p.kh - 1);
+                        if (so < 0) so += p.stages;
+                        mma_commit(empty_bar(so));
+                        if (t == steps - 1) {  // end of the strip: the remaining run-out stages
+                            for (int d = p.kh - 2; d >= 0; --d) {
+                                int sr = s - d;
+                                if (sr < 0) sr += p.stages;
+                                mma_commit(empty_bar(sr));
+                            }
+                        }
+                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+            mma_commit(tfull_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        if (sb < se) {
+            mbar_wait(tfull_bar, 0);
+            tc_fence_after();
+        }
+        const int f = 32 * q + lane;
+        const int taps = p.kh * p.kw;
+        float *o = p.partial + ((long long)split * p.F + f) * p.C * taps + j;
+        for (int i = 0; i < p.kh; ++i) {
+            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)i * p.acc_stride;
+            for (int c = 0; c < p.bnC; c += 32) {
+                uint32_t v[32];
+                if (sb < se) {
+                    tmem_ld32(t_row + (uint32_t)c, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
+                }
+                if (f < p.F) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj)
+                        if (c + jj < p.C) o[(long long)(c + jj) * taps + i * p.kw] = __uint_as_float(v[jj]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// filters -> [tap][out channel][in channel padded to 32]:  mode 0 (forward) Wp[(i,j)][f][c] = W[f][c][i][j];
+// mode 1 (dgrad) Wp[(i',j')][c][f] = W[f][c][kh-1-i'][kw-1-j']
+__global__ void conv_tma_permute_kernel(const float *__restrict__ w, float *__restrict__ wp, int F, int C, int kh, int kw,
+                                        int Nout, int Cp, int mode) {
+    const int taps = kh * kw;
+    const long long total = (long long)taps * Nout * Cp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(idx % Cp);
+        const long long r = idx / Cp;
+        const int no = (int)(r % Nout), t = (int)(r / Nout);
+        const int i = t / kw, jj = t - i * kw;
+        float v = 0.0f;
+        if (mode == 0) {
+            if (ci < C) v = __ldg(w + (((long long)no * C + ci) * kh + i) * kw + jj);
+        } else {
+            if (ci < F) v = __ldg(w + (((long long)ci * C + no) * kh + (kh - 1 - i)) * kw + (kw - 1 - jj));
+        }
+        wp[idx] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_ct_encode = nullptr;
+static bool g_ct_ready = false;
+
+int init_conv_tma() {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return DK_OK;
+    }
+    g_ct_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (cudaFuncSetAttribute(conv_s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_s1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess) {
+        cudaGetLastError();
+        return DK_OK;
+    }
+    if (const char *m = getenv("DK_CONV_TMA")) g_conv_tma_enabled = atoi(m);
+    g_ct_ready = true;
+    return DK_OK;
+}
+
+// fp32 tensor map of rank 3 or 4 with dense strides
+static int ct_map(CUtensorMap *out, const float *ptr, int rank, const uint64_t *dims, const uint32_t *box, CUtensorMapSwizzle sw) {
+    cuuint64_t d[4], strides[3];
+    cuuint32_t b[4], es[4] = {1, 1, 1, 1};
+    uint64_t pitch = 4;
+    for (int i = 0; i < rank; ++i) {
+        d[i] = dims[i];
+        b[i] = box[i];
+        pitch *= dims[i];
+        if (i < rank - 1) strides[i] = pitch;
+    }
+    CUresult r = g_ct_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float *>(ptr), d, strides, b, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("conv_tma: cuTensorMapEncodeTiled failed (%d), rank %d dims (%llu,%llu,%llu) box (%u,%u,%u)", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+        return DK_ERR_CUDA;
+    }
+    return DK_OK;
+}
+
+static int ct_round_up(int v, int m) { return (v + m - 1) / m * m; }
+static uint32_t ct_acc_stride(int bn) { return bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u; }
+static uint32_t ct_pow2_cols(uint32_t c) { uint32_t v = 32; while (v < c) v <<= 1; return v; }
+
+// shapes the forward-form kernel takes: input [N, Cin, H, W] -> output [N, Nout, OH, OW], stride 1, pads (ph, pw)
+static bool ct_fwd_ok(const float *x, int Cin, int H, int W, int Nout, int OW, int kh, int kw, int pw) {
+    const int wmax = W > OW ? W : OW;
+    return g_ct_ready && g_conv_tma_enabled && aligned16(x) && (W % 4) == 0 && wmax <= 128 && kh <= 5 && kw <= 7 && kh * kw > 1 &&
+           Cin >= 8 && W >= 8 && pw <= 4 && kw - 1 - pw <= 4 && ct_round_up(Nout, 32) <= 256 && kw * ct_round_up(Nout, 32) <= 512;
+}
+
+size_t conv_tma_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p) {
+    if (s != 1 || kh * kw <= 1) return 0;
+    const int taps = kh * kw;
+    const size_t big = (size_t)(F > C ? F : C);
+    const size_t perm = (size_t)taps * big * (size_t)ct_round_up((int)big, 32) * 4 + 1024;
+    // wgrad: the kw - 1 column-shifted copies of X, then the split-K partials (splits * kw <= SM count)
+    const size_t shifted = (size_t)(kw - 1) * N * C * H * W * 4 + 1024;
+    const size_t partial = (size_t)sm_count() * F * C * taps * 4 + 1024;
+    return (perm > shifted + partial ? perm : shifted + partial) + 1024;
+}
+
+static int ct_run_fwd(const float *x, const float *w, const float *bias, float *y, int N, int Cin, int H, int W, int Nout,
+                      int OH, int OW, int kh, int kw, int ph, int pw, int F, int C, int mode, void *ws, size_t ws_bytes,
+                      cudaStream_t st) {
+    CsParams q = {};
+    q.N = N; q.Cin = Cin; q.H = H; q.W = W; q.Nout = Nout; q.OH = OH; q.OW = OW; q.kh = kh; q.kw = kw; q.ph = ph; q.pw = pw;
+    q.bnF = ct_round_up(Nout, 32);
+    const int Cp = ct_round_up(Cin, 32);
+    q.cblocks = Cp / 32;
+    const int wmax = W > OW ? W : OW;
+    q.nb = wmax <= 32 ? 1 : wmax <= 64 ? 2 : 4;
+    q.nr = 4 / q.nb;
+    q.rgroups = (OH + q.nr - 1) / q.nr;
+    q.num_tiles = N * q.rgroups;
+    q.nbox = (q.nr + kh - 1) * q.nb;
+    q.b_bytes = (uint32_t)q.bnF * 128u;
+    q.jchunk = 256 / q.bnF;
+    if (q.jchunk > kw) q.jchunk = kw;
+    const uint32_t acc_cols = (uint32_t)(kw * q.bnF);
+    q.nacc = 2 * acc_cols <= 512 ? 2 : 1;
+    q.acc_stride = acc_cols;
+    q.tmem_cols = ct_pow2_cols((uint32_t)q.nacc * acc_cols);
+    q.xch_bytes = (uint32_t)kw * 2048u;
+    const int taps = kh * kw;
+    const size_t perm_bytes = (size_t)taps * Nout * Cp * sizeof(float);
+    if (ws == nullptr || ws_bytes < perm_bytes + 256) return DK_ERR_UNSUPPORTED;
+    float *wp = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ws) + 255u) & ~(uintptr_t)255u);
+    // resident filters if they leave room for at least 2 stages of input boxes
+    const uint32_t wres = (uint32_t)(taps * q.cblocks) * q.b_bytes;
+    const uint32_t a_stage = (uint32_t)q.nbox * CT_BOX;
+    const int avail = CT_SMEM_MAX - 1024 - 256 - (int)q.xch_bytes;
+    if ((int64_t)wres + 2 * (int64_t)a_stage <= avail) {
+        q.w_resident = 1;
+        q.wres_bytes = wres;
+        q.stage_bytes = a_stage;
+    } else {
+        q.w_resident = 0;
+        q.wres_bytes = 0;
+        q.stage_bytes = a_stage + (uint32_t)taps * q.b_bytes;
+    }
+    int stg = (avail - (int)q.wres_bytes) / (int)q.stage_bytes;
+    if (stg < 2) return DK_ERR_UNSUPPORTED;
+    q.stages = stg > CT_MAX_STAGES ? CT_MAX_STAGES : stg;
+    q.out = y;
+    q.bias = bias;
+    {
+        const long long total = (long long)taps * Nout * Cp;
+        const int grid = (int)(ceil_div(total, 256) < 4 * sm_count() ? ceil_div(total, 256) : 4 * sm_count());
+        conv_tma_permute_kernel<<<grid, 256, 0, st>>>(w, wp, F, C, kh, kw, Nout, Cp, mode);
+        DK_LAUNCH_CHECK();
+    }
+    CUtensorMap tx, tw;
+    const uint64_t dx[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Cin, (uint64_t)N};
+    const uint32_t bx[4] = {32, 1, 32, 1};
+    int rc = ct_map(&tx, x, 4, dx, bx, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    const uint64_t dw[3] = {(uint64_t)Cp, (uint64_t)Nout, (uint64_t)taps};
+    const uint32_t bw[3] = {32, (uint32_t)q.bnF, 1};
+    rc = ct_map(&tw, wp, 3, dw, bw, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const size_t smem = (size_t)q.wres_bytes + (size_t)q.stages * q.stage_bytes + q.xch_bytes + 1024 + 8 * (2 * CT_MAX_STAGES + 8);
+    const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
+    conv_s1_kernel<<<grid, CT_THREADS, smem, st>>>(tx, tw, q);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
+int conv_tma_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
+                 int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (s != 1) return DK_ERR_UNSUPPORTED;
+    const int OH = H + 2 * p - kh + 1, OW = W + 2 * p - kw + 1;
+    if (OH < 1 || OW < 1 || !ct_fwd_ok(x, C, H, W, F, OW, kh, kw, p)) return DK_ERR_UNSUPPORTED;
+    return ct_run_fwd(x, w, bias, y, N, C, H, W, F, OH, OW, kh, kw, p, p, F, C, 0, ws, ws_bytes, st);
+}
+
+int conv_tma_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int s,
+                   int p, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (s != 1) return DK_ERR_UNSUPPORTED;
+    const int OH = H + 2 * p - kh + 1, OW = W + 2 * p - kw + 1;
+    if (OH < 1 || OW < 1 || kh - 1 - p < 0 || kw - 1 - p < 0) return DK_ERR_UNSUPPORTED;
+    if (!ct_fwd_ok(dy, F, OH, OW, C, W, kh, kw, kw - 1 - p)) return DK_ERR_UNSUPPORTED;
+    // dX = dY (*) flipped filters, padding k - 1 - p: output H x W again
+    return ct_run_fwd(dy, w, nullptr, dx, N, F, OH, OW, C, H, W, kh, kw, kh - 1 - p, kw - 1 - p, F, C, 1, ws, ws_bytes, st);
+}
+
+// xs[jj][n][c][h][w] = x[n][c][h][w + d(jj)] (0 outside the row), d running over the kw - 1 non-zero values of j - p:
+// the only unaligned access of the wgrad path, done once per call by plain loads
+__global__ void __launch_bounds__(256)
+conv_tma_shift_kernel(const float *__restrict__ x, float *__restrict__ xs, long long rows, int W, int kw, int p) {
+    const int w4 = W >> 2;
+    const long long per = rows * w4;
+    const long long total = per * (kw - 1);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int jj = (int)(idx / per);
+        const long long r = idx - (long long)jj * per;
+        const long long row = r / w4;
+        const int c0 = (int)(r - row * w4) * 4;
+        const int j = jj < p ? jj : jj + 1;
+        const int d = j - p;
+        const float *src = x + row * W;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int cc = c0 + e + d;
+            v[e] = (cc >= 0 && cc < W) ? __ldg(src + cc) : 0.0f;
+        }
+        *reinterpret_cast<float4 *>(xs + ((long long)jj * rows + row) * W + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
+                   int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (s != 1 || !g_ct_ready || !g_conv_tma_enabled) return DK_ERR_UNSUPPORTED;
+    const int OH = H + 2 * p - kh + 1, OW = W + 2 * p - kw + 1;
+    if (OH < 1 || OW < 1 || kh * kw <= 1 || kh > 5 || kw > 7 || p >= kw) return DK_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(dy) || (W % 4) != 0 || (OW % 4) != 0 || F > 128 || F < 8 || C < 8 || OW < 8) return DK_ERR_UNSUPPORTED;
+    if ((int64_t)N * kw >= (1 << 30)) return DK_ERR_UNSUPPORTED;
+    CwParams q = {};
+    q.N = N; q.C = C; q.H = H; q.W = W; q.F = F; q.OH = OH; q.OW = OW; q.kh = kh; q.kw = kw; q.p = p;
+    q.bnC = ct_round_up(C, 32);
+    if (q.bnC > 256) return DK_ERR_UNSUPPORTED;
+    q.acc_stride = ct_acc_stride(q.bnC);
+    if ((uint32_t)kh * q.acc_stride > 512) return DK_ERR_UNSUPPORTED;
+    q.tmem_cols = ct_pow2_cols((uint32_t)kh * q.acc_stride);
+    q.a_rows = ct_round_up(F, 8);
+    q.a_bytes = 128u * 128u;  // the MMA reads 128 rows: the slot is always 16 KB, the box fills the first a_rows
+    q.b_bytes = (uint32_t)q.bnC * 128u;
+    q.stage_bytes = q.a_bytes + q.b_bytes;
+    q.csegs = (OW + 31) / 32;
+    q.strips = N * q.csegs;
+    int splits = sm_count() / kw;
+    if (splits < 1) splits = 1;
+    if (splits > q.strips) splits = q.strips;
+    q.strips_per_split = (int)ceil_div(q.strips, splits);
+    q.splits = (int)ceil_div(q.strips, q.strips_per_split);
+    int stg = (CT_SMEM_MAX - 1024 - 256) / (int)q.stage_bytes;
+    if (stg < kh + 2) return DK_ERR_UNSUPPORTED;
+    q.stages = stg > CT_MAX_STAGES ? CT_MAX_STAGES : stg;
+    const int taps = kh * kw;
+    const size_t shifted = (size_t)(kw - 1) * N * C * H * W * sizeof(float);
+    const size_t need = (size_t)q.splits * F * C * taps * sizeof(float);
+    if (ws == nullptr || ws_bytes < shifted + need + 1024) return DK_ERR_UNSUPPORTED;
+    float *xs = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ws) + 255u) & ~(uintptr_t)255u);
+    q.partial = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(xs) + shifted + 255u) & ~(uintptr_t)255u);
+    if (kw > 1) {
+        const long long rows = (long long)N * C * H;
+        const long long total = rows * (W / 4) * (kw - 1);
+        conv_tma_shift_kernel<<<stream_grid(total, 256), 256, 0, st>>>(x, xs, rows, W, kw, p);
+        DK_LAUNCH_CHECK();
+    }
+    CUtensorMap ta, tb, tbs;
+    const uint64_t da[4] = {(uint64_t)OW, (uint64_t)OH, (uint64_t)F, (uint64_t)N};
+    const uint32_t ba[4] = {32, 1, (uint32_t)q.a_rows, 1};
+    int rc = ct_map(&ta, dy, 4, da, ba, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    const uint64_t db[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
+    const uint32_t bb[4] = {32, 1, (uint32_t)q.bnC, 1};
+    rc = ct_map(&tb, x, 4, db, bb, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    tbs = tb;
+    if (kw > 1) {
+        const uint64_t dbs[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N * (uint64_t)(kw - 1)};
+        rc = ct_map(&tbs, xs, 4, dbs, bb, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    const size_t smem = (size_t)q.stages * q.stage_bytes + 1024 + 8 * (2 * CT_MAX_STAGES + 8);
+    conv_s1_wgrad_kernel<<<q.splits * kw, CT_THREADS, smem, st>>>(ta, tb, tbs, q);
+    DK_LAUNCH_CHECK();
+    splitk_reduce_launch(q.partial, w, dw, l2, (int64_t)F * C * taps, q.splits, st);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
+}  // namespace dk

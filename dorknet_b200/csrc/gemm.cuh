@@ -42,6 +42,16 @@ int conv_rows_wgrad(const float *dy, const float *x, const float *w, float *dw, 
                     int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st);
 size_t conv_rows_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
 extern int g_conv_rows_enabled;
+
+// ---- stride-1 k x k convolutions on 4-D tensor maps (conv_tma.cu): forward, dgrad, wgrad -------------------------------
+int conv_tma_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
+                 int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st);
+int conv_tma_dgrad(const float *dy, const float *w, float *dx, int N, int C, int H, int W, int F, int kh, int kw, int s,
+                   int p, void *ws, size_t ws_bytes, cudaStream_t st);
+int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
+                   int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t conv_tma_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
+extern int g_conv_tma_enabled;
 void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st);
 
 }  // namespace dk

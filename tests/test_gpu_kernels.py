@@ -149,6 +149,28 @@ def test_conv_tcgen05_vs_oracle(O, case):
     _conv_case(O, case)
 
 
+CONV_TMA_CASES = [
+    # N, C, H, W, F, k, s, p -- stride 1, W % 4 == 0: the 4-D tensor-map kernels of conv_tma.cu (forward, dgrad, wgrad)
+    (2, 64, 56, 56, 64, 3, 1, 1),    # cfg2: two 32-column segments per row (24 valid in the second), resident filters
+    (3, 32, 28, 28, 32, 3, 1, 1),    # MNIST conv2: one partial column segment
+    (2, 40, 12, 36, 48, 3, 1, 1),    # channel counts that are not multiples of 32, H not a multiple of 4, rectangular
+    (2, 16, 10, 16, 24, 3, 1, 0),    # no padding: output 8 x 14 (OW % 4 != 0: wgrad falls back, forward / dgrad stay)
+    (2, 8, 9, 20, 8, 5, 1, 2),       # 5 x 5, padding 2, 8 channels (one partial k step)
+    (1, 24, 8, 12, 16, 3, 1, 2),     # padding larger than (k-1)/2: output grows to 10 x 14
+    (2, 128, 12, 12, 128, 3, 1, 1),  # filters too large to stay resident: streamed next to the input boxes
+    (3, 64, 20, 8, 200, 3, 1, 1),    # F > 128: wgrad falls back, N = 224 forward
+]
+
+
+@pytest.mark.parametrize("case", CONV_TMA_CASES)
+def test_conv_tma_stride1_vs_oracle(O, case):
+    from dorknet_b200 import _lib
+    tc0, s0 = _lib.gemm_call_counts()
+    _conv_case(O, case)
+    tc1, s1 = _lib.gemm_call_counts()
+    assert tc1 - tc0 == 3 and s1 == s0, "expected forward, dgrad and wgrad on the tensor-core path"
+
+
 @pytest.mark.parametrize("case", [(4, 3, 225, 225, 64, 5, 2, 1), (2, 1, 28, 28, 32, 3, 1, 1)])
 def test_conv_rows_generic_staging_vs_oracle(O, case):
     """the same small-K kernels with span staging switched off (4-byte cp.async staging of any geometry)"""
