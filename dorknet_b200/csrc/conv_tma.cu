@@ -35,12 +35,14 @@ namespace dk {
 
 using namespace tc;
 
-constexpr int CT_THREADS = 192;
+constexpr int CT_THREADS = 192;       // wgrad: producer, MMA issuer, 4 epilogue warps
+constexpr int CS_THREADS = 320;       // forward / dgrad: producer, MMA issuer, 8 epilogue warps
 constexpr int CT_BOX = 4096;           // one (32 pixels x 32 channels) fp32 box
 constexpr int CT_MAX_STAGES = 8;
 constexpr int CT_SMEM_MAX = 227 * 1024 - 2048;
 constexpr uint32_t CT_MN_LBO = 4096, CT_MN_SBO = 512, CT_MN_KSTEP = 1024;
 
+int g_ct_kc16 = 0;           // 0: stages always hold 32 channels
 int g_conv_tma_enabled = 1;  // dk_tc_debug_set(17, 0) switches these kernels off (the gather variants take over)
 
 struct CsParams {
@@ -49,7 +51,9 @@ struct CsParams {
     int cblocks;        // input-channel blocks of 32
     int nb, nr;         // a tile = nr output rows x nb 32-column blocks (nb * nr = 4: M = 128 pixels)
     int rgroups, num_tiles;
-    int stages, nbox;   // nbox = (nr + kh - 1) * nb input boxes per stage (one stage = one channel block)
+    int stages, nbox;   // nbox = (nr + kh - 1) * nb input boxes per stage (one stage = kc channels)
+    int kc;             // channels per stage: 32, or 16 (twice as many, half-size stages: finer overlap of loads and MMAs)
+    uint32_t box_bytes; // kc * 128
     int w_resident;
     int jchunk;         // tap columns per MMA (N = jchunk * bnF <= 256)
     int nacc;           // accumulator sets in TMEM (2 = the epilogue overlaps the next tile)
@@ -69,13 +73,13 @@ struct CsParams {
 // TMEM lane = pixel, so the epilogue adds them up with warp shuffles (+ a shared-memory hand-over of the edge lanes
 // between the 32-column blocks of a row).  Columns outside the image are zero in X, hence in Z: padding again costs
 // nothing.
-__global__ void __launch_bounds__(CT_THREADS, 1)
+__global__ void __launch_bounds__(CS_THREADS, 1)
 conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const CsParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t wres = smem_base;                       // resident filter tiles [cblock][i][j][bnF x 128 B]
     const uint32_t stage0 = smem_base + p.wres_bytes;
-    const uint32_t xch_base = stage0 + (uint32_t)p.stages * p.stage_bytes;   // edge-lane hand-over [4 warps][kw][4][32]
+    const uint32_t xch_base = stage0 + (uint32_t)p.stages * p.stage_bytes;   // edge-lane hand-over (epilogue)
     const uint32_t bar_base = xch_base + p.xch_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (CT_MAX_STAGES + s); };
@@ -94,7 +98,7 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);
+            mbar_init(tempty_bar(a), 8);
         }
         mbar_init(wfull_bar, 1);
         fence_barrier_init();
@@ -123,20 +127,20 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t tx = (uint32_t)p.nbox * CT_BOX + (p.w_resident ? 0u : (uint32_t)taps * p.b_bytes);
+            const uint32_t tx = (uint32_t)p.nbox * p.box_bytes + (p.w_resident ? 0u : (uint32_t)taps * p.b_bytes);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int n = tile / p.rgroups, r0 = (tile - n * p.rgroups) * p.nr;
-                for (int cb = 0; cb < p.cblocks; ++cb) {
+                for (int ch = 0; ch < p.Cin; ch += p.kc) {  // one stage per kc channels
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sA = stage0 + (uint32_t)s * p.stage_bytes, fb = full_bar(s);
                     mbar_expect_tx(fb, tx);
                     for (int rr = 0; rr < rows_in; ++rr)
                         for (int b = 0; b < p.nb; ++b)
-                            tma_load_4d(sA + (uint32_t)(rr * p.nb + b) * CT_BOX, &tmX, fb, 32 * b, r0 + rr - p.ph, cb * 32, n);
-                    if (!p.w_resident) {
-                        const uint32_t sB = sA + (uint32_t)p.nbox * CT_BOX;
+                            tma_load_4d(sA + (uint32_t)(rr * p.nb + b) * p.box_bytes, &tmX, fb, 32 * b, r0 + rr - p.ph, ch, n);
+                    if (!p.w_resident) {  // (kc == 32 here)
+                        const uint32_t sB = sA + (uint32_t)p.nbox * p.box_bytes;
                         for (int t = 0; t < taps; ++t)
-                            tma_load_3d(sB + (uint32_t)t * p.b_bytes, &tmW, fb, cb * 32, 0, t);
+                            tma_load_3d(sB + (uint32_t)t * p.b_bytes, &tmW, fb, ch, 0, t);
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
@@ -157,17 +161,19 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 mbar_wait(tempty_bar(acc), aph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * p.acc_stride;
-                for (int cb = 0; cb < p.cblocks; ++cb) {
-                    int nks = 4;
-                    const int rem = p.Cin - cb * 32;
-                    if (rem < 32) nks = (rem + 7) / 8;
+                for (int ch = 0; ch < p.Cin; ch += p.kc) {
+                    int nks = p.kc / 8;
+                    const int rem = p.Cin - ch;
+                    if (rem < p.kc) nks = (rem + 7) / 8;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t sA = stage0 + (uint32_t)s * p.stage_bytes;
-                    const uint32_t wt = p.w_resident ? wres + (uint32_t)(cb * taps) * p.b_bytes : sA + (uint32_t)p.nbox * CT_BOX;
+                    // the filter tiles keep 32-channel rows (128 B, K-major): a 16-channel stage starts 64 B into them
+                    const uint32_t wt = (p.w_resident ? wres + (uint32_t)((ch >> 5) * taps) * p.b_bytes
+                                                      : sA + (uint32_t)p.nbox * p.box_bytes) + (uint32_t)(ch & 31) * 4u;
 #pragma unroll 1
                     for (int i = 0; i < p.kh; ++i) {
-                        const uint32_t a0 = sA + (uint32_t)(i * p.nb) * CT_BOX;
+                        const uint32_t a0 = sA + (uint32_t)(i * p.nb) * p.box_bytes;
 #pragma unroll 1
                         for (int j0 = 0; j0 < p.kw; j0 += p.jchunk) {
                             const int nj = p.kw - j0 < p.jchunk ? p.kw - j0 : p.jchunk;
@@ -176,9 +182,9 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                             const uint32_t dd = d_tmem + (uint32_t)(j0 * p.bnF);
 #pragma unroll 1
                             for (int ks = 0; ks < nks; ++ks) {
-                                const uint64_t ad = smem_desc(a0 + ks * CT_MN_KSTEP, CT_MN_LBO, CT_MN_SBO, LAYOUT_SW128_BASE32B);
+                                const uint64_t ad = smem_desc(a0 + ks * CT_MN_KSTEP, p.box_bytes, CT_MN_SBO, LAYOUT_SW128_BASE32B);
                                 const uint64_t bd = smem_desc(b0 + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                                mma_tf32(dd, ad, bd, idesc, (cb > 0 || i > 0 || ks > 0) ? 1u : 0u);
+                                mma_tf32(dd, ad, bd, idesc, (ch > 0 || i > 0 || ks > 0) ? 1u : 0u);
                             }
                         }
                     }
@@ -189,11 +195,16 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
         }
     } else {
-        // ================================ epilogue (warps 2..5) ========================
-        const int q = warp & 3;                      // TMEM lane quadrant = block (row q / nb, column block q % nb)
+        // ================================ epilogue (warps 2..9) ========================
+        // Eight warps: warp w may only touch TMEM lanes 32*(w%4).. (its quadrant = one 32-pixel block of the tile), so two
+        // warps share a quadrant and split the output channels in chunks of 32 (half 0: channels 0-31, 64-95, ...).
+        const int q = warp & 3;                      // block (row q / nb, column block q % nb) of the tile
+        const int half = (warp - 2) >> 2;
         const int trow = q / p.nb, cblk = q - trow * p.nb;
         const int col = 32 * cblk + lane;
-        float *xch = reinterpret_cast<float *>(smem_raw + (xch_base - smem_u32(smem_raw)));  // [4][kw][4][32]
+        // edge-lane hand-over between the column blocks of a row: [half][quadrant][tap column][edge lane 0..3][32 channels]
+        float *xch = reinterpret_cast<float *>(smem_raw + (xch_base - smem_u32(smem_raw))) + half * (4 * p.kw * 4 * 32);
+        const long long plane = (long long)p.OH * p.OW;
         int local = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
             const int acc = p.nacc == 2 ? (local & 1) : 0;
@@ -202,62 +213,70 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             const bool ok = row < p.OH && col < p.OW;
-            const long long plane = (long long)p.OH * p.OW;
             float *o = p.out + (long long)n * p.Nout * plane + (long long)row * p.OW + col;
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * p.acc_stride;
-            for (int c = 0; c < p.bnF; c += 32) {
+            for (int c = 32 * half; c < p.bnF; c += 64) {
                 float y[32];
+                {   // the unshifted tap column
+                    uint32_t v[32];
+                    tmem_ld32(t_row + (uint32_t)(p.pw * p.bnF + c), v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) y[jj] = 0.0f;
-                // pass 1 (several column blocks per row): publish the edge lanes every tap column will hand to its neighbour
-                if (p.nb > 1) {
-                    for (int j = 0; j < p.kw; ++j) {
-                        const int d = j - p.pw;  // Y[col] += Z_j[col + d]
-                        if (d == 0) continue;
-                        uint32_t v[32];
-                        tmem_ld32(t_row + (uint32_t)(j * p.bnF + c), v);
-                        tmem_ld_wait();
-                        // d > 0: the block to the LEFT needs my lanes 0 .. d-1;  d < 0: the block to the RIGHT needs my lanes 32+d .. 31
-                        const int e = d > 0 ? lane : lane - (32 + d);
-                        const int ne = d > 0 ? d : -d;
-                        if (e >= 0 && e < ne) {
-                            float *dst = xch + ((q * p.kw + j) * 4 + e) * 32;
-#pragma unroll
-                            for (int jj = 0; jj < 32; ++jj) dst[jj] = __uint_as_float(v[jj]);
-                        }
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    for (int jj = 0; jj < 32; ++jj) y[jj] = __uint_as_float(v[jj]);
                 }
                 for (int j = 0; j < p.kw; ++j) {
-                    const int d = j - p.pw;
+                    const int d = j - p.pw;  // Y[col] += Z_j[col + d]
+                    if (d == 0) continue;
                     uint32_t v[32];
                     tmem_ld32(t_row + (uint32_t)(j * p.bnF + c), v);
                     tmem_ld_wait();
-                    const int src = lane + d;
-                    const bool inside = src >= 0 && src < 32;
-                    // neighbour block of the same tile row that owns column col + d (if any)
-                    const int nq = src < 0 ? q - 1 : q + 1;
-                    const bool has_nb = !inside && (src < 0 ? cblk > 0 : cblk + 1 < p.nb);
-                    // the neighbour published exactly the lanes this block misses: index = lane (d < 0) or src - 32 (d > 0)
-                    const float *nsrc = xch + ((nq * p.kw + j) * 4 + (src < 0 ? lane : src - 32)) * 32;
+                    if (p.nb > 1) {
+                        // d > 0: the block to the LEFT misses my lanes 0 .. d-1;  d < 0: the block to the RIGHT my lanes 32+d .. 31
+                        const int e = d > 0 ? lane : lane - (32 + d);
+                        if (e >= 0 && e < (d > 0 ? d : -d)) {
+                            float4 *dst = reinterpret_cast<float4 *>(xch + ((q * p.kw + j) * 4 + e) * 32);
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        float t = __shfl_sync(0xffffffffu, __uint_as_float(v[jj]), src & 31);
-                        if (!inside) t = has_nb ? nsrc[jj] : 0.0f;
-                        y[jj] += t;
+                            for (int jj = 0; jj < 32; jj += 4)
+                                dst[jj >> 2] = make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]),
+                                                           __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
+                        }
                     }
-                }
-                if (ok) {
+                    const int src = lane + d;
+                    const float m = (src >= 0 && src < 32) ? 1.0f : 0.0f;  // lanes whose source column is in another block
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) {
-                        if (c + jj < p.Nout) {
-                            float rr = y[jj];
-                            if (p.bias) rr += __ldg(p.bias + c + jj);
-                            o[(long long)(c + jj) * plane] = rr;
+                    for (int jj = 0; jj < 32; ++jj)
+                        y[jj] = fmaf(__shfl_sync(0xffffffffu, __uint_as_float(v[jj]), src & 31), m, y[jj]);
+                }
+                if (p.nb > 1) {
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                    for (int j = 0; j < p.kw; ++j) {
+                        const int d = j - p.pw, src = lane + d;
+                        if (d == 0) continue;
+                        // the neighbour published exactly the lanes this block misses: index = lane (d < 0) or src - 32 (d > 0)
+                        const bool take = src < 0 ? cblk > 0 : (src >= 32 && cblk + 1 < p.nb);
+                        if (take) {
+                            const int nq = src < 0 ? q - 1 : q + 1;
+                            const float4 *nsrc = reinterpret_cast<const float4 *>(xch + ((nq * p.kw + j) * 4 + (src < 0 ? lane : src - 32)) * 32);
+#pragma unroll
+                            for (int jj = 0; jj < 32; jj += 4) {
+                                const float4 t = nsrc[jj >> 2];
+                                y[jj] += t.x; y[jj + 1] += t.y; y[jj + 2] += t.z; y[jj + 3] += t.w;
+                            }
                         }
                     }
                 }
-                if (p.nb > 1) asm volatile("bar.sync 1, 128;" ::: "memory");  // the hand-over buffer is free again
+                if (ok) {
+                    float *pp = o + (long long)c * plane;
+                    if (c + 32 <= p.Nout && p.bias == nullptr) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj, pp += plane) *pp = y[jj];
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj, pp += plane)
+                            if (c + jj < p.Nout) *pp = y[jj] + (p.bias ? __ldg(p.bias + c + jj) : 0.0f);
+                    }
+                }
+                if (p.nb > 1) asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");  // the hand-over buffer is free again
             }
             tc_fence_before();
             __syncwarp();
@@ -531,18 +550,27 @@ static int ct_run_fwd(const float *x, const float *w, const float *bias, float *
     q.nacc = 2 * acc_cols <= 512 ? 2 : 1;
     q.acc_stride = acc_cols;
     q.tmem_cols = ct_pow2_cols((uint32_t)q.nacc * acc_cols);
-    q.xch_bytes = (uint32_t)kw * 2048u;
+    q.xch_bytes = (uint32_t)kw * 4096u;
     const int taps = kh * kw;
     const size_t perm_bytes = (size_t)taps * Nout * Cp * sizeof(float);
     if (ws == nullptr || ws_bytes < perm_bytes + 256) return DK_ERR_UNSUPPORTED;
     float *wp = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ws) + 255u) & ~(uintptr_t)255u);
     // resident filters if they leave room for at least 2 stages of input boxes
     const uint32_t wres = (uint32_t)(taps * q.cblocks) * q.b_bytes;
-    const uint32_t a_stage = (uint32_t)q.nbox * CT_BOX;
+    uint32_t a_stage = (uint32_t)q.nbox * CT_BOX;
     const int avail = CT_SMEM_MAX - 1024 - 256 - (int)q.xch_bytes;
+    q.kc = 32;
+    q.box_bytes = CT_BOX;
     if ((int64_t)wres + 2 * (int64_t)a_stage <= avail) {
         q.w_resident = 1;
         q.wres_bytes = wres;
+        // little room next to the resident filters: half-size stages (16 channels) keep more loads in flight behind the
+        // stage the tensor core is reading
+        if ((avail - (int64_t)wres) / a_stage < 4 && g_ct_kc16 && Cin % 16 == 0) {
+            q.kc = 16;
+            q.box_bytes = CT_BOX / 2;
+            a_stage /= 2;
+        }
         q.stage_bytes = a_stage;
     } else {
         q.w_resident = 0;
@@ -562,7 +590,7 @@ static int ct_run_fwd(const float *x, const float *w, const float *bias, float *
     }
     CUtensorMap tx, tw;
     const uint64_t dx[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Cin, (uint64_t)N};
-    const uint32_t bx[4] = {32, 1, 32, 1};
+    const uint32_t bx[4] = {32, 1, (uint32_t)q.kc, 1};
     int rc = ct_map(&tx, x, 4, dx, bx, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
     const uint64_t dw[3] = {(uint64_t)Cp, (uint64_t)Nout, (uint64_t)taps};
@@ -571,7 +599,7 @@ static int ct_run_fwd(const float *x, const float *w, const float *bias, float *
     if (rc) return rc;
     const size_t smem = (size_t)q.wres_bytes + (size_t)q.stages * q.stage_bytes + q.xch_bytes + 1024 + 8 * (2 * CT_MAX_STAGES + 8);
     const int grid = q.num_tiles < sm_count() ? q.num_tiles : sm_count();
-    conv_s1_kernel<<<grid, CT_THREADS, smem, st>>>(tx, tw, q);
+    conv_s1_kernel<<<grid, CS_THREADS, smem, st>>>(tx, tw, q);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }
