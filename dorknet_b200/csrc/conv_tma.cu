@@ -42,6 +42,7 @@ constexpr int CT_MAX_STAGES = 8;
 constexpr int CT_SMEM_MAX = 227 * 1024 - 2048;
 constexpr uint32_t CT_MN_LBO = 4096, CT_MN_SBO = 512, CT_MN_KSTEP = 1024;
 
+int g_ct_wgrad2 = 1;         // 0: wgrad always through the column-shifted global copies
 int g_ct_kc16 = 0;           // 0: stages always hold 32 channels
 int g_conv_tma_enabled = 1;  // dk_tc_debug_set(17, 0) switches these kernels off (the gather variants take over)
 
@@ -118,32 +119,36 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            if (p.w_resident) {
-                mbar_expect_tx(wfull_bar, (uint32_t)(taps * p.cblocks) * p.b_bytes);
-                for (int cb = 0; cb < p.cblocks; ++cb)
-                    for (int t = 0; t < taps; ++t)
-                        tma_load_3d(wres + (uint32_t)(cb * taps + t) * p.b_bytes, &tmW, wfull_bar, cb * 32, 0, t);
-            }
-            int s = 0;
-            uint32_t ph = 0;
-            const uint32_t tx = (uint32_t)p.nbox * p.box_bytes + (p.w_resident ? 0u : (uint32_t)taps * p.b_bytes);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int n = tile / p.rgroups, r0 = (tile - n * p.rgroups) * p.nr;
-                for (int ch = 0; ch < p.Cin; ch += p.kc) {  // one stage per kc channels
+        // lane 0 owns the barriers; the boxes of a stage are issued by as many lanes as there are boxes (a single thread
+        // issuing them one after the other was the bottleneck of the first version)
+        if (p.w_resident && lane == 0) {
+            mbar_expect_tx(wfull_bar, (uint32_t)(taps * p.cblocks) * p.b_bytes);
+            for (int cb = 0; cb < p.cblocks; ++cb)
+                for (int t = 0; t < taps; ++t)
+                    tma_load_3d(wres + (uint32_t)(cb * taps + t) * p.b_bytes, &tmW, wfull_bar, cb * 32, 0, t);
+        }
+        int s = 0;
+        uint32_t ph = 0;
+        const uint32_t tx = (uint32_t)p.nbox * p.box_bytes + (p.w_resident ? 0u : (uint32_t)taps * p.b_bytes);
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int n = tile / p.rgroups, r0 = (tile - n * p.rgroups) * p.nr;
+            for (int ch = 0; ch < p.Cin; ch += p.kc) {  // one stage per kc channels
+                const uint32_t sA = stage0 + (uint32_t)s * p.stage_bytes, fb = full_bar(s);
+                if (lane == 0) {
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    const uint32_t sA = stage0 + (uint32_t)s * p.stage_bytes, fb = full_bar(s);
                     mbar_expect_tx(fb, tx);
-                    for (int rr = 0; rr < rows_in; ++rr)
-                        for (int b = 0; b < p.nb; ++b)
-                            tma_load_4d(sA + (uint32_t)(rr * p.nb + b) * p.box_bytes, &tmX, fb, 32 * b, r0 + rr - p.ph, ch, n);
-                    if (!p.w_resident) {  // (kc == 32 here)
-                        const uint32_t sB = sA + (uint32_t)p.nbox * p.box_bytes;
-                        for (int t = 0; t < taps; ++t)
-                            tma_load_3d(sB + (uint32_t)t * p.b_bytes, &tmW, fb, ch, 0, t);
-                    }
-                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
+                __syncwarp();
+                for (int b = lane; b < p.nbox; b += 32) {
+                    const int rr = b / p.nb, cb = b - rr * p.nb;
+                    tma_load_4d(sA + (uint32_t)b * p.box_bytes, &tmX, fb, 32 * cb, r0 + rr - p.ph, ch, n);
+                }
+                if (!p.w_resident) {  // (kc == 32 here)
+                    const uint32_t sB = sA + (uint32_t)p.nbox * p.box_bytes;
+                    for (int t = lane; t < taps; t += 32)
+                        tma_load_3d(sB + (uint32_t)t * p.b_bytes, &tmW, fb, ch, 0, t);
+                }
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -437,6 +442,253 @@ conv_s1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// ---- wgrad, F <= 64: all kh * kw taps from ONE dY row box and ONE X row box per step ------------------------------------
+// For X row r the kh row taps pair it with the dY rows r + p - i.  Two consecutive dY rows of 64 filters stacked are a full
+// M = 128 operand: [dY(oh - 1); dY(oh)] against X row r yields tap i + 1 in TMEM lanes 0-63 and tap i in lanes 64-127, so
+// ceil(kh / 2) MMAs per step cover every row tap.  The kw column taps are kw copies of the X row shifted by j - p pixels,
+// stacked along N ([j][c] rows, N = kw * C): shifting cannot be a load (unaligned boxes trap), so four warps build the
+// shifted K-major tiles in shared memory from one aligned (40 pixel x C channel) raw box -- 16-byte loads, register
+// renaming, 16-byte swizzled stores.  A step therefore fetches 8 KB of dY + 10 KB of X for kh * kw taps (the column-shifted
+// global copies of the fallback kernel below cost 3 x the traffic plus a pre-pass).  dY rows live in a ring (consecutive
+// loads in consecutive 8 KB slots; slot 0 is mirrored behind the last slot so that a pair never wraps).
+struct Cw2Params {
+    int N, C, H, W, F, OH, OW, kh, kw, p;
+    int bnC, a_rows, csegs, chunks, rc;   // rc = X rows per work unit, chunks = row chunks per strip
+    int units, units_per_cta;
+    int ring;                            // dY ring slots (+1 mirror)
+    int npairs;
+    uint32_t tmem_cols, acc_stride;      // acc_stride = kw * bnC columns per row-tap pair
+    float *partial;                      // [CTAs][F][C][kh][kw]
+};
+
+// 16 pixels of one channel row, shifted by D columns, as four 16-byte chunks of a swizzled K-major tile row
+template <int D>
+__device__ __forceinline__ void cw2_store_shifted(const float (&v)[24], uint8_t *row, uint32_t chunk0, uint32_t sw) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+        *reinterpret_cast<float4 *>(row + (((chunk0 + kk) ^ sw) << 4)) =
+            make_float4(v[4 + 4 * kk + D], v[5 + 4 * kk + D], v[6 + 4 * kk + D], v[7 + 4 * kk + D]);
+}
+
+constexpr int CW2_RAW_W = 40;  // raw X box: 4 halo pixels left, 32, 4 right
+constexpr uint32_t CW2_DY_SLOT = 8192;
+constexpr int CW2_RAW_STAGES = 6;   // raw X row boxes in flight (the shifted tiles behind them are double-buffered)
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmXR, const Cw2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring_base = smem_base;                                     // (ring + 1) x 8 KB
+    const uint32_t b_tile = (uint32_t)(p.kw * p.bnC) * 128u;                  // kw shifted tiles of bnC rows
+    const uint32_t b_base = ring_base + (uint32_t)(p.ring + 1) * CW2_DY_SLOT;  // 2 x b_tile
+    const uint32_t raw_bytes = (uint32_t)p.bnC * CW2_RAW_W * 4u;
+    const uint32_t raw_base = b_base + 2u * b_tile;                           // CW2_RAW_STAGES x raw box
+    const uint32_t bar_base = (raw_base + (uint32_t)CW2_RAW_STAGES * raw_bytes + 15u) & ~15u;
+    auto dyfull = [&](int s) { return bar_base + 8u * s; };
+    auto dyempty = [&](int s) { return bar_base + 8u * (16 + s); };
+    auto rawfull = [&](int s) { return bar_base + 8u * (32 + s); };
+    auto rawempty = [&](int s) { return bar_base + 8u * (40 + s); };
+    auto bfull = [&](int s) { return bar_base + 8u * (48 + s); };
+    auto bempty = [&](int s) { return bar_base + 8u * (50 + s); };
+    const uint32_t tfull_bar = bar_base + 8u * 52;
+    const uint32_t tmem_slot = bar_base + 8u * 53;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDY);
+        tma_prefetch_desc(&tmXR);
+        for (int s = 0; s < p.ring; ++s) {
+            mbar_init(dyfull(s), 1);
+            mbar_init(dyempty(s), 1);
+        }
+        for (int s = 0; s < CW2_RAW_STAGES; ++s) {
+            mbar_init(rawfull(s), 1);
+            mbar_init(rawempty(s), 4);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bfull(s), 4);
+            mbar_init(bempty(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int u_lo = blockIdx.x * p.units_per_cta;
+    int u_hi = u_lo + p.units_per_cta;
+    if (u_hi > p.units) u_hi = p.units;
+    const int run_in = p.kh - 1;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int L = 0;        // dY loads so far (ring position)
+            int xs = 0;       // X rows so far (raw double buffer)
+            for (int u = u_lo; u < u_hi; ++u) {
+                const int strip = u / p.chunks, chunk = u - strip * p.chunks;
+                const int n = strip / p.csegs, c0 = (strip - n * p.csegs) * 32;
+                const int r_lo = chunk * p.rc;
+                int r_hi = r_lo + p.rc;
+                if (r_hi > p.H) r_hi = p.H;
+                const int oh0 = r_lo + p.p - run_in;  // first dY row of the unit (rows outside the tensor arrive as zeros)
+                const int nload = (r_hi - r_lo) + run_in;
+                for (int t = 0; t < nload; ++t, ++L) {
+                    const int slot = L % p.ring;
+                    mbar_wait(dyempty(slot), (((uint32_t)(L / p.ring)) & 1u) ^ 1u);
+                    const uint32_t fb = dyfull(slot), bytes = (uint32_t)p.a_rows * 128u;
+                    mbar_expect_tx(fb, slot == 0 ? 2u * bytes : bytes);
+                    tma_load_4d(ring_base + (uint32_t)slot * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
+                    if (slot == 0) tma_load_4d(ring_base + (uint32_t)p.ring * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
+                    if (t >= run_in) {  // the X row of this step
+                        const int rs = xs % CW2_RAW_STAGES;
+                        mbar_wait(rawempty(rs), (((uint32_t)(xs / CW2_RAW_STAGES)) & 1u) ^ 1u);
+                        mbar_expect_tx(rawfull(rs), raw_bytes);
+                        tma_load_4d(raw_base + (uint32_t)rs * raw_bytes, &tmXR, rawfull(rs), c0 - 4, r_lo + (t - run_in), 0, n);
+                        ++xs;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(128, p.kw * p.bnC, 0, 0);
+            int L = 0, xs = 0;
+            uint32_t started = 0;  // bit k: accumulator k has been written
+            for (int u = u_lo; u < u_hi; ++u) {
+                const int chunk = u % p.chunks;
+                const int r_lo = chunk * p.rc;
+                int r_hi = r_lo + p.rc;
+                if (r_hi > p.H) r_hi = p.H;
+                const int nload = (r_hi - r_lo) + run_in;
+                for (int t = 0; t < nload; ++t, ++L) {
+                    // every dY load is waited for exactly once, in order (the run-in rows carry no step of their own)
+                    mbar_wait(dyfull(L % p.ring), ((uint32_t)(L / p.ring)) & 1u);
+                    if (t < run_in) continue;
+                    const int bs = xs & 1;
+                    mbar_wait(bfull(bs), ((uint32_t)(xs >> 1)) & 1u);
+                    tc_fence_after();
+                    const uint32_t sB = b_base + (uint32_t)bs * b_tile;
+                    // row tap i pairs this X row with the dY row loaded i loads ago
+#pragma unroll 1
+                    for (int k = 0; k < p.npairs; ++k) {
+                        const int i_lo = 2 * k;                      // tap in lanes 64-127 (or 0-63 when it has no partner)
+                        const bool paired = i_lo + 1 < p.kh;
+                        const int Ltop = L - (paired ? i_lo + 1 : i_lo);
+                        const uint32_t sA = ring_base + (uint32_t)(Ltop % p.ring) * CW2_DY_SLOT;
+                        const uint32_t d_tmem = tmem_base + (uint32_t)k * p.acc_stride;
+#pragma unroll 1
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t ad = smem_desc(sA + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                            const uint64_t bd = smem_desc(sB + ks * 32u, 16u, 1024u, LAYOUT_SW128);
+                            mma_tf32(d_tmem, ad, bd, idesc, (((started >> k) & 1u) || ks > 0) ? 1u : 0u);
+                        }
+                        started |= 1u << k;
+                    }
+                    mma_commit(bempty(bs));
+                    mma_commit(dyempty((L - run_in) % p.ring));  // the oldest dY row of this step is done
+                    if (t == nload - 1)
+                        for (int d = run_in - 1; d >= 0; --d) mma_commit(dyempty((L - d) % p.ring));
+                    ++xs;
+                }
+            }
+            mma_commit(tfull_bar);
+        }
+    } else {
+        // ================================ shifter (warps 2..5), then epilogue ==========
+        const int t128 = threadIdx.x - 64;          // 0..127
+        const int c = t128 >> 1, hh = t128 & 1;      // channel row, 16-pixel half
+        int total_steps = 0;
+        for (int u = u_lo; u < u_hi; ++u) {
+            const int r_lo = (u % p.chunks) * p.rc;
+            int r_hi = r_lo + p.rc;
+            if (r_hi > p.H) r_hi = p.H;
+            total_steps += r_hi - r_lo;
+        }
+        for (int xs = 0; xs < total_steps; ++xs) {
+            const int rs = xs % CW2_RAW_STAGES, bs = xs & 1;
+            mbar_wait(rawfull(rs), ((uint32_t)(xs / CW2_RAW_STAGES)) & 1u);
+            mbar_wait(bempty(bs), (((uint32_t)(xs >> 1)) & 1u) ^ 1u);
+            if (c < p.bnC) {
+                // raw[c][16*hh .. 16*hh + 23] covers the 16 pixels of this half shifted by -4 .. +4
+                const float4 *src = reinterpret_cast<const float4 *>(smem_raw + (raw_base - smem_u32(smem_raw)) + (uint32_t)rs * raw_bytes +
+                                                                     (uint32_t)c * (CW2_RAW_W * 4) + (uint32_t)hh * 64u);
+                float v[24];
+#pragma unroll
+                for (int k4 = 0; k4 < 6; ++k4) {
+                    const float4 t4 = src[k4];
+                    v[4 * k4] = t4.x; v[4 * k4 + 1] = t4.y; v[4 * k4 + 2] = t4.z; v[4 * k4 + 3] = t4.w;
+                }
+                uint8_t *bt = smem_raw + (b_base - smem_u32(smem_raw)) + (uint32_t)bs * b_tile + (uint32_t)c * 128u;
+                for (int j = 0; j < p.kw; ++j) {
+                    uint8_t *row = bt + (uint32_t)(j * p.bnC) * 128u;
+                    const uint32_t sw = (uint32_t)(c & 7), ch0 = 4u * (uint32_t)hh;
+                    switch (j - p.p) {  // tile j holds X[col + d]: raw index 4 + col + d (uniform branch)
+                        case -4: cw2_store_shifted<-4>(v, row, ch0, sw); break;
+                        case -3: cw2_store_shifted<-3>(v, row, ch0, sw); break;
+                        case -2: cw2_store_shifted<-2>(v, row, ch0, sw); break;
+                        case -1: cw2_store_shifted<-1>(v, row, ch0, sw); break;
+                        case 0: cw2_store_shifted<0>(v, row, ch0, sw); break;
+                        case 1: cw2_store_shifted<1>(v, row, ch0, sw); break;
+                        case 2: cw2_store_shifted<2>(v, row, ch0, sw); break;
+                        case 3: cw2_store_shifted<3>(v, row, ch0, sw); break;
+                        default: cw2_store_shifted<4>(v, row, ch0, sw); break;
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bfull(bs));
+                mbar_arrive(rawempty(rs));
+            }
+        }
+        // epilogue: accumulator k, lanes 0-63 = tap 2k+1 (or the unpaired tap), lanes 64-127 = tap 2k
+        const int q = warp & 3;
+        if (u_lo < u_hi) {
+            mbar_wait(tfull_bar, 0);
+            tc_fence_after();
+        }
+        const int f = 32 * (q & 1) + lane;
+        const int taps = p.kh * p.kw;
+        float *o = p.partial + ((long long)blockIdx.x * p.F + f) * p.C * taps;
+        for (int k = 0; k < p.npairs; ++k) {
+            const bool paired = 2 * k + 1 < p.kh;
+            const int i = paired ? (q < 2 ? 2 * k + 1 : 2 * k) : 2 * k;
+            const bool live = paired || q < 2;
+            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)k * p.acc_stride;
+            for (int j = 0; j < p.kw; ++j) {
+                for (int cc = 0; cc < p.bnC; cc += 32) {
+                    uint32_t v[32];
+                    if (u_lo < u_hi) {
+                        tmem_ld32(t_row + (uint32_t)(j * p.bnC + cc), v);
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
+                    }
+                    if (live && f < p.F) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj)
+                            if (cc + jj < p.C) o[(long long)(cc + jj) * taps + i * p.kw + j] = __uint_as_float(v[jj]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 // filters -> [tap][out channel][in channel padded to 32]:  mode 0 (forward) Wp[(i,j)][f][c] = W[f][c][i][j];
 // mode 1 (dgrad) Wp[(i',j')][c][f] = W[f][c][kh-1-i'][kw-1-j']
 __global__ void conv_tma_permute_kernel(const float *__restrict__ w, float *__restrict__ wp, int F, int C, int kh, int kw,
@@ -476,7 +728,8 @@ int init_conv_tma() {
     }
     g_ct_encode = reinterpret_cast<EncodeTiledFn>(fn);
     if (cudaFuncSetAttribute(conv_s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_s1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess) {
+        cudaFuncSetAttribute(conv_s1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_s1_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess) {
         cudaGetLastError();
         return DK_OK;
     }
@@ -654,6 +907,55 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
     if (OH < 1 || OW < 1 || kh * kw <= 1 || kh > 5 || kw > 7 || p >= kw) return DK_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(dy) || (W % 4) != 0 || (OW % 4) != 0 || F > 128 || F < 8 || C < 8 || OW < 8) return DK_ERR_UNSUPPORTED;
     if ((int64_t)N * kw >= (1 << 30)) return DK_ERR_UNSUPPORTED;
+    if (g_ct_wgrad2 && F <= 64 && ct_round_up(C, 32) <= 64 && kw * ct_round_up(C, 32) <= 256 && p <= 4 && kw - 1 - p <= 4 &&
+        ((kh + 1) / 2) * kw * ct_round_up(C, 32) <= 512) {
+        Cw2Params q = {};
+        q.N = N; q.C = C; q.H = H; q.W = W; q.F = F; q.OH = OH; q.OW = OW; q.kh = kh; q.kw = kw; q.p = p;
+        q.bnC = ct_round_up(C, 32);
+        q.a_rows = ct_round_up(F, 8);
+        q.csegs = (OW + 31) / 32;
+        const int strips = N * q.csegs;
+        // work unit = rc X rows of one strip; pick the chunking that fills the SMs best (each unit re-reads kh - 1 dY rows)
+        int best_rc = H;
+        double best_cost = 1e30;
+        for (int div = 1; div <= 8; ++div) {
+            const int rc = (H + div - 1) / div;
+            if (rc < 4 && div > 1) break;
+            const int chunks = (H + rc - 1) / rc;
+            const long long units = (long long)strips * chunks;
+            const double cost = (double)ceil_div(units, sm_count()) * (rc + kh - 1);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best_rc = rc; }
+        }
+        q.rc = best_rc;
+        q.chunks = (H + q.rc - 1) / q.rc;
+        q.units = strips * q.chunks;
+        q.units_per_cta = (int)ceil_div(q.units, sm_count());
+        const int ctas = (int)ceil_div(q.units, q.units_per_cta);
+        q.npairs = (kh + 1) / 2;
+        q.acc_stride = (uint32_t)(kw * q.bnC);
+        q.tmem_cols = ct_pow2_cols((uint32_t)q.npairs * q.acc_stride);
+        q.ring = kh + 5 > 15 ? 15 : kh + 5;
+        const int taps = kh * kw;
+        const size_t need = (size_t)ctas * F * C * taps * sizeof(float);
+        if (ws == nullptr || ws_bytes < need + 1024) return DK_ERR_UNSUPPORTED;
+        q.partial = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(ws) + 255u) & ~(uintptr_t)255u);
+        CUtensorMap ta, tr;
+        const uint64_t da[4] = {(uint64_t)OW, (uint64_t)OH, (uint64_t)F, (uint64_t)N};
+        const uint32_t ba[4] = {32, 1, (uint32_t)q.a_rows, 1};
+        int rc2 = ct_map(&ta, dy, 4, da, ba, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc2) return rc2;
+        const uint64_t dbr[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N};
+        const uint32_t bbr[4] = {CW2_RAW_W, 1, (uint32_t)q.bnC, 1};
+        rc2 = ct_map(&tr, x, 4, dbr, bbr, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc2) return rc2;
+        const size_t smem = (size_t)(q.ring + 1) * CW2_DY_SLOT + 2 * (size_t)(kw * q.bnC) * 128 + CW2_RAW_STAGES * (size_t)q.bnC * CW2_RAW_W * 4 + 1024 + 16 + 8 * 64;
+        if (smem > (size_t)CT_SMEM_MAX) return DK_ERR_UNSUPPORTED;
+        conv_s1_wgrad2_kernel<<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
+        DK_LAUNCH_CHECK();
+        splitk_reduce_launch(q.partial, w, dw, l2, (int64_t)F * C * taps, ctas, st);
+        DK_LAUNCH_CHECK();
+        return DK_OK;
+    }
     CwParams q = {};
     q.N = N; q.C = C; q.H = H; q.W = W; q.F = F; q.OH = OH; q.OW = OW; q.kh = kh; q.kw = kw; q.p = p;
     q.bnC = ct_round_up(C, 32);

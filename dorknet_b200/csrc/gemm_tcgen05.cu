@@ -1208,6 +1208,7 @@ int dk_tc_debug_set(int key, int value) {
         case 14: dk::g_two_per_sm = value; break;  // 0: forward / dgrad GEMMs never run two CTAs per SM
         case 11: dk::g_short_a = value; break;  // 0: wgrad dY boxes always 128 rows
         case 10: dk::g_repack_mask = value; break;  // bit0: pad misaligned planes for TMA, bit1: repack small strided planes
+        case 19: dk::g_ct_wgrad2 = value; break;  // 0: conv_tma wgrad through column-shifted global copies only
         case 18: dk::g_ct_kc16 = value; break;  // conv_tma forward / dgrad: 0 = 32-channel stages only
         case 17: dk::g_conv_tma_enabled = value; break;  // 0: stride-1 k x k convolutions skip conv_tma.cu (gather variants instead)
         case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
