@@ -40,7 +40,7 @@ def _cupy_shim():
 
 
 def install(shim_cupy=True, stub_h5py=True):
-    """Idempotent.  Refuses to shadow a real, already-imported `layers` package."""
+    """Idempotent (stub_h5py: bind `h5py` to dorknet_b200.minih5 when the real package is missing).  Refuses to shadow a real, already-imported `layers` package."""
     pkg = importlib.import_module("dorknet_b200.layers")
     existing = sys.modules.get("layers")
     if existing is not None and existing is not pkg:
@@ -61,10 +61,6 @@ def install(shim_cupy=True, stub_h5py=True):
         try:
             importlib.import_module("h5py")
         except ImportError:
-            stub = types.ModuleType("h5py")
-
-            class File:
-                def __init__(self, *a, **k):
-                    raise NotImplementedError("h5py is not installed; checkpoints are outside the B200 hot path")
-            stub.File = File
-            sys.modules["h5py"] = stub
+            # the reference's `import h5py` (network/feed_forward_network.py:2, every layer module) gets the pure-Python
+            # HDF5 subset its checkpoints use: save_weights_to_h5 / load_network_from_json_and_h5 run unchanged
+            sys.modules["h5py"] = importlib.import_module("dorknet_b200.minih5")

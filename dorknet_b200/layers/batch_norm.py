@@ -33,6 +33,10 @@ class _RunningStats(dict):
 
 class BatchNormLayer(Layer):
     """https://arxiv.org/pdf/1502.03167.pdf -- same constructor as batch_norm.py:13-14."""
+    _h5_attrs = ("input_dimension", "run_momentum", "incoming_chans", "eps")
+    _h5_params = ("gamma", "beta")  # layers/batch_norm.py:176-232
+    _h5_state = ("running_mean", "running_std")
+
 
     def __init__(self, layer_name, input_dimension=4, incoming_chans=None, run_momentum=0.95, is_on_gpu=True):
         super().__init__(layer_name)

@@ -8,6 +8,9 @@ from ..array import LazyDeviceArray
 class ConvLayer(Layer):
     """Dense k x k convolution as an implicit GEMM: pad, im2col and the NHWC->NCHW transpose of
     convolution.py:58-87 never materialise; wgrad / dgrad replace the two GEMMs + row2im of :90-126."""
+    _h5_attrs = ("with_bias", "num_filters", "filter_chans", "f_rows", "f_cols", "stride", "padding")
+    _h5_params = ("weights", "bias")  # layers/convolution.py:226-281
+
 
     def __init__(self, layer_name, filter_block_shape=None, stride=1, padding=1,
                  with_bias=True, weight_regulariser=None, weight_initialiser="normal"):

@@ -5,6 +5,9 @@ from .layer import Layer, api, runtime, asarray
 
 
 class DenseLayer(Layer):
+    _h5_attrs = ("incoming_chans", "output_dim", "with_bias")
+    _h5_params = ("weights", "bias")  # layers/dense_layer.py:69-117
+
 
     def __init__(self, layer_name, incoming_chans=None, output_dim=None, with_bias=True,
                  weight_regulariser=None, weight_initialiser="normal"):

@@ -6,6 +6,9 @@ from .layer import Layer, api, runtime, asarray
 
 class DepthwiseConvLayer(Layer):
     """filter_block_shape = (num_incoming_channels, num_filter_rows, num_filter_cols)"""
+    _h5_attrs = ("stride", "padding", "with_bias", "num_filters", "f_rows", "f_cols")
+    _h5_params = ("weights", "bias")  # layers/depthwise_convolution.py:300-353
+
 
     def __init__(self, layer_name, filter_block_shape=None, stride=1, padding=1, with_bias=True,
                  weight_regulariser=None, weight_initialiser="normal"):

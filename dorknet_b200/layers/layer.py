@@ -98,12 +98,19 @@ class Layer:
             out += self.weight_regulariser.forward(self._param("weights"))
         return out
 
-    # checkpoints (HDF5) are outside the hot path
+    # -- checkpoints: the reference's HDF5 layout (dorknet_b200/checkpoint.py) ------------------
+    _h5_attrs = ()  # constructor arguments stored as attrs of <name>/layer_info
+    _h5_optional_attrs = {}  # attr -> default when an old file lacks it
+    _h5_params = ()  # learned_params keys (+ grads/<key>)
+    _h5_state = ()  # non_learned_params keys
+
     def save_to_h5(self, open_f, save_grads=True):
-        raise NotImplementedError("HDF5 checkpoints are not part of the B200 hot path yet")
+        from ..checkpoint import save_layer
+        save_layer(self, open_f, save_grads=save_grads)
 
     def load_from_h5(self, open_f, load_grads=True):
-        raise NotImplementedError("HDF5 checkpoints are not part of the B200 hot path yet")
+        from ..checkpoint import load_layer
+        load_layer(self, open_f, load_grads=load_grads)
 
 
 __all__ = ["Layer", "api", "runtime", "DeviceArray", "DeviceScalar", "asarray", "empty", "zeros", "np"]

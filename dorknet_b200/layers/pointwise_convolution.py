@@ -9,6 +9,10 @@ class PointwiseConvLayer(Layer):
     """1x1 convolution.  The reference transposes to NHWC, calls a GEMM and transposes back
     (pointwise_convolution.py:46-55); here the GEMM runs directly on the NCHW tensor
     (Y[n] = W[F,C] . X[n][C,HW]), so no transposed copy exists in either direction."""
+    _h5_attrs = ("with_bias", "num_filters", "num_channels", "stride")
+    _h5_optional_attrs = {"stride": 1}  # layers/pointwise_convolution.py:111-115
+    _h5_params = ("weights", "bias")  # layers/pointwise_convolution.py:77-130
+
 
     def __init__(self, layer_name, stride=1, filter_block_shape=None, with_bias=True,
                  weight_regulariser=None, weight_initialiser="normal"):

@@ -96,3 +96,38 @@ class ResidualBlock(Layer):
         if type(first) is DepthwiseConvLayer and tuple(first.input_shape) == tuple(skip_dx.shape):
             return first.backward(first_dx_in, dx_add=skip_dx)
         return first.backward(first_dx_in) + skip_dx
+
+    # -- checkpoints (residual_block.py:99-152): the block's layer_info lists its members by type and name, the
+    #    members are ordinary top-level groups of the file
+    def save_to_h5(self, open_f, save_grads=True):
+        info = open_f.create_dataset(self.layer_name + "/layer_info", dtype=np.float32)
+        info.attrs["type"] = type(self).__name__
+        info.attrs["layer_type_list"] = [type(l).__name__ for l in self.layer_list]
+        info.attrs["layer_name_list"] = [l.layer_name for l in self.layer_list]
+        info.attrs["post_skip_activation_type"] = type(self.post_skip_activation).__name__
+        info.attrs["post_skip_activation_name"] = self.post_skip_activation.layer_name
+        members = list(self.layer_list)
+        if self.skip_projection is not None:
+            info.attrs["skip_projection_type"] = type(self.skip_projection).__name__
+            info.attrs["skip_projection_name"] = self.skip_projection.layer_name
+            members.append(self.skip_projection)
+        members.append(self.post_skip_activation)
+        for l in members:
+            l.save_to_h5(open_f, save_grads=save_grads)
+
+    def load_from_h5(self, open_f, load_grads=True):
+        from ..checkpoint import make_layer
+        info = open_f[self.layer_name + "/layer_info"].attrs
+        self.layer_list = [make_layer(t, str(n) if not isinstance(n, bytes) else n.decode())
+                           for t, n in zip(info["layer_type_list"], info["layer_name_list"])]
+        for l in self.layer_list:
+            l.load_from_h5(open_f, load_grads=load_grads)
+        self.skip_projection = None
+        if info.get("skip_projection_type", None):
+            self.skip_projection = make_layer(info["skip_projection_type"], info["skip_projection_name"])
+            if type(self.skip_projection) is not PointwiseConvLayer:
+                print("ResidualBlock: Unrecognised skip_projection type {}".format(info["skip_projection_type"]))
+            self.skip_projection.load_from_h5(open_f, load_grads=load_grads)
+        self.post_skip_activation = make_layer(info["post_skip_activation_type"], info["post_skip_activation_name"])
+        self.post_skip_activation.load_from_h5(open_f, load_grads=load_grads)
+        self.is_on_gpu = False

@@ -77,8 +77,34 @@ class FeedForwardNetwork:
         with open(fname, "w") as f:
             json.dump(structure, f, indent=4)
 
-    def save_weights_to_h5(self, fname):
-        raise NotImplementedError("HDF5 checkpoints are outside the B200 hot path (SURVEY.md §8f-2)")
+    def save_weights_to_h5(self, fname, optimiser=None):
+        """feed_forward_network.py:90-95: one group per layer in the reference's HDF5 layout.  `optimiser`
+        (extension): also store its velocities / running squared gradients."""
+        from ..checkpoint import h5_module, save_optimiser_state
+        with h5_module().File(fname, "w") as f:
+            for layer in self.layers:
+                layer.save_to_h5(f)
+            if self.loss_layer is not None:
+                self.loss_layer.save_to_h5(f)
+            if optimiser is not None:
+                save_optimiser_state(optimiser, f)
 
-    def load_network_from_json_and_h5(self, json_fname, h5_fname):
-        raise NotImplementedError("HDF5 checkpoints are outside the B200 hot path (SURVEY.md §8f-2)")
+    def load_network_from_json_and_h5(self, json_fname, h5_fname, optimiser=None):
+        """feed_forward_network.py:106-139: layer order and names from the JSON structure file, types and
+        parameters from the HDF5 file."""
+        from ..checkpoint import h5_module, load_optimiser_state, make_layer
+        with open(json_fname, "r") as f:
+            structure = json.load(f)
+        with h5_module().File(h5_fname, "r") as f:
+            self.name = structure.pop("name")
+            for layer_name in structure.keys():
+                l_type = f[layer_name + "/layer_info"].attrs["type"]
+                layer = make_layer(l_type, layer_name)
+                layer.load_from_h5(f)
+                if type(layer).__name__ == "SoftmaxWithCrossEntropy":
+                    self.loss_layer = layer
+                else:
+                    self.layers.append(layer)
+            if optimiser is not None:
+                load_optimiser_state(optimiser, f)
+        self.is_on_gpu = False

@@ -5,9 +5,13 @@ from ._multi import MultiTensorOptimiser, collect_layers
 
 
 class RMSProp(MultiTensorOptimiser):
-    def __init__(self, network, learning_rate, decay_rate):
+    def __init__(self, network, learning_rate, decay_rate, fixed_traversal=False, include_skip_projections=False):
+        """fixed_traversal=False is the reference (RMSProp.py:12-15 re-tests the block, so nothing inside a
+        ResidualBlock is updated: SURVEY.md F5); True descends as SGDMomentum does; include_skip_projections also
+        updates the skip projections (both opt-in)."""
         super().__init__(network, learning_rate)
-        self.learnable_layers = collect_layers(network, descend=False)
+        self.learnable_layers = collect_layers(network, descend=fixed_traversal or include_skip_projections,
+                                               include_skip=include_skip_projections)
         self.decay_rate = decay_rate
         self.grad_cache = {}
 

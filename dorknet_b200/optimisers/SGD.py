@@ -7,9 +7,13 @@ from ._multi import MultiTensorOptimiser, collect_layers
 class SGD(MultiTensorOptimiser):
     needs_state = False
 
-    def __init__(self, network, learning_rate):
+    def __init__(self, network, learning_rate, fixed_traversal=False, include_skip_projections=False):
+        """fixed_traversal=False is the reference (SGD.py:8-11 never updates anything inside a ResidualBlock:
+        SURVEY.md F5); True descends into blocks as SGDMomentum does; include_skip_projections additionally updates
+        the skip projections (both opt-in)."""
         super().__init__(network, learning_rate)
-        self.learnable_layers = collect_layers(network, descend=False)
+        self.learnable_layers = collect_layers(network, descend=fixed_traversal or include_skip_projections,
+                                               include_skip=include_skip_projections)
 
     def update_weights(self):
         """w += -lr * g for every tensor of the update set, one launch."""

@@ -67,6 +67,50 @@ class MultiTensorOptimiser:
         else:
             plain(tab, n, max_n)
 
+    # -- state checkpoint (the reference keeps this state in memory only) -------------------
+    def hyper_parameters(self):
+        out = {"learning_rate": float(self.learning_rate)}
+        for k in ("momentum", "decay_rate"):
+            if hasattr(self, k):
+                out[k] = float(getattr(self, k))
+        return out
+
+    def state_dict(self):
+        """{(layer_name, param): host ndarray} of the per-tensor state (velocities / running squared gradients);
+        empty for plain SGD.  Tensors that were never updated yet are reported as zeros, their state's value."""
+        out = {}
+        if not self.needs_state:
+            return out
+        for layer in self.learnable_layers:
+            for k in layer.learned_params.keys():
+                st = self.grad_cache.get(layer, {}).get(k)
+                if isinstance(st, DeviceArray):
+                    st = st.get()
+                elif st is None:
+                    st = np.zeros(np.shape(layer.learned_params[k]), np.float32)
+                out[(layer.layer_name, k)] = np.asarray(st, np.float32)
+        return out
+
+    def load_state_dict(self, state):
+        """Inverse of state_dict(); every tensor of the update set must be present with its shape."""
+        if not self.needs_state:
+            return
+        for layer in self.learnable_layers:
+            for k in layer.learned_params.keys():
+                key = (layer.layer_name, k)
+                if key not in state:
+                    raise KeyError("optimiser state has no entry for {}/{}".format(*key))
+                v = np.ascontiguousarray(state[key], np.float32)
+                if v.shape != tuple(np.shape(layer.learned_params[k])):
+                    raise ValueError("optimiser state {}/{}: shape {} != parameter shape {}".format(
+                        key[0], key[1], v.shape, tuple(np.shape(layer.learned_params[k]))))
+                cur = self.grad_cache.setdefault(layer, {}).get(k)
+                if isinstance(cur, DeviceArray) and cur.shape == v.shape:
+                    cur.set(v)  # in place: the device table (and a captured CUDA graph) keeps pointing at it
+                else:
+                    self.grad_cache[layer][k] = v  # uploaded by _build_table
+                    self._sig = None
+
     def set_learning_rate(self, new_lr):
         self.learning_rate = new_lr
 

@@ -51,3 +51,50 @@ def test_p2p_gradient_exchange_two_gpus():
                           "--master-addr", "127.0.0.1", "--master-port", "29541",
                           os.path.join(ROOT, "tests", "p2p_check.py")], capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("which", ["mini", "mnist"])
+def test_batchnorm_folded_inference_matches_test_mode(which):
+    """fold_batchnorm(net) scores like net.forward(test_mode=True) (batch_norm.py:101-115 as an affine
+    map absorbed by the preceding layer's weights); every linear -> BatchNorm pair disappears; terminal_layer_name
+    early exit (feed_forward_network.py:55-56) still works."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import dorknet_b200.workloads as wl
+    from dorknet_b200.inference import fold_batchnorm
+    from net_defs import build_small_net
+    M = wl.ours()
+    rng = np.random.default_rng(11)
+    if which == "mini":
+        net, shape, classes = build_small_net(M, seed=5), (6, 3, 33, 33), 5
+    else:
+        net, shape, classes = wl.build_mnist_convnet(M, seed=5), (16, 1, 28, 28), 10
+    X = rng.standard_normal(shape).astype(np.float32)
+    Y = np.zeros((shape[0], classes), np.float32)
+    Y[np.arange(shape[0]), rng.integers(0, classes, shape[0])] = 1
+    opt = M.SGDMomentum(net, 0.05, 0.9)
+    for _ in range(3):  # running statistics and gamma / beta away from their initial values
+        net.forward(X, Y)
+        net.backward()
+        opt.update_weights()
+    Xt = rng.standard_normal(shape).astype(np.float32)
+    _, want = net.forward(Xt, None, test_mode=True)
+    want = want.get()
+    folded = fold_batchnorm(net)
+    n_bn = sum(1 for l in wl.iter_param_layers(net) if type(l).__name__ == "BatchNormLayer")
+    assert len(folded.folded_batchnorms) == n_bn and n_bn > 0
+    assert not any(type(l).__name__ == "BatchNormLayer" for l in wl.iter_param_layers(folded))
+    _, got = folded.forward(Xt)
+    got = got.get()
+    assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max() + 1e-6
+    assert (np.argmax(got, 1) == np.argmax(want, 1)).mean() >= 0.9
+    # early exit at a surviving layer: same activations as the unfolded network one BatchNorm later
+    first = net.layers[0].layer_name
+    _, a = folded.forward(Xt, terminal_layer_name=first)
+    _, b = net.forward(Xt, None, test_mode=True, terminal_layer_name=net.layers[1].layer_name)
+    a, b = a.get(), b.get()
+    assert a.shape == b.shape and np.abs(a - b).max() <= 2e-3 * np.abs(b).max() + 1e-6
+    with pytest.raises(KeyError):
+        folded.forward(Xt, terminal_layer_name=net.layers[1].layer_name)
+    with pytest.raises(ValueError):
+        folded.forward(Xt, Y, test_mode=False)

@@ -40,6 +40,34 @@ def test_optimiser_update_sets_reproduce_reference_quirks():
     assert [l.layer_name for l in collect_layers(net, descend=True, include_skip=True)] == ["a", "b", "c", "skip"]
 
 
+def test_sgd_and_rmsprop_fixed_traversal_is_opt_in_and_state_round_trips():
+    """SURVEY §8f-4: the reference update sets stay the default; fixed_traversal / include_skip_projections widen them;
+    state_dict / load_state_dict carry velocities by (layer name, parameter)."""
+    from dorknet_b200.optimisers.SGD import SGD
+    from dorknet_b200.optimisers.RMSProp import RMSProp
+    from dorknet_b200.optimisers.SGDMomentum import SGDMomentum
+    a, b, c, skip, relu = FakeLayer("a"), FakeLayer("b"), FakeLayer("c"), FakeLayer("skip"), FakeLayer("r", False)
+    net = FakeNet([a, relu, FakeBlock("blk", [b, relu, c], skip)])
+    names = lambda o: [l.layer_name for l in o.learnable_layers]  # noqa: E731
+    assert names(SGD(net, 0.1)) == ["a"] and names(RMSProp(net, 0.1, 0.9)) == ["a"]
+    assert names(SGD(net, 0.1, fixed_traversal=True)) == ["a", "b", "c"]
+    assert names(RMSProp(net, 0.1, 0.9, fixed_traversal=True)) == ["a", "b", "c"]
+    assert names(SGD(net, 0.1, include_skip_projections=True)) == ["a", "b", "c", "skip"]
+    assert names(RMSProp(net, 0.1, 0.9, fixed_traversal=True, include_skip_projections=True)) == ["a", "b", "c", "skip"]
+    opt = SGDMomentum(net, 0.1, 0.9)
+    assert opt.hyper_parameters() == {"learning_rate": 0.1, "momentum": 0.9}
+    sd = opt.state_dict()
+    assert sorted(sd) == [("a", "weights"), ("b", "weights"), ("c", "weights")] and all(v.shape == (2,) for v in sd.values())
+    sd[("b", "weights")] = np.array([1.0, 2.0], np.float32)
+    opt.load_state_dict(sd)
+    np.testing.assert_array_equal(opt.state_dict()[("b", "weights")], [1.0, 2.0])
+    with pytest.raises(KeyError):
+        opt.load_state_dict({("a", "weights"): np.zeros(2, np.float32)})
+    with pytest.raises(ValueError):
+        opt.load_state_dict({k: np.zeros(3, np.float32) for k in sd})
+    assert SGD(net, 0.1).state_dict() == {}
+
+
 def test_constructors_match_reference_signatures_and_init():
     from dorknet_b200.layers.convolution import ConvLayer
     from dorknet_b200.layers.depthwise_convolution import DepthwiseConvLayer
