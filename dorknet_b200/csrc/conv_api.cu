@@ -23,7 +23,7 @@ static size_t conv_ws(int N, int C, int H, int W, int F, int kh, int kw, int s, 
     const size_t simt = simt_wgrad_ws_bytes(F, C * kh * kw, (int64_t)N * OH * OW);
     const size_t tc = max_sz(max_sz(tc_conv_ws_bytes(N, C, H, W, F, kh, kw, s, p), conv_rows_ws_bytes(N, C, H, W, F, kh, kw, s, p)),
                              conv_tma_ws_bytes(N, C, H, W, F, kh, kw, s, p));
-    return max_sz(simt, tc) + 256;
+    return max_sz(max_sz(simt, tc), tc_conv_mat_ws_bytes(N, C, H, W, F, kh, kw, s, p)) + 256;
 }
 
 }  // namespace dk

@@ -34,6 +34,7 @@ int tc_dense_bwd(const float *dy, const float *x, const float *w, float *dx, flo
                  int out_dim, void *ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
 size_t tc_dense_ws_bytes(int B, int in_dim, int out_dim);
+size_t tc_conv_mat_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
 
 // ---- small-K (C*kh*kw <= 128) row-staged implicit-GEMM convolution: forward + wgrad (conv_rows.cu) -------------------
 int conv_rows_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,

@@ -884,8 +884,9 @@ static int repack_launch(const float *src, float *dst, int64_t rows, int SH, int
 }
 
 // ---- pointwise (1x1, pad 0, stride s) ------------------------------------------------------------------------
+// x_pitch > 0: x is a dense [N][C][x_pitch] tensor (x_pitch % 4 == 0, rows zero-padded past H*W; s must be 1)
 static int pw_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int s,
-                  void *ws, size_t ws_bytes, cudaStream_t st) {
+                  void *ws, size_t ws_bytes, cudaStream_t st, int64_t x_pitch = 0) {
     const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
     const int64_t P = (int64_t)OH * OW;
     if (!tma_ok(w, C) || !dims_ok(P, (int64_t)H * W)) return DK_ERR_UNSUPPORTED;
@@ -898,6 +899,11 @@ static int pw_fwd(const float *x, const float *w, const float *bias, float *y, i
     CUtensorMap ta = {}, tb;
     int rc = make_map(&tb, w, C, F, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    if (x_pitch > 0) {
+        rc = make_map(&ta, x, x_pitch, C, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+        if (rc) return rc;
+        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st, true);
+    }
     if (s == 1 && tma_ok(x, P)) {
         rc = make_map(&ta, x, P, C, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
         if (rc) return rc;
@@ -947,7 +953,7 @@ static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
 }
 
 static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
-                    int s, void *ws, size_t ws_bytes, cudaStream_t st) {
+                    int s, void *ws, size_t ws_bytes, cudaStream_t st, int64_t x_pitch = 0) {
     const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
     const int64_t P = (int64_t)OH * OW;
     if (!dims_ok(P, (int64_t)H * W)) return DK_ERR_UNSUPPORTED;
@@ -955,8 +961,8 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     q.mode = 1; q.a_mn = 0; q.b_mn = 0; q.b_batched = 1;
     q.M = F; q.N = C; q.K = (int)P; q.batches = N;
     fill_common(q);
-    bool a_tma = tma_ok(dy, P), b_tma = (s == 1) && tma_ok(x, P);
-    const bool hybrid = g_hybrid_wgrad && a_tma && b_tma;
+    bool a_tma = tma_ok(dy, P), b_tma = x_pitch > 0 || ((s == 1) && tma_ok(x, P));
+    const bool hybrid = g_hybrid_wgrad && a_tma && b_tma && x_pitch == 0;
     if (a_tma && b_tma && !hybrid) {
         // wide pipeline items for long planes: 4 (or 2) consecutive k-blocks per item, if at least two stages still fit and
         // the rounding of the plane to whole items wastes little
@@ -986,7 +992,7 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     q.epi = 1; q.out = reinterpret_cast<float *>(ws); q.bias = nullptr; q.ldo = 0;
     CUtensorMap ta = {}, tb = {};
     int rc = DK_OK;
-    int64_t pa = P, pb = P;  // row pitches of the operands the maps describe
+    int64_t pa = P, pb = x_pitch > 0 ? x_pitch : P;  // row pitches of the operands the maps describe
     {
         void *rest = reinterpret_cast<char *>(ws) + need;
         size_t rest_bytes = ws_bytes - need;
@@ -1096,11 +1102,175 @@ static int cv_dgrad(const float *dy, const float *w, float *dx, int N, const Con
     return tc_launch(ta, tb, q, ConvDgradMN{dy, g}, ConvDgradWKM{w, g}, st);
 }
 
+// ---- general convolution through materialised patches ------------------------------------------------------------------
+// Shapes the aligned-box kernels of conv_tma.cu / conv_rows.cu cannot take (stride > 1 with K > 128, row pitches that are not
+// a multiple of 16 bytes: MNIST's 4x4 stride-2 and 14x14 layers) used to run on the gather variants above, which are bound by
+// the issue rate of four loader warps (dgrad of 32 -> 64 4x4 s2 at 28x28, batch 64: 1.27 ms for 9.6 MB).  The reference's own
+// decomposition (im2col.pyx:16-36 + matmul + row2im, convolution.py:58-126) maps onto the all-TMA pointwise GEMMs instead: the
+// patches are written ONCE, transposed -- Pt[n][k = (c,i,j)][p = (oh,ow)], pitch rounded up to 4 floats -- so that a
+// convolution over C channels IS the pointwise convolution of a K = C*kh*kw channel tensor:
+//   forward  Y[n]  = W[F,K] . Pt[n]                 (pw_fwd)
+//   wgrad    dW    = sum_n dY[n] . Pt[n]^T          (pw_wgrad)
+//   dgrad    dPt[n] = W^T . dY[n], then dX = gather-form col2im of dPt (every dX element adds its <= ceil(k/s)^2 taps: no atomics)
+// The patch tensor lives in the caller's workspace; for these layers it is a few tens of MB and stays in the 126 MB L2.
+constexpr size_t TC_MAT_MAX_BYTES = (size_t)768 << 20;
+int g_conv_mat_enabled = 1;
+
+// one warp per (n, k) row of Pt: the (c, i, j) split is done once per row, a lane writes 4 consecutive pixels per pass
+// (one 16-byte store; consecutive lanes -> consecutive 16-byte chunks), all index arithmetic in 32 bits
+template <int S>
+__global__ void __launch_bounds__(256)
+im2col_t_kernel(const float *__restrict__ x, float *__restrict__ pt, ConvGeom g, int P, int Pp, int rows) {
+    const int s = S > 0 ? S : g.s;
+    const int kk = g.kh * g.kw, K = g.C * kk, q4 = Pp >> 2;
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+        const int n = row / K, k = row - n * K;
+        const int c = k / kk, t = k - c * kk;
+        const int i = t / g.kw, j = t - i * g.kw;
+        const float *xc = x + ((long long)n * g.C + c) * g.H * g.W;
+        float *dst = pt + (long long)row * Pp;
+        for (int c4 = lane; c4 < q4; c4 += 32) {
+            const int p0 = c4 * 4;
+            int oh = p0 / g.OW, ow = p0 - oh * g.OW;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ih = oh * s - g.p + i, iw = ow * s - g.p + j;
+                v[e] = (p0 + e < P && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) ? __ldg(xc + ih * g.W + iw) : 0.0f;
+                if (++ow == g.OW) { ow = 0; ++oh; }
+            }
+            *reinterpret_cast<float4 *>(dst + p0) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// dX[n][c][h][w] = sum over the taps (i, j) that reach it of dPt[n][(c,i,j)][oh][ow], oh*s + i - p = h, ow*s + j - p = w
+// (im2col.pyx:209-234 scatter-adds; this is the same sum written as a gather, so it needs no atomics and is deterministic).
+// A thread owns one dX element; consecutive threads = consecutive w, so for a fixed tap the warp reads dPt with stride 1/s.
+// KH, KW, S > 0: compile-time filter geometry (the tap loops unroll and the divisions by S become shifts).
+template <int KH, int KW, int S>
+__global__ void __launch_bounds__(256)
+col2im_t_kernel(const float *__restrict__ dpt, float *__restrict__ dx, ConvGeom g, int P, long long planes) {
+    const int kh = KH > 0 ? KH : g.kh, kw = KW > 0 ? KW : g.kw, s = S > 0 ? S : g.s;
+    const int HW = g.H * g.W;
+    const int per_plane = (HW + 255) / 256;
+    for (long long blk = blockIdx.x; blk < planes * per_plane; blk += gridDim.x) {
+        const long long plane = blk / per_plane;  // (n, c)
+        const int e = (int)(blk - plane * per_plane) * 256 + threadIdx.x;
+        if (e >= HW) continue;
+        const int h = e / g.W, w = e - h * g.W;
+        const float *base = dpt + plane * (long long)(kh * kw) * P;
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kh; ++i) {
+            const int th = h + g.p - i;
+            const int oh = th / s;
+            if (th < 0 || oh * s != th || oh >= g.OH) continue;
+#pragma unroll
+            for (int j = 0; j < kw; ++j) {
+                const int tw = w + g.p - j;
+                const int ow = tw / s;
+                if (tw < 0 || ow * s != tw || ow >= g.OW) continue;
+                acc += __ldg(base + (i * kw + j) * P + oh * g.OW + ow);
+            }
+        }
+        dx[plane * HW + e] = acc;
+    }
+}
+
+template <int KH, int KW, int S>
+static void col2im_launch(const float *dpt, float *dx, const ConvGeom &g, int P, long long planes, cudaStream_t st) {
+    const long long blocks = planes * ((g.H * g.W + 255) / 256);
+    const int grid = (int)(blocks < (long long)sm_count() * 16 ? blocks : (long long)sm_count() * 16);
+    col2im_t_kernel<KH, KW, S><<<grid, 256, 0, st>>>(dpt, dx, g, P, planes);
+}
+
+static size_t mat_patch_bytes(int N, const ConvGeom &g) {
+    const int64_t P = (int64_t)g.OH * g.OW;
+    return (size_t)N * g.C * g.kh * g.kw * (size_t)repack_pitch(P) * sizeof(float) + 512;
+}
+static bool mat_ok(const float *w, int N, const ConvGeom &g) {
+    const int Kf = g.C * g.kh * g.kw;
+    if (!g_conv_mat_enabled || g.kh * g.kw <= 1 || g.OH < 1 || g.OW < 1) return false;
+    if (!tma_ok(w, Kf) || (int64_t)N * Kf >= ((int64_t)1 << 30)) return false;
+    return mat_patch_bytes(N, g) <= TC_MAT_MAX_BYTES;
+}
+size_t tc_conv_mat_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p) {
+    const ConvGeom g = mk_geom(C, H, W, F, kh, kw, s, p);
+    if (g.OH < 1 || g.OW < 1 || kh * kw <= 1 || !g_conv_mat_enabled) return 0;
+    const size_t pb = mat_patch_bytes(N, g);
+    if (pb > TC_MAT_MAX_BYTES || (C * kh * kw) % 4 != 0) return 0;
+    // patches (or dPt) + what the pointwise GEMM over K = C*kh*kw channels wants (split-K partials, repacked dY)
+    return pb + tc_conv_ws_bytes(N, C * kh * kw, g.OH, g.OW, F, 1, 1, 1, 0) + 1024;
+}
+
+static int mat_im2col(const float *x, float *pt, int N, const ConvGeom &g, cudaStream_t st) {
+    const int P = g.OH * g.OW, Pp = (int)repack_pitch(P);
+    const int rows = N * g.C * g.kh * g.kw;  // < 2^30 (mat_ok)
+    const int want = (rows + 7) / 8, cap = sm_count() * 16;
+    const int grid = want < cap ? want : cap;
+    if (g.s == 1) im2col_t_kernel<1><<<grid, 256, 0, st>>>(x, pt, g, P, Pp, rows);
+    else if (g.s == 2) im2col_t_kernel<2><<<grid, 256, 0, st>>>(x, pt, g, P, Pp, rows);
+    else im2col_t_kernel<0><<<grid, 256, 0, st>>>(x, pt, g, P, Pp, rows);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
+static int cvm_fwd(const float *x, const float *w, const float *bias, float *y, int N, const ConvGeom &g, void *ws,
+                   size_t ws_bytes, cudaStream_t st) {
+    if (!mat_ok(w, N, g)) return DK_ERR_UNSUPPORTED;
+    float *pt = ws_carve(ws, ws_bytes, mat_patch_bytes(N, g));
+    if (pt == nullptr) return DK_ERR_UNSUPPORTED;
+    int rc = mat_im2col(x, pt, N, g, st);
+    if (rc) return rc;
+    return pw_fwd(pt, w, bias, y, N, g.C * g.kh * g.kw, g.OH, g.OW, g.F, 1, ws, ws_bytes, st, repack_pitch((int64_t)g.OH * g.OW));
+}
+
+static int cvm_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, const ConvGeom &g, void *ws,
+                     size_t ws_bytes, cudaStream_t st) {
+    if (!mat_ok(w, N, g)) return DK_ERR_UNSUPPORTED;
+    {   // dY must reach the GEMM through TMA (directly or repacked): the gather loaders assume unpadded plane pitches
+        const int64_t P = (int64_t)g.OH * g.OW;
+        if (!tma_ok(dy, P) && !repack_wanted(dy, P, 1, true)) return DK_ERR_UNSUPPORTED;
+    }
+    float *pt = ws_carve(ws, ws_bytes, mat_patch_bytes(N, g));
+    if (pt == nullptr) return DK_ERR_UNSUPPORTED;
+    const int Kf = g.C * g.kh * g.kw;
+    // (the rest of the workspace must hold the split-K partials; pw_wgrad reports DK_ERR_WORKSPACE otherwise)
+    if (ws_bytes < tc_conv_ws_bytes(N, Kf, g.OH, g.OW, g.F, 1, 1, 1, 0)) return DK_ERR_UNSUPPORTED;
+    int rc = mat_im2col(x, pt, N, g, st);
+    if (rc) return rc;
+    return pw_wgrad(dy, pt, w, dw, l2, N, Kf, g.OH, g.OW, g.F, 1, ws, ws_bytes, st, repack_pitch((int64_t)g.OH * g.OW));
+}
+
+static int cvm_dgrad(const float *dy, const float *w, float *dx, int N, const ConvGeom &g, void *ws, size_t ws_bytes,
+                     cudaStream_t st) {
+    if (!mat_ok(w, N, g)) return DK_ERR_UNSUPPORTED;
+    float *dpt = ws_carve(ws, ws_bytes, mat_patch_bytes(N, g));
+    if (dpt == nullptr) return DK_ERR_UNSUPPORTED;
+    const int Kf = g.C * g.kh * g.kw, P = g.OH * g.OW;
+    int rc = pw_dgrad(dy, w, dpt, N, Kf, g.OH, g.OW, g.F, 1, ws, ws_bytes, st);  // dPt[n][k][p], pitch P
+    if (rc) return rc;
+    const long long planes = (long long)N * g.C;
+    if (g.kh == 4 && g.kw == 4 && g.s == 2) col2im_launch<4, 4, 2>(dpt, dx, g, P, planes, st);
+    else if (g.kh == 3 && g.kw == 3 && g.s == 1) col2im_launch<3, 3, 1>(dpt, dx, g, P, planes, st);
+    else if (g.kh == 3 && g.kw == 3 && g.s == 2) col2im_launch<3, 3, 2>(dpt, dx, g, P, planes, st);
+    else if (g.kh == 5 && g.kw == 5 && g.s == 2) col2im_launch<5, 5, 2>(dpt, dx, g, P, planes, st);
+    else col2im_launch<0, 0, 0>(dpt, dx, g, P, planes, st);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
 int tc_conv_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int F, int kh,
                 int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (!g_tc_ready || (g_tc_disable_mask & 1)) return DK_ERR_UNSUPPORTED;
     if (kh == 1 && kw == 1 && p == 0) return pw_fwd(x, w, bias, y, N, C, H, W, F, s, ws, ws_bytes, st);
     if (g_tc_disable_mask & 8) return DK_ERR_UNSUPPORTED;
+    {
+        const int rc = cvm_fwd(x, w, bias, y, N, mk_geom(C, H, W, F, kh, kw, s, p), ws, ws_bytes, st);
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     return cv_fwd(x, w, bias, y, N, mk_geom(C, H, W, F, kh, kw, s, p), st);
 }
 
@@ -1112,6 +1282,10 @@ int tc_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int 
         return pw_dgrad(dy, w, dx, N, C, OH, OW, F, s, ws, ws_bytes, st);
     }
     if (g_tc_disable_mask & 8) return DK_ERR_UNSUPPORTED;
+    {
+        const int rc = cvm_dgrad(dy, w, dx, N, mk_geom(C, H, W, F, kh, kw, s, p), ws, ws_bytes, st);
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     return cv_dgrad(dy, w, dx, N, mk_geom(C, H, W, F, kh, kw, s, p), st);
 }
 
@@ -1120,18 +1294,37 @@ int tc_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, fl
     if (!g_tc_ready || (g_tc_disable_mask & 4)) return DK_ERR_UNSUPPORTED;
     if (kh == 1 && kw == 1 && p == 0) return pw_wgrad(dy, x, w, dw, l2, N, C, H, W, F, s, ws, ws_bytes, st);
     if (g_tc_disable_mask & 8) return DK_ERR_UNSUPPORTED;
+    {
+        const int rc = cvm_wgrad(dy, x, w, dw, l2, N, mk_geom(C, H, W, F, kh, kw, s, p), ws, ws_bytes, st);
+        if (rc != DK_ERR_UNSUPPORTED) return rc;
+    }
     return cv_wgrad(dy, x, w, dw, l2, N, mk_geom(C, H, W, F, kh, kw, s, p), ws, ws_bytes, st);
 }
 
 // ---- DenseLayer (dense_layer.py:46-67): three small GEMMs, all operands through TMA ----------------------------------
+// out_dim % 4 != 0 (MNIST: 10 classes): W[in][out] and dY[B][out] have row pitches TMA cannot take; they are copied into
+// the workspace with the pitch rounded up to 4 floats (zero padded: padded k add nothing, padded n are masked by the
+// epilogue) -- two tiny copies instead of leaving the tensor cores.
 static bool dense_ok(const float *a, const float *b, const float *c, int B, int in_dim, int out_dim) {
-    return g_tc_ready && !(g_tc_disable_mask & 16) && aligned16(a) && aligned16(b) && aligned16(c) && in_dim % 4 == 0 &&
-           out_dim % 4 == 0 && B > 0;
+    return g_tc_ready && !(g_tc_disable_mask & 16) && aligned16(a) && aligned16(b) && aligned16(c) && in_dim % 4 == 0 && B > 0 &&
+           in_dim < (1 << 24) && out_dim < (1 << 24);
+}
+size_t tc_dense_ws_bytes(int B, int in_dim, int out_dim) {
+    if (out_dim % 4 == 0) return 0;
+    return repack_bytes(in_dim, out_dim) + repack_bytes(B, out_dim) + 1024;
 }
 
-int tc_dense_fwd(const float *x, const float *w, const float *bias, float *y, int B, int in_dim, int out_dim, void *,
-                 size_t, cudaStream_t st) {
-    if (!dense_ok(x, w, y, B, in_dim, out_dim)) return DK_ERR_UNSUPPORTED;
+int tc_dense_fwd(const float *x, const float *w, const float *bias, float *y, int B, int in_dim, int out_dim, void *ws,
+                 size_t ws_bytes, cudaStream_t st) {
+    if (!dense_ok(x, w, x, B, in_dim, out_dim)) return DK_ERR_UNSUPPORTED;
+    int64_t wp = out_dim;  // row pitch of the W operand
+    if (out_dim % 4 != 0) {
+        float *wpad = ws_carve(ws, ws_bytes, repack_bytes(in_dim, out_dim));
+        if (wpad == nullptr) return DK_ERR_UNSUPPORTED;
+        int rc = repack_launch(w, wpad, in_dim, 1, out_dim, out_dim, 1, out_dim, st);
+        if (rc) return rc;
+        w = wpad; wp = repack_pitch(out_dim);
+    }
     TcParams q = {};
     q.mode = 0; q.a_mn = 0; q.b_mn = 1; q.b_batched = 0;
     q.M = B; q.N = out_dim; q.K = in_dim; q.batches = 1;
@@ -1141,25 +1334,39 @@ int tc_dense_fwd(const float *x, const float *w, const float *bias, float *y, in
     CUtensorMap ta, tb;
     int rc = make_map(&ta, x, in_dim, B, 1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);          // A(m=b, k): k contiguous
     if (rc) return rc;
-    rc = make_map(&tb, w, out_dim, in_dim, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);    // B(k, n) = W[k][n]: n contiguous
+    rc = make_map(&tb, w, wp, in_dim, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);         // B(k, n) = W[k][n]: n contiguous
     if (rc) return rc;
     return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
 }
 
 int tc_dense_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float l2, int B, int in_dim,
-                 int out_dim, void *, size_t, cudaStream_t st) {
-    if (!dense_ok(dy, x, w, B, in_dim, out_dim) || !aligned16(dx) || !aligned16(dw)) return DK_ERR_UNSUPPORTED;
+                 int out_dim, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!dense_ok(x, w, dx, B, in_dim, out_dim) || !aligned16(dw)) return DK_ERR_UNSUPPORTED;
+    const float *w_l2 = w;  // the weight-decay term reads the real (unpadded) weights
+    int64_t op = out_dim;   // row pitch of the W and dY operands
+    if (out_dim % 4 != 0) {
+        float *wpad = ws_carve(ws, ws_bytes, repack_bytes(in_dim, out_dim));
+        float *gpad = ws_carve(ws, ws_bytes, repack_bytes(B, out_dim));
+        if (wpad == nullptr || gpad == nullptr) return DK_ERR_UNSUPPORTED;
+        int rc = repack_launch(w, wpad, in_dim, 1, out_dim, out_dim, 1, out_dim, st);
+        if (rc) return rc;
+        rc = repack_launch(dy, gpad, B, 1, out_dim, out_dim, 1, out_dim, st);
+        if (rc) return rc;
+        w = wpad; dy = gpad; op = repack_pitch(out_dim);
+    } else if (!aligned16(dy)) {
+        return DK_ERR_UNSUPPORTED;
+    }
     {   // dx[B, in] = dy[B, out] @ W^T : A(m=b, k=o) = dy, B(n=i, k=o) = W[i][o] (both K-major)
         TcParams q = {};
         q.mode = 0; q.a_mn = 0; q.b_mn = 0; q.b_batched = 0;
-        q.M = B; q.N = in_dim; q.K = out_dim; q.batches = 1;
+        q.M = B; q.N = in_dim; q.K = (int)op; q.batches = 1;
         fill_common(q);
         q.num_tiles = q.m_blocks * q.n_blocks;
         q.epi = 1; q.out = dx;
         CUtensorMap ta, tb;
-        int rc = make_map(&ta, dy, out_dim, B, 1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        int rc = make_map(&ta, dy, op, B, 1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
-        rc = make_map(&tb, w, out_dim, in_dim, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+        rc = make_map(&tb, w, op, in_dim, 1, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
         rc = tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
         if (rc) return rc;
@@ -1171,16 +1378,15 @@ int tc_dense_bwd(const float *dy, const float *x, const float *w, float *dx, flo
         fill_common(q);
         q.num_tiles = q.m_blocks * q.n_blocks;
         q.epi = 1; q.out = dw;
-        if (l2 != 0.0f) { q.epi_w = w; q.epi_l2 = l2; }
+        if (l2 != 0.0f) { q.epi_w = w_l2; q.epi_l2 = l2; }
         CUtensorMap ta, tb;
         int rc = make_map(&ta, x, in_dim, B, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
         if (rc) return rc;
-        rc = make_map(&tb, dy, out_dim, B, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+        rc = make_map(&tb, dy, op, B, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
         if (rc) return rc;
         return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
     }
 }
-size_t tc_dense_ws_bytes(int, int, int) { return 0; }
 
 }  // namespace dk
 
@@ -1211,6 +1417,7 @@ int dk_tc_debug_set(int key, int value) {
         case 19: dk::g_ct_wgrad2 = value; break;  // 0: conv_tma wgrad through column-shifted global copies only
         case 18: dk::g_ct_kc16 = value; break;  // conv_tma forward / dgrad: 0 = 32-channel stages only
         case 17: dk::g_conv_tma_enabled = value; break;  // 0: stride-1 k x k convolutions skip conv_tma.cu (gather variants instead)
+        case 20: dk::g_conv_mat_enabled = value; break;  // 0: no materialised-patch path (general convolutions fall to the gather variants)
         case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
         default: dk::set_error("dk_tc_debug_set: unknown key %d", key); return DK_ERR_INVALID;
     }

@@ -1,9 +1,12 @@
 """ResidualBlock (reference: layers/residual_block.py:12-151)."""
+import numpy as np
+
 from .layer import Layer, api, runtime, asarray
 from .activations import ReLu
 from .depthwise_convolution import DepthwiseConvLayer
 from ..array import LazyBNOutput
 from .batch_norm import BatchNormLayer
+from .pointwise_convolution import PointwiseConvLayer
 
 
 class ResidualBlock(Layer):

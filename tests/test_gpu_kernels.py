@@ -171,6 +171,35 @@ def test_conv_tma_stride1_vs_oracle(O, case):
     assert tc1 - tc0 == 3 and s1 == s0, "expected forward, dgrad and wgrad on the tensor-core path"
 
 
+CONV_MAT_CASES = [
+    # N, C, H, W, F, k, s, p -- shapes outside conv_tma.cu / conv_rows.cu: materialised transposed patches + the all-TMA
+    # pointwise GEMMs (gemm_tcgen05.cu cvm_*), dX by gather-form col2im
+    (3, 32, 28, 28, 64, 4, 2, 1),    # MNIST conv3: 4x4 stride 2, 14 x 14 output (P = 196)
+    (3, 64, 14, 14, 128, 4, 2, 1),   # MNIST conv5: 7 x 7 output (P = 49: padded patch pitch, dY repacked for wgrad)
+    (3, 64, 14, 14, 64, 3, 1, 1),    # MNIST conv4: stride 1 but 56-byte rows (conv_tma needs 16-byte pitches)
+    (2, 32, 14, 14, 64, 4, 2, 1),
+    (2, 16, 15, 17, 24, 3, 2, 1),    # x.5 patch counts (floor), odd rectangular planes, P = 8 * 9
+    (2, 20, 11, 11, 12, 5, 3, 2),    # stride 3, 5 x 5: taps that never reach some dX elements
+    (1, 16, 9, 9, 300, 3, 1, 0),     # F > 256: two n-blocks
+    (2, 64, 30, 30, 64, 3, 2, 0),    # no padding, stride 2
+]
+
+
+@pytest.mark.parametrize("case", CONV_MAT_CASES)
+def test_conv_materialised_patches_vs_oracle(O, case):
+    """every pass stays on the tensor-core path, and agrees with the gather variants it replaces"""
+    from dorknet_b200 import _lib, api
+    tc0, s0 = _lib.gemm_call_counts()
+    _conv_case(O, case)
+    tc1, s1 = _lib.gemm_call_counts()
+    assert tc1 - tc0 == 3 and s1 == s0, "expected forward, dgrad and wgrad on the tensor-core path"
+    api.dk_tc_debug_set(20, 0)
+    try:
+        _conv_case(O, case)
+    finally:
+        api.dk_tc_debug_set(20, 1)
+
+
 @pytest.mark.parametrize("case", [(4, 3, 225, 225, 64, 5, 2, 1), (2, 1, 28, 28, 32, 3, 1, 1)])
 def test_conv_rows_generic_staging_vs_oracle(O, case):
     """the same small-K kernels with span staging switched off (4-byte cp.async staging of any geometry)"""
@@ -237,9 +266,10 @@ def test_full_size_properties_resnet_shapes():
     assert abs(lhs - rhs) <= 2e-3 * abs(rhs)
 
 
-@pytest.mark.parametrize("case", [(64, 512, 120), (8, 128, 12), (130, 64, 300), (16, 1024, 120)])
+@pytest.mark.parametrize("case", [(64, 512, 120), (8, 128, 12), (130, 64, 300), (16, 1024, 120), (64, 128, 10), (5, 64, 33)])
 def test_dense_tcgen05_vs_oracle(O, case):
-    """DenseLayer on the tensor-core path (in/out multiples of 4): fwd, dX, dW (+l2), db."""
+    """DenseLayer on the tensor-core path: fwd, dX, dW (+l2), db.  The last two cases have out_dim % 4 != 0 (MNIST's 10
+    classes): W and dY are re-pitched into the workspace."""
     from dorknet_b200 import _lib
     from dorknet_b200.layers.dense_layer import DenseLayer
     from dorknet_b200.regularisers.l2 import l2
