@@ -381,6 +381,19 @@ def _bn_bwd_join_bytes(a):
     return 4 * 5 * N * C * HW  # the BatchNorm backward part only (the ReLU backward it absorbed is not counted)
 
 
+def _dw_fwd_bn_bytes(a):
+    N, C, H, W, kh, kw, s, p = a[4:12]
+    OH, OW = (H + 2 * p - kh) // s + 1, (W + 2 * p - kw) // s + 1
+    # the unfused work it stands for: the depthwise forward + the BatchNorm forward on its output (3n), SURVEY 8(d)
+    return 4 * N * C * (H * W + OH * OW) + 4 * 3 * N * C * OH * OW
+
+
+def _pw_dgrad_affine_bytes(a):
+    N, C, OH, OW, F = a[6:11]
+    # the unfused work it stands for: the pointwise dgrad (dY read, dX_hat written) + the BatchNorm backward (5n), SURVEY 8(d)
+    return 4 * N * OH * OW * (F + C) + 4 * 5 * N * C * OH * OW
+
+
 # entry points that launch the same kernels are one family for the roofline
 FAMILY_OF = {"dk_bn_bwd_join": "dk_bn_bwd"}
 
@@ -392,6 +405,10 @@ BYTES_FN = {
     "dk_dwconv_fwd": _dw_fwd_bytes, "dk_dwconv_bwd": _dw_bwd_bytes,
     "dk_pwconv_fwd": _pw_fwd_bytes, "dk_pwconv_dgrad": _pw_dgrad_bytes, "dk_pwconv_wgrad": _pw_wgrad_bytes,
     "dk_conv2d_fwd": _conv_fwd_bytes, "dk_conv2d_wgrad": _conv_wgrad_bytes, "dk_conv2d_dgrad": _conv_dgrad_bytes,
+    "dk_pwconv_dgrad_affine": _pw_dgrad_affine_bytes,
+    "dk_bn_fold_fwd": lambda a: 4 * 2 * a[8] * a[9], "dk_bn_fold_bwd": lambda a: 4 * 3 * a[15] * a[16],
+    "dk_dwconv_fwd_bn": _dw_fwd_bn_bytes,
+    "dk_bias_grad": lambda a: 4 * a[2] * a[3] * a[4],
     "dk_relu_fwd": lambda a: 4 * 2 * a[3], "dk_relu_bwd": lambda a: 4 * 3 * a[3],
     "dk_add_relu_fwd": lambda a: 4 * 3 * a[3], "dk_add": lambda a: 4 * 3 * a[3],
 }

@@ -202,6 +202,45 @@ class LazyReluOutput(LazyDeviceArray):
         self._thunk = thunk
 
 
+class LazyDWOutput(LazyDeviceArray):
+    """Output of a training-mode DepthwiseConvLayer.forward that has not been launched yet.  Any reader gets the plain
+    depthwise forward on first use; a BatchNormLayer that is being folded into the pointwise GEMM behind it instead asks the
+    layer for the variant that also accumulates the BatchNorm statistics while the outputs are in registers
+    (dk_dwconv_fwd_bn), so the statistics cost no pass over the activation."""
+
+    __slots__ = ("layer",)
+
+    def __init__(self, buf, thunk, layer):
+        super().__init__(buf, thunk)
+        self.layer = layer
+
+    def launched_by_consumer(self):
+        self._thunk = None
+
+
+class ZeroSumGrad(DeviceArray):
+    """The input gradient a BatchNormLayer.backward returns: per channel it sums to zero over (N, H, W) -- exactly, in real
+    arithmetic, because sum(x_hat) = 0 (batch_norm.py:125-156).  A layer that needs the channel sums of its upstream
+    gradient (a bias gradient, the folded BatchNorm of bn_fold.cu) may skip that reduction when it receives one."""
+
+    __slots__ = ()
+
+
+class FoldedBNGrad(LazyDeviceArray):
+    """What PointwiseConvLayer.backward returns when the BatchNorm in front of it was folded into its GEMMs (bn_fold.cu):
+    the BatchNorm's own backward has already happened inside the dgrad epilogue -- `dx` is the gradient with respect to the
+    BatchNorm's INPUT and bn.grads are written.  The BatchNorm's backward() recognises the object and hands `dx` on.  Anyone
+    else reading it (`.ptr`, `.get()`) gets what the reference's pointwise layer returns, the gradient with respect to the
+    BatchNorm's output, computed on first use by the plain dgrad GEMM."""
+
+    __slots__ = ("bn", "dx")
+
+    def __init__(self, buf, thunk, bn, dx):
+        super().__init__(buf, thunk)
+        self.bn = bn
+        self.dx = dx
+
+
 class LazyStridedGrad(LazyDeviceArray):
     """Input gradient of a stride-s PointwiseConvLayer: zero except at [:, :, ::s, ::s] (pointwise_convolution.py:68-72).
     Reading it (`.ptr`, `.get()`, `+`) produces the reference's zero-stuffed full-size tensor.  A consumer that can use

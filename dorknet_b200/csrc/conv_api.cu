@@ -126,6 +126,18 @@ int dk_pwconv_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     return simt_conv_dgrad(dy, w, dx, N, C, H, W, F, 1, 1, stride, 0, OH, OW, as_stream(stream));
 }
 
+int dk_pwconv_dgrad_affine(const float *dy, const float *w, const float *x, const float *cb, const float *cd, float *dx,
+                           int N, int C, int OH, int OW, int F, void *ws, size_t ws_bytes, dk_stream_t stream) {
+    int rc = conv_check("dk_pwconv_dgrad_affine", N, C, OH, OW, F, 1, 1, 1, 0);
+    if (rc) return rc;
+    DK_REQUIRE(dy && w && x && cb && cd && dx, "dk_pwconv_dgrad_affine: NULL pointer");
+    DK_TRY_TC(tc_pw_dgrad_affine(dy, w, x, cb, cd, dx, N, C, OH, OW, F, ws, ws_bytes, as_stream(stream)));
+    /* fallback: the plain dgrad, then the affine term as its own pass */
+    rc = dk_pwconv_dgrad(dy, w, dx, N, C, OH, OW, F, 1, ws, ws_bytes, stream);
+    if (rc) return rc;
+    return affine_add_launch(dx, x, cb, cd, N, C, OH * OW, as_stream(stream));
+}
+
 int dk_pwconv_wgrad(const float *dy, const float *x, const float *w, float *dw, float *dbias, float l2, int N, int C,
                     int H, int W, int F, int stride, void *ws, size_t ws_bytes, dk_stream_t stream) {
     return dk_conv2d_wgrad(dy, x, w, dw, dbias, l2, N, C, H, W, F, 1, 1, stride, 0, ws, ws_bytes, stream);

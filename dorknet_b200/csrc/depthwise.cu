@@ -14,6 +14,7 @@
 //
 // Optional input transform relu?(x*scale[c]+shift[c]): a deferred BatchNorm(+ReLU) of the producer
 // applied while staging, so the normalised activation is never written to HBM.
+#include "bn.cuh"
 #include "common.cuh"
 
 namespace dk {
@@ -452,6 +453,9 @@ static int dw_geom(DwGeom &g, int N, int C, int H, int W, int kh, int kw, int s,
 
 // register-window fast path for 3x3 / stride 1 / pad 1 (depthwise_rows.cu)
 size_t dw_rows_ws_bytes(int N, int C, int H, int W, int kh, int kw, int s, int p);
+size_t dw_rows_fwd_bn_ws_bytes(int N, int C, int H, int W, int kh, int kw, int s, int p);
+int dw_rows_fwd_bn(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int kh, int kw,
+                   int s, int p, const BnFinalize &fin, float *trunc_resid, void *ws, size_t ws_bytes, cudaStream_t st);
 int dw_rows_fwd(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int kh, int kw,
                 int s, int p, cudaStream_t st);
 int dw_rows_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias, const float *dx_add,
@@ -559,6 +563,38 @@ int dk_dwconv_fwd(const float *x, const float *w, const float *bias, float *y, c
     if (kh == 3 && kw == 3 && stride == 1) return dw_launch_fwd<3, 3, 1>(x, w, bias, y, in_scale, in_shift, in_relu, g, st);
     if (kh == 3 && kw == 3 && stride == 2) return dw_launch_fwd<3, 3, 2>(x, w, bias, y, in_scale, in_shift, in_relu, g, st);
     return dw_launch_fwd<0, 0, 0>(x, w, bias, y, in_scale, in_shift, in_relu, g, st);
+}
+
+size_t dk_dwconv_fwd_bn_ws_bytes(int N, int C, int H, int W, int kh, int kw, int stride, int pad) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || !g_dw_rows_enabled) return 0;
+    return dw_rows_fwd_bn_ws_bytes(N, C, H, W, kh, kw, stride, pad);
+}
+
+int dk_dwconv_fwd_bn(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int kh, int kw,
+                     int stride, int pad, const float *gamma, const float *beta, float *running_mean, float *running_std,
+                     int first_batch, float momentum, float eps, float *save_mean, float *save_invstd, float *save_scale,
+                     float *save_shift, float *trunc_resid, void *ws, size_t ws_bytes, dk_stream_t stream) {
+    DwGeom g;
+    int rc = dw_geom(g, N, C, H, W, kh, kw, stride, pad, false, "dk_dwconv_fwd_bn");
+    if (rc) return rc;
+    DK_REQUIRE(x && w && y && gamma && beta && save_mean && save_invstd && save_scale && save_shift, "dk_dwconv_fwd_bn: NULL pointer");
+    DK_REQUIRE((running_mean == nullptr) == (running_std == nullptr), "dk_dwconv_fwd_bn: running stats must come in pairs");
+    const size_t need = dk_dwconv_fwd_bn_ws_bytes(N, C, H, W, kh, kw, stride, pad);
+    DK_REQUIRE(need > 0, "dk_dwconv_fwd_bn: shape not covered (3x3, stride 1, pad 1, W %% 4 == 0, H*W >= 512): "
+                         "call dk_dwconv_fwd + dk_bn_fwd_train instead (dk_dwconv_fwd_bn_ws_bytes returns 0 for it)");
+    DK_REQUIRE(ws != nullptr && ws_bytes >= need, "dk_dwconv_fwd_bn: workspace too small (%zu < %zu bytes)", ws_bytes, need);
+    BnFinalize fin = {};
+    fin.mode = 1;
+    fin.gamma = gamma; fin.beta = beta;
+    fin.running_mean = running_mean; fin.running_std = running_std;
+    fin.first_batch = first_batch; fin.momentum = momentum; fin.eps = eps;
+    fin.save_mean = save_mean; fin.save_invstd = save_invstd; fin.save_scale = save_scale; fin.save_shift = save_shift;
+    rc = dw_rows_fwd_bn(x, w, bias, y, N, C, H, W, kh, kw, stride, pad, fin, trunc_resid, ws, ws_bytes, as_stream(stream));
+    if (rc == DK_ERR_UNSUPPORTED) {
+        set_error("dk_dwconv_fwd_bn: x / y must be 16-byte aligned");
+        return DK_ERR_INVALID;
+    }
+    return rc;
 }
 
 int dk_dwconv_bwd(const float *dy, const float *x, const float *w, float *dx, float *dw, float *dbias,

@@ -12,6 +12,7 @@
 // Backward is one pass over dY and X (im2col.pyx:143-178 does the same fusion on the CPU): it writes dX and
 // per-(plane, band) partial sums of dW / db -- reduced deterministically by dw_reduce_kernel (depthwise.cu), as the
 // reference sums its per-image dW (depthwise_convolution.py:193).
+#include "bn.cuh"
 #include "common.cuh"
 
 namespace dk {
@@ -93,10 +94,15 @@ __device__ __forceinline__ void load_row(const float *__restrict__ src, bool ok,
 }
 
 // ---------------------------------------------------------------------------------------------- forward
-template <int VEC>
+// STATS: the kernel also leaves, per (plane, band) segment and warp piece, the sums BatchNorm needs of the values it just
+// produced -- sum y, sum y^2 and sum (y - tf32_truncate(y)) -- so that a BatchNorm that follows (and is folded into the
+// pointwise GEMM after it, bn_fold.cu) costs no pass over the activation at all (dw_stats_finalize_kernel turns them into
+// mean / invstd / scale / shift).  Same fixed-order segmented reduction as the backward kernel's dW sums.
+template <int VEC, bool STATS>
 __global__ void __launch_bounds__(DWR_THREADS)
 dw3x3_rows_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-                      float *__restrict__ y, long long planes, int C, int H, int W, int bands) {
+                      float *__restrict__ y, long long planes, int C, int H, int W, int bands,
+                      float *__restrict__ stat_partial) {
     const int SP = W / VEC;
     const long long gid = (long long)blockIdx.x * DWR_THREADS + threadIdx.x;
     const long long total = planes * bands * SP;
@@ -117,6 +123,7 @@ dw3x3_rows_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, 
     const float *xp = x + plane * (long long)H * W;
     float *yp = y + plane * (long long)H * W;
 
+    float st_sum = 0.0f, st_sq = 0.0f, st_res = 0.0f;
     float win[DWR_RB + 2][VEC + 2];
     load_row<VEC>(xp, ok, h0 - 1, H, W, strip, SP, lane, win[0]);
     load_row<VEC>(xp, ok, h0, H, W, strip, SP, lane, win[1]);
@@ -142,13 +149,93 @@ dw3x3_rows_fwd_kernel(const float *__restrict__ x, const float *__restrict__ w, 
                     for (int j = 0; j < 3; ++j) a = fmaf(win[r + i][v + j], k[i * 3 + j], a);
                 o[v] = a;
             }
-            if (ok && hb + r < rows) st_vec<VEC>(yp + (long long)(h0 + hb + r) * W + strip * VEC, o);
+            if (ok && hb + r < rows) {
+                st_vec<VEC>(yp + (long long)(h0 + hb + r) * W + strip * VEC, o);
+                if (STATS) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        st_sum += o[v];
+                        st_sq = fmaf(o[v], o[v], st_sq);
+                        st_res += o[v] - __uint_as_float(__float_as_uint(o[v]) & 0xFFFFE000u);  // what kind::tf32 drops
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int v = 0; v < VEC + 2; ++v) {
             win[0][v] = win[DWR_RB][v];
             win[1][v] = win[DWR_RB + 1][v];
         }
+    }
+    if (STATS) {
+        float acc[3] = {st_sum, st_sq, st_res};
+        const long long key = ok ? t : -1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float v = ok ? acc[i] : 0.0f;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {  // segmented inclusive scan by (plane, band), towards higher lanes
+                const float up = __shfl_up_sync(0xffffffffu, v, d);
+                const long long kup = __shfl_up_sync(0xffffffffu, key, d);
+                if (lane >= d && kup == key) v += up;
+            }
+            acc[i] = v;
+        }
+        const long long knext = __shfl_down_sync(0xffffffffu, key, 1);
+        if (ok && (lane == 31 || knext != key)) {
+            const long long first_gid = t * SP;
+            const int piece = (int)((gid >> 5) - (first_gid >> 5));
+            const int pieces_max = (SP + 30) / 32 + 1;
+            float *dst = stat_partial + ((t * pieces_max) + piece) * 3;
+            dst[0] = acc[0];
+            dst[1] = acc[1];
+            dst[2] = acc[2];
+        }
+    }
+}
+
+// One CTA per channel: adds the (image, band, piece) partial sums of dw3x3_rows_fwd_kernel<.., true> in a fixed order, in
+// double (sum y^2 - (sum y)^2 / n cancels), and finalises the BatchNorm statistics exactly like the BatchNorm kernels do
+// (bn.cuh: batch_norm.py:66-89); trunc_resid[c] = mean of y - tf32_truncate(y) (bn_fold.cu uses it to keep the folded GEMM's
+// output mean exact).
+__global__ void __launch_bounds__(128)
+dw_stats_finalize_kernel(const float *__restrict__ partial, int N, int C, int bands, int pieces_max, int SP, long long count,
+                         BnFinalize fin, float *__restrict__ trunc_resid) {
+    __shared__ double red[3][128];
+    const int c = blockIdx.x;
+    const int per_plane = bands * pieces_max;
+    const int total = N * per_plane;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+        const int n = k / per_plane, q = k - n * per_plane;
+        const int band = q / pieces_max, piece = q - band * pieces_max;
+        const long long seg = ((long long)n * C + c) * bands + band;
+        const long long first = seg * SP, last = first + SP - 1;
+        const int npieces = (int)((last >> 5) - (first >> 5)) + 1;
+        if (piece < npieces) {
+            const float *src = partial + (seg * pieces_max + piece) * 3;
+            a0 += (double)src[0];
+            a1 += (double)src[1];
+            a2 += (double)src[2];
+        }
+    }
+    red[0][threadIdx.x] = a0;
+    red[1][threadIdx.x] = a1;
+    red[2][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a0 = a1 = a2 = 0.0;
+        for (int i = 0; i < 128; ++i) {
+            a0 += red[0][i];
+            a1 += red[1][i];
+            a2 += red[2][i];
+        }
+        const double mean = a0 / (double)count;
+        double var = a1 / (double)count - mean * mean;  // biased (batch_norm_stats_cy.pyx:44)
+        if (var < 0.0) var = 0.0;
+        float sc, sh;
+        bn_finalize_channel(fin, c, (float)mean, (float)var, true, &sc, &sh);
+        if (trunc_resid) trunc_resid[c] = (float)(a2 / (double)count);
     }
 }
 
@@ -363,9 +450,31 @@ int dw_rows_fwd(const float *x, const float *w, const float *bias, float *y, int
     DwRowsPlan pl;
     if (!dw_rows_plan(pl, x, y, x, y, N, C, H, W, kh, kw, s, p)) return DK_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)ceil_div(pl.total, DWR_THREADS);
-    if (pl.vec == 4) dw3x3_rows_fwd_kernel<4><<<grid, DWR_THREADS, 0, st>>>(x, w, bias, y, pl.planes, C, H, W, pl.bands);
-    else if (pl.vec == 2) dw3x3_rows_fwd_kernel<2><<<grid, DWR_THREADS, 0, st>>>(x, w, bias, y, pl.planes, C, H, W, pl.bands);
-    else dw3x3_rows_fwd_kernel<1><<<grid, DWR_THREADS, 0, st>>>(x, w, bias, y, pl.planes, C, H, W, pl.bands);
+    if (pl.vec == 4) dw3x3_rows_fwd_kernel<4, false><<<grid, DWR_THREADS, 0, st>>>(x, w, bias, y, pl.planes, C, H, W, pl.bands, nullptr);
+    else if (pl.vec == 2) dw3x3_rows_fwd_kernel<2, false><<<grid, DWR_THREADS, 0, st>>>(x, w, bias, y, pl.planes, C, H, W, pl.bands, nullptr);
+    else dw3x3_rows_fwd_kernel<1, false><<<grid, DWR_THREADS, 0, st>>>(x, w, bias, y, pl.planes, C, H, W, pl.bands, nullptr);
+    DK_LAUNCH_CHECK();
+    return DK_OK;
+}
+
+// forward + the BatchNorm statistics of its output (two launches; the second is C small CTAs)
+size_t dw_rows_fwd_bn_ws_bytes(int N, int C, int H, int W, int kh, int kw, int s, int p) {
+    // (planes of fewer than 512 pixels belong to the channel-group kernels of depthwise_group.cu)
+    if (kh != 3 || kw != 3 || s != 1 || p != 1 || W % 4 != 0 || H * W < 512) return 0;
+    const int sp = W / 4;
+    return (size_t)N * C * dw_rows_bands((long long)N * C, sp, H) * ((sp + 30) / 32 + 1) * 3 * sizeof(float);
+}
+int dw_rows_fwd_bn(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int kh, int kw,
+                   int s, int p, const BnFinalize &fin, float *trunc_resid, void *ws, size_t ws_bytes, cudaStream_t st) {
+    DwRowsPlan pl;
+    if (!dw_rows_plan(pl, x, y, x, y, N, C, H, W, kh, kw, s, p) || pl.vec != 4) return DK_ERR_UNSUPPORTED;
+    const size_t need = (size_t)pl.planes * pl.bands * pl.pieces_max * 3 * sizeof(float);
+    if (ws == nullptr || ws_bytes < need || (long long)N * pl.bands * pl.pieces_max >= (1ll << 31)) return DK_ERR_UNSUPPORTED;
+    float *partial = reinterpret_cast<float *>(ws);
+    const unsigned grid = (unsigned)ceil_div(pl.total, DWR_THREADS);
+    dw3x3_rows_fwd_kernel<4, true><<<grid, DWR_THREADS, 0, st>>>(x, w, bias, y, pl.planes, C, H, W, pl.bands, partial);
+    DK_LAUNCH_CHECK();
+    dw_stats_finalize_kernel<<<C, 128, 0, st>>>(partial, N, C, pl.bands, pl.pieces_max, pl.sp, (long long)N * H * W, fin, trunc_resid);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }

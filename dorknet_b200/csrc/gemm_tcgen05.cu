@@ -36,6 +36,8 @@ constexpr int TC_BK = 32;                  // floats of K per stage (= one 128-b
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_XR_MAX = 8;                 // slots of the epilogue-operand ring
+constexpr uint32_t TC_X_SLOT = 128 * 32 * 4;  // 16 KB: four [32 channels][32 pixels] boxes
 
 struct TcParams {
     int mode;       // 0: tile = (batch, m-block, n-block), K loop over k-blocks.  1: tile = (m-block, n-block, split), K loop over (batch, k-block) items
@@ -56,6 +58,11 @@ struct TcParams {
     int epi_ow, epi_s;  // epi 2: output-pixel row length and the stride of the zero-stuffed scatter
     const float *epi_w;  // epi 1: optional "+ epi_l2 * epi_w[m*N + n]" (weight decay folded into a dense wgrad)
     float epi_l2;
+    // epi 0: optional "+ epi_cb[n] * epi_x[(b*N + n)*ldo + m] + epi_cd[n]" -- the backward of a BatchNorm folded into this
+    // dgrad GEMM (bn_fold.cu): epi_x is the BatchNorm's input, laid out like the output
+    const float *epi_x, *epi_cb, *epi_cd;
+    int xring;       // > 0: epi_x tiles are staged by TMA into a ring of `xring` 16 KB slots (128 pixels x 32 channels) instead of
+                     // being loaded by the epilogue warps themselves
     uint32_t tmem_cols, acc_stride;
     uint32_t a_tx;   // bytes one stage's A tile receives from TMA (a K-major A with fewer than 128 rows loads only those)
     // MN-major shared-memory descriptor fields (bytes) -- runtime so a bring-up probe can sweep them
@@ -251,8 +258,8 @@ constexpr int TC_GATHER_THREADS = TC_THREADS + 128;
 
 template <class AG, class BG>
 __global__ void __launch_bounds__((AG::kGather || BG::kGather) ? TC_GATHER_THREADS : TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
-               const AG ag, const BG bg) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmX, const TcParams p, const AG ag, const BG bg) {
     constexpr bool kAnyGather = AG::kGather || BG::kGather;
     constexpr bool kAnyTma = !AG::kGather || !BG::kGather;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -261,12 +268,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t b_bytes = (uint32_t)p.bn * TC_BK * 4;
     const uint32_t kpi = (uint32_t)p.kpi;  // stage layout: kpi A sub-tiles, then kpi B sub-tiles
     const uint32_t stage_bytes = kpi * (TC_A_BYTES + b_bytes);
-    const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+    const uint32_t xs_base = smem_base + (uint32_t)p.stages * stage_bytes;  // epilogue-operand ring (p.xring slots)
+    const uint32_t bar_base = xs_base + (uint32_t)p.xring * TC_X_SLOT;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * TC_MAX_STAGES + 4);
+    auto xfull_bar = [&](int i) { return bar_base + 8u * (2 * TC_MAX_STAGES + 6 + i); };
+    auto xempty_bar = [&](int i) { return bar_base + 8u * (2 * TC_MAX_STAGES + 6 + TC_XR_MAX + i); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -281,6 +291,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 4);
         }
+        for (int i = 0; i < p.xring; ++i) {
+            mbar_init(xfull_bar(i), 1);
+            mbar_init(xempty_bar(i), 4);
+        }
+        if (p.xring) tma_prefetch_desc(&tmX);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -306,8 +321,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (kAnyTma && lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
+            int s = 0, xs = 0;
+            uint32_t ph = 0, xph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int b = 0, m0, n0, item0 = 0;
                 if (p.mode == 0) {
@@ -325,7 +340,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     item0 = split * p.items_per_split;
                 }
                 const int iters = tile_iters(tile);
-                for (int it = 0; it < iters; ++it) {
+                for (int it = 0; it <= iters; ++it) {
+                    if (it == iters) {
+                        // the tile's operands are on their way: now the second operand of its epilogue, one slot per
+                        // 32-channel chunk (pixels / channels past the tensor are zero-filled)
+                        for (int c = 0; c < p.bn && p.xring > 0; c += 32) {
+                            mbar_wait(xempty_bar(xs), xph ^ 1u);
+                            const uint32_t xb = xfull_bar(xs), dst = xs_base + (uint32_t)xs * TC_X_SLOT;
+                            mbar_expect_tx(xb, TC_X_SLOT);
+#pragma unroll
+                            for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(dst + j * 4096u, &tmX, xb, m0 + 32 * j, n0 + c, b);
+                            if (++xs == p.xring) { xs = 0; xph ^= 1u; }
+                        }
+                        break;
+                    }
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + kpi * TC_A_BYTES;
                     const uint32_t fb = full_bar(s);
@@ -526,7 +554,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ================================ epilogue (warps 2..5) ========================
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
-        int local = 0;
+        int local = 0, xs = 0;
+        uint32_t xph = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
             const int acc = local & 1;
             const uint32_t aph = (uint32_t)(local >> 1) & 1u;
@@ -552,8 +581,53 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < p.bn; c += 32) {
                 uint32_t v[32];
                 tmem_ld32(t_row + (uint32_t)c, v);
-                tmem_ld_wait();
                 const int nb = n0 + c;
+                if (p.xring > 0) {
+                    // folded BatchNorm backward, second operand staged by TMA: slot = [4 pixel groups][32 channels][32 pixels]
+                    mbar_wait(xfull_bar(xs), xph);
+                    const uint32_t xa = xs_base + (uint32_t)xs * TC_X_SLOT + (uint32_t)q * 4096u + (uint32_t)lane * 4u;
+                    tmem_ld_wait();
+                    float *o = p.out + ((long long)b * p.N + nb) * p.ldo + m;
+                    if (nb + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float r = fmaf(__ldg(p.epi_cb + nb + j), ld_shared_f32(xa + j * 128u), __uint_as_float(v[j])) +
+                                            __ldg(p.epi_cd + nb + j);
+                            if (m_ok) o[(long long)j * p.ldo] = r;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (nb + j < p.N) {
+                                const float r = fmaf(__ldg(p.epi_cb + nb + j), ld_shared_f32(xa + j * 128u), __uint_as_float(v[j])) +
+                                                __ldg(p.epi_cd + nb + j);
+                                if (m_ok) o[(long long)j * p.ldo] = r;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(xempty_bar(xs));
+                    if (++xs == p.xring) { xs = 0; xph ^= 1u; }
+                    continue;
+                }
+                if (p.epi == 0 && p.epi_x != nullptr) {
+                    // folded BatchNorm backward: the second operand of the epilogue is read like the output is written
+                    // (lane <-> pixel, 128 B per channel and warp); the loads are in flight while the accumulator arrives
+                    const long long off = ((long long)b * p.N + nb) * p.ldo + m;
+                    float xv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xv[j] = (m_ok && nb + j < p.N) ? __ldg(p.epi_x + off + (long long)j * p.ldo) : 0.0f;
+                    tmem_ld_wait();
+                    if (m_ok) {
+                        float *o = p.out + off;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.N)
+                                o[(long long)j * p.ldo] = fmaf(__ldg(p.epi_cb + nb + j), xv[j], __uint_as_float(v[j])) + __ldg(p.epi_cd + nb + j);
+                    }
+                    continue;
+                }
+                tmem_ld_wait();
                 if (p.epi == 0) {
                     // lane <-> pixel: for every output channel the warp stores 32 consecutive floats (one 128 B line)
                     float *o = p.out + ((long long)b * p.N + nb) * p.ldo + m;
@@ -561,6 +635,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (nb + 32 <= p.N && p.bias == nullptr) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) o[(long long)j * p.ldo] = __uint_as_float(v[j]);
+                        } else if (nb + 32 <= p.N) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) o[(long long)j * p.ldo] = __uint_as_float(v[j]) + __ldg(p.bias + nb + j);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
@@ -652,6 +729,7 @@ static int g_hybrid_wgrad = 0;               // 1: pointwise wgrad takes X throu
 static int g_wide_items = 0;                 // wgrad k-blocks per item: 0 = automatic (pw_wgrad), 1 / 2 / 4 = forced
 static int g_two_per_sm = 1;                 // see tc_launch
 static int g_ctas_per_sm = 1;                // persistent CTAs per SM the grids / split plans are sized for
+static int g_epi_ring = 1;                   // 0: the affine dgrad epilogue loads its second operand itself (no TMA ring)
 static int g_tc_disable_mask = 0;  // bit0 fwd, bit1 dgrad, bit2 wgrad (bring-up / tests)
 
 int init_gemm_tcgen05() {
@@ -748,27 +826,35 @@ static void fill_common(TcParams &p) {
 // lose (more split-K partials / loader warps competing), so they keep one CTA per SM
 template <class AG, class BG>
 static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, TcParams p, const AG &ag, const BG &bg,
-                     cudaStream_t st, bool two_per_sm = false) {
+                     cudaStream_t st, bool two_per_sm = false, const CUtensorMap *tx = nullptr) {
     static bool attr_set = false;
     if (!attr_set) {
         DK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<AG, BG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TC_SMEM_BUDGET + 2048));
+                                     TC_SMEM_BUDGET + 4096));
         attr_set = true;
     }
     const int stage_bytes = p.kpi * (TC_A_BYTES + p.bn * TC_BK * 4);
     int per_sm = g_ctas_per_sm;
+    if (tx == nullptr) p.xring = 0;
+    const int xbytes = p.xring * (int)TC_X_SLOT;
     if (two_per_sm && g_two_per_sm && per_sm == 1 && p.num_tiles >= 2 * sm_count() && p.tmem_cols <= 256) {
-        const int st2 = (98 * 1024) / stage_bytes;
+        // (with an epilogue-operand ring the two CTAs share the whole 227 KB: 110 KB each)
+        const int st2 = ((xbytes ? 110 : 98) * 1024 - xbytes) / stage_bytes;
         if (st2 >= 3) {
             per_sm = 2;
             if (p.stages > st2) p.stages = st2;
         }
     }
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + 8 * (2 * TC_MAX_STAGES + 8);
+    if (per_sm == 1 && xbytes) {
+        const int st1 = (g_smem_budget - xbytes) / stage_bytes;
+        if (st1 < 2) return DK_ERR_UNSUPPORTED;
+        if (p.stages > st1) p.stages = st1;
+    }
+    const size_t smem = (size_t)p.stages * stage_bytes + xbytes + 1024 /*align slack*/ + 8 * (2 * TC_MAX_STAGES + 8 + 2 * TC_XR_MAX);
     const int cap = sm_count() * per_sm;
     const int grid = p.num_tiles < cap ? p.num_tiles : cap;
     const int threads = (AG::kGather || BG::kGather) ? TC_GATHER_THREADS : TC_THREADS;
-    tc_gemm_kernel<AG, BG><<<grid, threads, smem, st>>>(ta, tb, p, ag, bg);
+    tc_gemm_kernel<AG, BG><<<grid, threads, smem, st>>>(ta, tb, tx ? *tx : ta, p, ag, bg);
     DK_LAUNCH_CHECK();
     return DK_OK;
 }
@@ -922,7 +1008,8 @@ static int pw_fwd(const float *x, const float *w, const float *bias, float *y, i
 }
 
 static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, int OH, int OW, int F, int s, void *ws,
-                    size_t ws_bytes, cudaStream_t st) {
+                    size_t ws_bytes, cudaStream_t st, const float *epi_x = nullptr, const float *epi_cb = nullptr,
+                    const float *epi_cd = nullptr) {
     const int64_t P = (int64_t)OH * OW;
     if (!tma_ok(w, C) || !dims_ok(P, P * s * s)) return DK_ERR_UNSUPPORTED;
     TcParams q = {};
@@ -932,12 +1019,28 @@ static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     q.num_tiles = N * q.m_blocks * q.n_blocks;
     q.out = dx; q.bias = nullptr; q.ldo = (int)P;
     q.epi = s == 1 ? 0 : 2; q.epi_ow = OW; q.epi_s = s;
+    if (epi_x != nullptr) {
+        if (s != 1) return DK_ERR_UNSUPPORTED;
+        q.epi_x = epi_x; q.epi_cb = epi_cb; q.epi_cd = epi_cd;
+    }
     CUtensorMap ta = {}, tb;
     int rc = make_map(&tb, w, C, F, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);  // B(k=f, n=c) = W[f][c]: n contiguous
     if (rc) return rc;
     if (tma_ok(dy, P)) {
         rc = make_map(&ta, dy, P, F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
         if (rc) return rc;
+        if (epi_x != nullptr && g_epi_ring && tma_ok(epi_x, P)) {
+            // the epilogue's second operand through TMA: two tiles' worth of 32-channel chunks, at most TC_XR_MAX / what fits
+            CUtensorMap tx;
+            rc = make_map(&tx, epi_x, P, C, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+            const int chunks = q.bn / 32;
+            q.xring = chunks >= 4 ? 4 : 2 * chunks > TC_XR_MAX ? TC_XR_MAX : 2 * chunks;
+            if (chunks == 2 && q.num_tiles >= 2 * sm_count()) q.xring = 2;  // (two CTAs per SM: one tile's worth each)
+            rc = tc_launch(ta, tb, q, NoGather{}, NoGather{}, st, true, &tx);
+            if (rc != DK_ERR_UNSUPPORTED) return rc;
+            q.xring = 0;
+        }
         return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st, s == 1);
     }
     if (repack_wanted(dy, P, 1, false)) {
@@ -1289,6 +1392,13 @@ int tc_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int 
     return cv_dgrad(dy, w, dx, N, mk_geom(C, H, W, F, kh, kw, s, p), st);
 }
 
+// pointwise dgrad (stride 1) whose epilogue adds cb[c]*x + cd[c]: the backward of the BatchNorm folded into this layer
+int tc_pw_dgrad_affine(const float *dy, const float *w, const float *x, const float *cb, const float *cd, float *dx, int N,
+                       int C, int OH, int OW, int F, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!g_tc_ready || (g_tc_disable_mask & 2)) return DK_ERR_UNSUPPORTED;
+    return pw_dgrad(dy, w, dx, N, C, OH, OW, F, 1, ws, ws_bytes, st, x, cb, cd);
+}
+
 int tc_conv_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
                   int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (!g_tc_ready || (g_tc_disable_mask & 4)) return DK_ERR_UNSUPPORTED;
@@ -1417,6 +1527,7 @@ int dk_tc_debug_set(int key, int value) {
         case 19: dk::g_ct_wgrad2 = value; break;  // 0: conv_tma wgrad through column-shifted global copies only
         case 18: dk::g_ct_kc16 = value; break;  // conv_tma forward / dgrad: 0 = 32-channel stages only
         case 17: dk::g_conv_tma_enabled = value; break;  // 0: stride-1 k x k convolutions skip conv_tma.cu (gather variants instead)
+        case 21: dk::g_epi_ring = value; break;  // 0: dk_pwconv_dgrad_affine loads the BatchNorm input from the epilogue warps
         case 20: dk::g_conv_mat_enabled = value; break;  // 0: no materialised-patch path (general convolutions fall to the gather variants)
         case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
         default: dk::set_error("dk_tc_debug_set: unknown key %d", key); return DK_ERR_INVALID;

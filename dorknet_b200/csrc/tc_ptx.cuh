@@ -150,6 +150,11 @@ __device__ __forceinline__ uint32_t mn_tile_off(int m, int k) {
 __device__ __forceinline__ uint32_t km_tile_off(int r, int k) {
     return (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
 }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }

@@ -2,8 +2,7 @@
 import numpy as np
 
 from .layer import Layer, api, runtime, asarray, empty
-from ..array import LazyStridedGrad
-from ..array import LazyBNOutput
+from ..array import FoldedBNGrad, LazyBNOutput, LazyDWOutput, LazyStridedGrad, ZeroSumGrad
 
 
 class _RunningStats(dict):
@@ -99,6 +98,28 @@ class BatchNormLayer(Layer):
         api.dk_bn_apply_strided(self._x.ptr, out.ptr, base + 8 * C, base + 12 * C, 1, N, C, H, W, int(stride),
                                 runtime.stream())
 
+    def can_fold(self, policy=True):
+        """May the PointwiseConvLayer that received our deferred output fold the normalisation into its GEMMs (bn_fold.cu)?
+        policy True: only when the statistics come for free from the producing depthwise kernel (a still-unlaunched
+        LazyDWOutput), which is what makes the fold a win; "always": whenever the output is still deferred."""
+        if self._pending is None or self._relu_claimed or self.input_dimension != 4:
+            return False
+        if policy == "always":
+            return True
+        return bool(policy) and isinstance(self._x, LazyDWOutput) and not self._x.is_materialised
+
+    def fold_statistics(self):
+        """A PointwiseConvLayer took our deferred output and folds the normalisation into its GEMMs: only the statistics
+        are produced (batch mean / std, running statistics, saved scale / shift) -- by the depthwise forward kernel itself
+        when our input is a still-unlaunched LazyDWOutput, else by the statistics pass.  Returns (x, saved base pointer,
+        has_residual); backward() is served by that layer (array.FoldedBNGrad)."""
+        pending, self._pending = self._pending, None
+        if pending is None:
+            raise RuntimeError("BatchNormLayer {}: output already materialised".format(self.layer_name))
+        has_resid = self._fold_stats()
+        self._relu_fused = False
+        return self._x, self._bufs["saved"].ptr, has_resid
+
     def apply_saved(self, y, relu):
         """y = relu?(x*scale + shift) from the statistics of the last training forward (a late reader of an output
         whose full-size pass was skipped)."""
@@ -162,7 +183,7 @@ class BatchNormLayer(Layer):
                 self.non_learned_params["running_mean"] = empty(self._stat_shape(C))
                 self.non_learned_params["running_std"] = empty(self._stat_shape(C))
             rm, rs = self.non_learned_params["running_mean"], self.non_learned_params["running_std"]
-            sv = self._buf("saved", (4, C))  # mean, invstd, scale, shift
+            sv = self._buf("saved", (5, C))  # mean, invstd, scale, shift, TF32 truncation residual (folded path only)
             ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
             base = sv.ptr
             self._flush()
@@ -184,6 +205,13 @@ class BatchNormLayer(Layer):
                 api.dk_bn_fwd_train(X.ptr, out_ptr, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, int(first), mom, eps,
                                     base, base + 4 * C, base + 8 * C, base + 12 * C, relu, N, C, HW, ws, wsn,
                                     runtime.stream())
+            def fold_stats():
+                if isinstance(X, LazyDWOutput) and not X.is_materialised:
+                    X.layer.forward_with_bn_statistics(X, gamma.ptr, beta.ptr, rm.ptr, rs.ptr, first, mom, eps, base)
+                    return True
+                run(None, 0)
+                return False
+            self._fold_stats = fold_stats
             if self.defer_apply:
                 # nothing is launched until the consumer is known: a ReLu asks for the fused variant, anybody else
                 # (or a reader of the running statistics) gets the plain one
@@ -205,12 +233,15 @@ class BatchNormLayer(Layer):
 
     def backward(self, upstream_dx):
         """batch_norm.py:118-174: grads["gamma"], grads["beta"] and dx in two passes over (dY, X)."""
+        if isinstance(upstream_dx, FoldedBNGrad) and upstream_dx.bn is self and not upstream_dx.is_materialised:
+            return upstream_dx.dx  # dgamma / dbeta / dx were produced by the pointwise layer this BatchNorm is folded into
         dY = asarray(upstream_dx)
         self._flush()
         N, C, HW = self._dims(self.input_shape)
         sv = self._bufs["saved"]
         base = sv.ptr
         dx = self._buf("dx", self.input_shape)
+        dx = ZeroSumGrad(dx.t, dx.shape)
         dg, db = self._grad("gamma"), self._grad("beta")
         ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
         if (isinstance(dY, LazyStridedGrad) and not dY.is_materialised and dY.stride == 2 and self.input_dimension == 4
@@ -236,6 +267,7 @@ class BatchNormLayer(Layer):
         N, C, HW = self._dims(self.input_shape)
         base = self._bufs["saved"].ptr
         dx = self._buf("dx", self.input_shape)
+        dx = ZeroSumGrad(dx.t, dx.shape)
         dg, db = self._grad("gamma"), self._grad("beta")
         ws, wsn = self._zeroed_ws(api.dk_bn_ws_bytes(C))
         api.dk_bn_bwd_join(dY.ptr, block_out.ptr, self._x.ptr, self._param("gamma").ptr, base, base + 4 * C, base + 8 * C,

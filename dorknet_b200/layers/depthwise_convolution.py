@@ -1,7 +1,10 @@
 """DepthwiseConvLayer (reference: layers/depthwise_convolution.py:10-352, layers/im2col.pyx:109-178)."""
+import os
+
 import numpy as np
 
 from .layer import Layer, api, runtime, asarray
+from ..array import LazyDWOutput
 
 
 class DepthwiseConvLayer(Layer):
@@ -38,6 +41,7 @@ class DepthwiseConvLayer(Layer):
             self.learned_params = {}
             self.grads = {}
         self._x = None
+        self.defer_forward = os.environ.get("DK_DW_DEFER", "1") != "0"  # training: return a lazy output so that a folded BatchNorm can ride on the forward kernel
 
     def __repr__(self):
         out = "DepthwiseConvLayer({}, ".format(self.layer_name)
@@ -62,11 +66,34 @@ class DepthwiseConvLayer(Layer):
         self.input_shape = X.shape
         y = self._buf("y", (N, C, int(self.num_row_patches), int(self.num_col_patches)))
         bias = self._param("bias").ptr if self.with_bias else None
-        api.dk_dwconv_fwd(X.ptr, self._param("weights").ptr, bias, y.ptr, None, None, 0,
-                          N, C, H, W, self.f_rows, self.f_cols, s, p, runtime.stream())
+
+        def plain():
+            api.dk_dwconv_fwd(X.ptr, self._param("weights").ptr, bias, y.ptr, None, None, 0,
+                              N, C, H, W, self.f_rows, self.f_cols, s, p, runtime.stream())
         if not test_mode:
             self._x = X
+            if self.defer_forward and api.dk_dwconv_fwd_bn_ws_bytes(N, C, H, W, self.f_rows, self.f_cols, s, p) > 0:
+                # nothing is launched until the consumer is known: a BatchNorm that gets folded into the pointwise layer
+                # behind it takes the variant that also produces its statistics (forward_with_bn_statistics)
+                return LazyDWOutput(y, plain, self)
+        plain()
         return y
+
+    def forward_with_bn_statistics(self, out, gamma, beta, running_mean, running_std, first_batch, momentum, eps, saved):
+        """The deferred forward of `out` (a LazyDWOutput of this layer) + the training statistics of the BatchNorm that
+        consumes it, in one pass (dk_dwconv_fwd_bn).  `saved`: device pointer to the BatchNorm's [5, C] block
+        (mean, invstd, scale, shift, truncation residual)."""
+        if out.layer is not self or out.is_materialised:
+            raise RuntimeError("DepthwiseConvLayer {}: output already produced".format(self.layer_name))
+        N, C, H, W = self.input_shape
+        s, p = int(self.stride), int(self.padding)
+        bias = self._param("bias").ptr if self.with_bias else None
+        x_ptr = self._x.ptr  # (may launch the producer's own deferred kernels: before ours, in stream order)
+        ws, wsn = runtime.scratch(api.dk_dwconv_fwd_bn_ws_bytes(N, C, H, W, self.f_rows, self.f_cols, s, p))
+        out.launched_by_consumer()
+        api.dk_dwconv_fwd_bn(x_ptr, self._param("weights").ptr, bias, out._buf.ptr, N, C, H, W, self.f_rows, self.f_cols, s, p,
+                             gamma, beta, running_mean, running_std, int(first_batch), float(momentum), float(eps),
+                             saved, saved + 4 * C, saved + 8 * C, saved + 12 * C, saved + 16 * C, ws, wsn, runtime.stream())
 
     def backward(self, upstream_dx, dx_add=None):
         """depthwise_convolution.py:186-196: fused dX + per-plane dW partials, summed over images.

@@ -1,8 +1,10 @@
 """PointwiseConvLayer (reference: layers/pointwise_convolution.py:6-129)."""
+import os
+
 import numpy as np
 
 from .layer import Layer, api, runtime, asarray
-from ..array import LazyReluOutput, LazyStridedGrad
+from ..array import FoldedBNGrad, LazyBNOutput, LazyReluOutput, LazyStridedGrad, ZeroSumGrad
 
 
 class PointwiseConvLayer(Layer):
@@ -44,6 +46,11 @@ class PointwiseConvLayer(Layer):
         self._xgeom = None
         self.lazy_strided_dx = True  # stride > 1: return the input gradient as a LazyStridedGrad
         self.fuse_strided_input = True  # BatchNorm -> ReLU -> stride-s input: normalise only the pixels this layer reads
+        # BatchNorm (no ReLU) -> this layer, stride 1: fold the normalisation into the GEMMs (bn_fold.cu).  True: when the
+        # BatchNorm's statistics ride on the depthwise kernel before it (always a win); "always": whenever possible; False: never
+        self.fold_bn_input = {"0": False, "always": "always"}.get(os.environ.get("DK_FOLD_BN", "1"), True)
+        self.trust_zero_sum = os.environ.get("DK_FOLD_ZEROSUM", "1") != "0"  # skip the channel sums of a BatchNorm's input gradient
+        self._folded_bn = None
 
     def __repr__(self):
         out = "PointwiseConvLayer({}, ".format(self.layer_name)
@@ -65,6 +72,23 @@ class PointwiseConvLayer(Layer):
         self.input_shape = X.shape
         y = self._buf("y", (N, self.num_filters, OH, OW))
         bias = self._param("bias").ptr if self.with_bias else None
+        self._folded_bn = None
+        if (s == 1 and self.fold_bn_input and not test_mode and isinstance(X, LazyBNOutput) and X.fusable
+                and (H * W) % 4 == 0 and X.bn.can_fold(self.fold_bn_input)):
+            # BatchNorm -> pointwise with nothing in between: y = (W diag(scale)) . x + W . shift.  The BatchNorm only
+            # produces its statistics (inside the depthwise kernel that feeds it); this GEMM reads the BatchNorm's INPUT and
+            # the normalised tensor is never produced (unless somebody else reads it: X.consume() leaves a late-reader thunk)
+            bn = X.bn
+            x_raw, saved, has_resid = bn.fold_statistics()
+            X.consume()
+            wf, bf = self._buf("w_fold", (self.num_filters, C)), self._buf("b_fold", (self.num_filters,))
+            api.dk_bn_fold_fwd(self._param("weights").ptr, bias, saved + 8 * C, saved + 12 * C, saved,
+                               saved + 16 * C if has_resid else None, wf.ptr, bf.ptr, self.num_filters, C, runtime.stream())
+            self._folded_bn = bn
+            self._x, self._xgeom = x_raw, (H, W, 1)
+            ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, H, W, self.num_filters, 1))
+            api.dk_pwconv_fwd(x_raw.ptr, wf.ptr, bf.ptr, y.ptr, N, C, H, W, self.num_filters, 1, ws, wsn, runtime.stream())
+            return y
         if (s > 1 and self.fuse_strided_input and not test_mode and isinstance(X, LazyReluOutput)
                 and not X.is_materialised and X.bn._pending is not None):
             # BatchNorm -> ReLU -> X[:, :, ::s, ::s]: only the pixels this layer reads are normalised, into a compact
@@ -91,6 +115,8 @@ class PointwiseConvLayer(Layer):
         st = runtime.stream()
         ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, max(H, OH * s), max(W, OW * s), F, s))
         dbias = self._grad("bias").ptr if self.with_bias else None
+        if self._folded_bn is not None:
+            return self._backward_folded(dY, N, C, H, W, F, ws, wsn, st)
         xh, xw, xs = self._xgeom  # (a compact, already subsampled operand has stride 1)
         api.dk_pwconv_wgrad(dY.ptr, self._x.ptr, w.ptr, self._grad("weights").ptr, dbias, self._l2_strength(),
                             N, C, xh, xw, F, xs, ws, wsn, st)
@@ -112,3 +138,33 @@ class PointwiseConvLayer(Layer):
             return LazyStridedGrad(dx, full, s, compact)
         api.dk_pwconv_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, OH, OW, F, s, ws, wsn, st)
         return dx
+
+    def _backward_folded(self, dY, N, C, H, W, F, ws, wsn, st):
+        """Backward of (BatchNorm -> this layer) as ONE unit (bn_fold.cu): the raw wgrad GEMM dY . x^T, a [F, C]-sized
+        kernel that turns it into dW, the BatchNorm's dgamma / dbeta and the coefficients of its input gradient, and the
+        dgrad GEMM on the folded weights whose epilogue adds cb*x + cd.  No pass over the activations besides the two
+        GEMMs; the BatchNorm's own backward kernel does not run."""
+        bn, w = self._folded_bn, self._param("weights")
+        saved = bn._bufs["saved"].ptr
+        g_raw = self._buf("g_raw", (F, C))
+        api.dk_pwconv_wgrad(dY.ptr, self._x.ptr, w.ptr, g_raw.ptr, None, 0.0, N, C, H, W, F, 1, ws, wsn, st)
+        s_col = None
+        if self.with_bias or not isinstance(dY, ZeroSumGrad) or not self.trust_zero_sum:
+            # channel sums of dY: the bias gradient, and the shift term of the folded wgrad.  A BatchNorm's input gradient
+            # sums to zero per channel (array.ZeroSumGrad), which is what arrives here in the depthwise-separable unit
+            sbuf = self._grad("bias") if self.with_bias else self._buf("s_col", (F,))
+            api.dk_bias_grad(dY.ptr, sbuf.ptr, N, F, H * W, None, 0, st)
+            s_col = sbuf.ptr
+        coef = self._buf("bn_coef", (2, C))
+        api.dk_bn_fold_bwd(g_raw.ptr, s_col, w.ptr, bn._param("gamma").ptr, saved, saved + 4 * C, saved + 8 * C,
+                           saved + 12 * C, self._l2_strength(), N * H * W, self._grad("weights").ptr,
+                           bn._grad("gamma").ptr, bn._grad("beta").ptr, coef.ptr, coef.ptr + 4 * C, F, C, st)
+        bn_dx = bn._buf("dx", bn.input_shape)
+        api.dk_pwconv_dgrad_affine(dY.ptr, self._bufs["w_fold"].ptr, self._x.ptr, coef.ptr, coef.ptr + 4 * C, bn_dx.ptr,
+                                   N, C, H, W, F, ws, wsn, st)
+        dx = self._buf("dx", (N, C, H, W))
+
+        def plain():  # somebody other than the folded BatchNorm reads our result: the reference's dX = W^T dY
+            ws2, wsn2 = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, H, W, F, 1))
+            api.dk_pwconv_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, H, W, F, 1, ws2, wsn2, runtime.stream())
+        return FoldedBNGrad(dx, plain, bn, ZeroSumGrad(bn_dx.t, bn_dx.shape))

@@ -179,6 +179,37 @@ int dk_pwconv_wgrad(const float *dy, const float *x, const float *w, float *dw, 
                     int N, int C, int H, int W, int F, int stride,
                     void *ws, size_t ws_bytes, dk_stream_t stream);
 
+/* ---- BatchNorm (no ReLU) -> PointwiseConvLayer, folded (training): layers/batch_norm.py:54-174 applied to the input of
+ * layers/pointwise_convolution.py:46-75.  Between the two layers there is no non-linearity, so with the batch statistics
+ * known (dk_bn_fwd_train with y = NULL) the normalisation is absorbed by the GEMM and its backward by the GEMM's epilogue;
+ * the normalised activation is never written or read (csrc/bn_fold.cu has the algebra).
+ *   dk_bn_fold_fwd: w_out[f,c] = w[f,c]*scale[c]; b_out[f] = (bias[f]) + sum_c w[f,c]*shift[c]; then
+ *                   dk_pwconv_fwd(x_raw, w_out, b_out) == pointwise(batchnorm(x_raw)).  With mean (and trunc_resid, the
+ *                   per-channel mean of x - tf32_truncate(x) left by dk_dwconv_fwd_bn) non-NULL, w_out is stored
+ *                   TF32-truncated and b_out compensates what the tensor core's operand truncation does to the output
+ *                   mean of a GEMM over un-centred activations (csrc/bn_fold.cu).
+ *   dk_dwconv_fwd_bn: the depthwise forward of dk_dwconv_fwd AND the training statistics of the BatchNorm that follows it
+ *                   (dk_bn_fwd_train with y = NULL: save_*, running_*), accumulated while the outputs are still in
+ *                   registers -- no pass over the activation.  dk_dwconv_fwd_bn_ws_bytes returns 0 for shapes it does not
+ *                   cover (then call the two functions separately).
+ *   dk_bn_fold_bwd: from g_raw = dk_pwconv_wgrad(dy, x_raw) (l2 = 0) and s_col[f] = sum_{n,p} dy (dk_bias_grad; NULL when the
+ *                   caller knows it is zero, e.g. dy is a BatchNorm's input gradient): dw (+ l2*w), the BatchNorm's dgamma /
+ *                   dbeta [C], and the coefficients cb, cd [C] of its input gradient.  count = N*H*W of the BatchNorm.
+ *   dk_pwconv_dgrad_affine: dx[n,c,p] = sum_f w[f,c]*dy[n,f,p] + cb[c]*x[n,c,p] + cd[c] (stride 1): called with the FOLDED
+ *                   weights and the BatchNorm's input x it yields the BatchNorm's input gradient directly. */
+int dk_bn_fold_fwd(const float *w, const float *bias, const float *scale, const float *shift, const float *mean,
+                   const float *trunc_resid, float *w_out, float *b_out, int F, int C, dk_stream_t stream);
+size_t dk_dwconv_fwd_bn_ws_bytes(int N, int C, int H, int W, int kh, int kw, int stride, int pad);
+int dk_dwconv_fwd_bn(const float *x, const float *w, const float *bias, float *y, int N, int C, int H, int W, int kh, int kw,
+                     int stride, int pad, const float *gamma, const float *beta, float *running_mean, float *running_std,
+                     int first_batch, float momentum, float eps, float *save_mean, float *save_invstd, float *save_scale,
+                     float *save_shift, float *trunc_resid, void *ws, size_t ws_bytes, dk_stream_t stream);
+int dk_bn_fold_bwd(const float *g_raw, const float *s_col, const float *w, const float *gamma, const float *save_mean,
+                   const float *save_invstd, const float *save_scale, const float *save_shift, float l2, int64_t count,
+                   float *dw, float *dgamma, float *dbeta, float *cb, float *cd, int F, int C, dk_stream_t stream);
+int dk_pwconv_dgrad_affine(const float *dy, const float *w, const float *x, const float *cb, const float *cd, float *dx,
+                           int N, int C, int OH, int OW, int F, void *ws, size_t ws_bytes, dk_stream_t stream);
+
 /* ---- DenseLayer: layers/dense_layer.py:46-67 ------------------------------------------------ */
 /* y[B,out] = x[B,in] @ w[in,out] (+ bias). */
 size_t dk_dense_ws_bytes(int B, int in_dim, int out_dim);

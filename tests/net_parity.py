@@ -53,7 +53,12 @@ TOL = {
     "grad_l2": 0.30,      # per tensor, relative L2 error vs the exact gradient
     "grad_cos": 2e-2,     # 1 - cosine between the whole gradient (all tensors) and the exact one
     "running": 1.5e-2,    # BatchNorm batch mean / std of the step (running statistics after the first batch), vs float64
-    "scores_test": 2e-2,  # test-mode scores after the SGDMomentum update, vs the reference
+    # test-mode scores after the SGDMomentum update, vs the reference.  They inherit the gradient's TF32 noise through the
+    # update (see above).  Measured on ResNet-18-depsep: 1.4e-2 with every BatchNorm as its own kernel, 2.4e-2 with the
+    # depthwise BatchNorms folded into the pointwise GEMMs (bn_fold.cu: the GEMMs then truncate un-centred activations,
+    # whose TF32 rounding noise is larger by sqrt(1 + mean^2/var) -- the output MEAN is kept exact, the per-layer gates
+    # below are unchanged)
+    "scores_test": 3e-2,
     "layer_fwd": 2e-3, "layer_dgrad": 2e-3, "layer_wgrad": 5e-3,  # (b): each GEMM of the step vs fp32 on the same operands
 }
 # fp32 SIMT GEMM backend (GPU-side cross-check): fp32 against float64.  Measured: MNIST 1.9e-6 from the exact gradient
@@ -103,7 +108,25 @@ def layerwise_check(captured, check):
             bias = l._param("bias").ptr if getattr(l, "with_bias", False) else None
             dwt, l2s = empty(w.shape), l._l2_strength()
             dbt = empty((w.shape[0],)) if bias is not None else None
-            if t == "PointwiseConvLayer":
+            if t == "PointwiseConvLayer" and getattr(l, "_folded_bn", None) is not None:
+                # BatchNorm folded into this layer (bn_fold.cu): the GEMMs consumed the BatchNorm's INPUT, the folded
+                # weights / bias, and produced the raw wgrad G and the BatchNorm's input gradient
+                x, bn = l._x, l._folded_bn
+                N, C, H, W = x.shape
+                F = l.num_filters
+                wf, bf, y = l._bufs["w_fold"], l._bufs["b_fold"], l._bufs["y"]
+                ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, H, W, F, 1))
+                yt = empty(y.shape)
+                api.dk_pwconv_fwd(x.ptr, wf.ptr, bf.ptr, yt.ptr, N, C, H, W, F, 1, ws, wsn, st)
+                check("layer_fwd", "fwd " + nm + " (folded BN)", nerr(y.get(), yt.get()))
+                api.dk_pwconv_wgrad(dY.ptr, x.ptr, w.ptr, dwt.ptr, None, 0.0, N, C, H, W, F, 1, ws, wsn, st)
+                check("layer_wgrad", "wgrad " + nm + " (raw, folded BN)", nerr(l._bufs["g_raw"].get(), dwt.get()))
+                coef = l._bufs["bn_coef"]
+                dx = bn._bufs["dx"]
+                dxt = empty(dx.shape)
+                api.dk_pwconv_dgrad_affine(dY.ptr, wf.ptr, x.ptr, coef.ptr, coef.ptr + 4 * C, dxt.ptr, N, C, H, W, F, ws, wsn, st)
+                check("layer_dgrad", "dgrad " + nm + " (+ BN backward epilogue)", nerr(dx.get(), dxt.get()))
+            elif t == "PointwiseConvLayer":
                 x, (xh, xw, xs) = l._x, l._xgeom
                 N, C = x.shape[0], x.shape[1]
                 F = l.num_filters
@@ -181,12 +204,22 @@ def container_namespace(kind):
     return M
 
 
-def run(net_name="r18", container="ours", backend=0, verbose=True):
+# fp32 SIMT backend WITH the depthwise BatchNorms folded into the pointwise GEMMs (bn_fold.cu).  The fold is the same
+# mathematics in another operation order: y = W'x + b' cancels W'.mean against b' in fp32, which perturbs the activations at
+# the 1e-6 level instead of 1e-7 -- and this network turns a 1e-6 perturbation into per-cent changes of the few gradients
+# that are sums of nearly cancelling terms (module docstring; the reference's own fp32 gradients are 9.4e-2 from exact on
+# the same tensors: measured 9.4e-2 on res7_dw2_pw/weights for both).  Forward quantities and the direction stay tight.
+TOL_FP32_FOLDED = dict(TOL_FP32, grad_gemm=0.12, grad_dw=0.12, grad_bn=0.12, grad_l2=0.05)
+
+
+def run(net_name="r18", container="ours", backend=0, verbose=True, fold=None):
+    """fold: None = product default (fold where the statistics ride on the depthwise kernel); False = every BatchNorm as
+    its own layer (the reference's operation order); "always" / True as PointwiseConvLayer.fold_bn_input."""
     from dorknet_b200 import api, workloads, launch_count
     d = np.load(os.path.join(ROOT, "tests", "golden", {"r18": "r18_b8", "mnist": "mnist_b16"}[net_name] + ".npz"))
     M = container_namespace(container)
     api.dk_set_gemm_backend(backend)
-    tol = TOL if backend == 0 else TOL_FP32
+    tol = TOL if backend == 0 else (TOL_FP32 if fold is False else TOL_FP32_FOLDED)
     try:
         if net_name == "r18":
             net = workloads.build_resnet18_depsep(M, classes=120, conv0_padding=1, seed=0)
@@ -195,6 +228,10 @@ def run(net_name="r18", container="ours", backend=0, verbose=True):
         else:
             net = workloads.build_mnist_convnet(M, seed=0)
             X, Y, lr = d["X"], d["Y"], 0.01
+        if fold is not None:
+            for l in workloads.iter_param_layers(net):
+                if hasattr(l, "fold_bn_input"):
+                    l.fold_bn_input = fold
         # same seed, same draw order as the reference build: check before comparing anything
         for l in workloads.iter_param_layers(net):
             for k, v in l.learned_params.items():
@@ -277,6 +314,7 @@ if __name__ == "__main__":
     ap.add_argument("--net", default="r18", choices=["r18", "mnist"])
     ap.add_argument("--container", default="ours", choices=["ours", "ref"])
     ap.add_argument("--backend", type=int, default=0)
+    ap.add_argument("--fold", default="default", choices=["default", "off", "always"])
     a = ap.parse_args()
-    run(a.net, a.container, a.backend)
+    run(a.net, a.container, a.backend, fold={"default": None, "off": False, "always": "always"}[a.fold])
     print("net_parity ok")

@@ -234,6 +234,11 @@ def test_mini_resnet_three_training_steps(golden, L, backend, bn_fused):
         for l in defs.iter_param_layers(net):
             for k in list(l.learned_params.keys()):
                 l.learned_params[k] = d["init/%s/%s" % (l.layer_name, k)].copy()
+            if hasattr(l, "fold_bn_input"):
+                # BatchNorm folded into the pointwise GEMMs (bn_fold.cu) is the same mathematics with other TF32 roundings
+                # (raw activations and scaled weights are truncated instead of normalised activations and weights): the two
+                # tightly pinned configurations keep the reference's operation order, the product default folds
+                l.fold_bn_input = chaotic
         opt = L.SGDMomentum(net, 0.02, 0.9)
         tol = 3e-4 if backend == 0 else 2e-4
         # absolute floor for gradients that are small because they cancel (zero in exact arithmetic for a BN that

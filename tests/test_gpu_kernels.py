@@ -458,3 +458,163 @@ def test_input_pipeline_u8_nhwc(mixup):
     assert_close(Xd.get(), Xref, 1e-6 if mixup else 0.0, "X")
     assert np.array_equal(Yd.get(), Yref)
     up.release()
+
+
+FOLD_CASES = [
+    # N, C, H, W, F, bias, zero_sum upstream
+    (4, 64, 56, 56, 64, False, True),     # the 56 x 56 unit of ResNet-18-depsep
+    (8, 128, 28, 28, 128, False, True),
+    (8, 256, 14, 14, 512, False, True),   # F = 512: two n-blocks in wgrad, 256-column accumulators in dgrad
+    (6, 512, 6, 6, 512, False, True),     # small planes (36 pixels): one partial M tile per image
+    (6, 512, 7, 7, 512, False, True),     # 7 x 7 planes (49 pixels, nothing TMA-aligned): NOT folded, the unfused pair runs
+    (3, 24, 10, 12, 40, True, False),     # bias + an upstream gradient with non-zero channel sums (S term), odd channel counts
+    (2, 8, 5, 5, 8, False, False),        # P = 25: nothing TMA-aligned
+]
+
+
+@pytest.mark.parametrize("case", FOLD_CASES)
+@pytest.mark.parametrize("backend", [0, 1])
+def test_batchnorm_folded_into_pointwise_vs_oracle(O, case, backend):
+    """BatchNorm (no ReLU) -> PointwiseConvLayer as one unit (bn_fold.cu): y, dW, the BatchNorm's dgamma / dbeta and
+    its input gradient against the oracle's unfused chain (batch_norm.py:54-174 + pointwise_convolution.py:46-75).  The
+    BatchNorm launches its statistics pass only; its backward kernel does not run.  backend 1 (fp32 SIMT GEMMs) pins the
+    algebra tightly, backend 0 is the TF32 product path."""
+    from dorknet_b200 import api
+    from dorknet_b200.array import FoldedBNGrad, ZeroSumGrad, asarray
+    from dorknet_b200.layers.batch_norm import BatchNormLayer
+    from dorknet_b200.layers.pointwise_convolution import PointwiseConvLayer
+    from dorknet_b200.regularisers.l2 import l2
+    N, C, H, W, F, bias, zero_sum = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = (rng.standard_normal((N, C, H, W)) * rng.uniform(0.5, 3.0, (1, C, 1, 1)) + rng.uniform(-2, 2, (1, C, 1, 1))).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, (1, C, 1, 1)).astype(np.float32)
+    beta = rng.uniform(-0.5, 0.5, (1, C, 1, 1)).astype(np.float32)
+    Wt = (rng.standard_normal((F, C)) / np.sqrt(C)).astype(np.float32)
+    b = rng.standard_normal(F).astype(np.float32) if bias else None
+    dY = rng.standard_normal((N, F, H, W)).astype(np.float32)
+    if zero_sum:
+        dY -= dY.mean(axis=(0, 2, 3), keepdims=True)
+    api.dk_set_gemm_backend(backend)
+    try:
+        bn = BatchNormLayer("bn", input_dimension=4, incoming_chans=C)
+        bn.learned_params["gamma"], bn.learned_params["beta"] = gamma, beta
+        pw = PointwiseConvLayer("pw", filter_block_shape=(F, C), with_bias=bias, weight_regulariser=l2(1e-2))
+        pw.fold_bn_input = "always"  # (the default folds only when the statistics ride on a depthwise kernel: next test)
+        pw.learned_params["weights"] = Wt
+        if bias:
+            pw.learned_params["bias"] = b
+        Xh, cache, rm, rs = O.bn_fwd_train(X, gamma, beta, None, None)
+        Yo, pcache = O.pointwise_fwd(Xh, Wt, b, 1)
+        Y = pw.forward(bn.forward(X))
+        g_tol, w_tol = (GEMM, GEMM_W) if backend == 0 else (FP32_RED, FP32_RED)
+        if (H * W) % 4 != 0:
+            assert pw._folded_bn is None
+            assert_close(Y.get(), Yo, g_tol, "Y (not foldable)")
+            return
+        assert pw._folded_bn is bn
+        assert_close(Y.get(), Yo, g_tol, "Y")
+        assert_close(bn.non_learned_params["running_mean"].get(), rm, FP32, "running_mean")
+        assert_close(bn.non_learned_params["running_std"].get(), rs, FP32, "running_std")
+        dXh_o, pg = O.pointwise_bwd(dY, Wt, pcache, 1, l2_strength=1e-2, with_bias=bias)
+        dXo, bg = O.bn_bwd(dXh_o, gamma, cache)
+        up = asarray(dY)
+        if zero_sum:
+            up = ZeroSumGrad(up.t, up.shape)
+        back = pw.backward(up)
+        assert isinstance(back, FoldedBNGrad) and not back.is_materialised
+        dX = bn.backward(back)
+        assert not back.is_materialised, "the BatchNorm must take the folded gradient, not trigger the plain dgrad"
+        # the BatchNorm-critical sums are differences of TF32 GEMM results: gates relative to the largest entry, with the
+        # wgrad tolerance (they ARE wgrad results); fp32 backend: reduction tolerance
+        assert_close(pw.grads["weights"].get(), pg["weights"], w_tol, "dW")
+        if bias:
+            assert_close(pw.grads["bias"].get(), pg["bias"], FP32_RED, "db")
+        scale_g = float(np.max(np.abs(bg["gamma"])))
+        assert_close(bn.grads["gamma"].get(), bg["gamma"], w_tol, "dgamma", atol=w_tol * scale_g)
+        assert_close(bn.grads["beta"].get(), bg["beta"], w_tol, "dbeta", atol=w_tol * max(scale_g, float(np.max(np.abs(bg["beta"])))))
+        assert_close(dX.get(), dXo, 2 * g_tol, "dX", atol=1e-6)
+        # a late reader of either deferred object gets the reference's tensors
+        assert_close(back.get(), dXh_o, g_tol, "dX_hat (late reader)")
+        # and the unfused pair agrees too
+        pw.fold_bn_input = False
+        Y2 = pw.forward(bn.forward(X))
+        assert pw._folded_bn is None
+        assert_close(Y2.get(), Yo, g_tol, "Y unfused")
+    finally:
+        api.dk_set_gemm_backend(0)
+
+
+DW_BN_PW_CASES = [
+    # N, C, H, W, F
+    (4, 64, 56, 56, 64),     # the first units of ResNet-18-depsep: 14 strips per row, segments cut by warp boundaries
+    (8, 128, 28, 28, 128),
+    (3, 40, 24, 32, 72),     # odd channel counts, rectangular
+    (2, 16, 64, 64, 16),     # several bands per plane
+]
+
+
+@pytest.mark.parametrize("case", DW_BN_PW_CASES)
+@pytest.mark.parametrize("backend", [0, 1])
+def test_depthwise_batchnorm_pointwise_unit_fused_vs_oracle(O, case, backend):
+    """dw3x3 -> BatchNorm -> pointwise, the product default: the depthwise forward kernel also produces the BatchNorm
+    statistics (dk_dwconv_fwd_bn), the normalisation is folded into the pointwise GEMMs (bn_fold.cu) and the BatchNorm's
+    backward into the dgrad epilogue -- against the oracle's three separate layers, forward, running statistics and every
+    gradient down to the depthwise input."""
+    from dorknet_b200 import api
+    from dorknet_b200.array import LazyDWOutput
+    from dorknet_b200.layers.batch_norm import BatchNormLayer
+    from dorknet_b200.layers.depthwise_convolution import DepthwiseConvLayer
+    from dorknet_b200.layers.pointwise_convolution import PointwiseConvLayer
+    N, C, H, W, F = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = np.maximum(rng.standard_normal((N, C, H, W)) + 0.5, 0).astype(np.float32)  # post-ReLU-like: positive mean
+    Wd = (rng.standard_normal((C, 3, 3)) / 3.0 + 0.1).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, (1, C, 1, 1)).astype(np.float32)
+    beta = rng.uniform(-0.5, 0.5, (1, C, 1, 1)).astype(np.float32)
+    Wp = (rng.standard_normal((F, C)) / np.sqrt(C)).astype(np.float32)
+    dY = rng.standard_normal((N, F, H, W)).astype(np.float32)
+    dY -= dY.mean(axis=(0, 2, 3), keepdims=True)
+    api.dk_set_gemm_backend(backend)
+    try:
+        dw = DepthwiseConvLayer("dw", filter_block_shape=(C, 3, 3), stride=1, padding=1, with_bias=False)
+        dw.learned_params["weights"] = Wd
+        bn = BatchNormLayer("bn", input_dimension=4, incoming_chans=C)
+        bn.learned_params["gamma"], bn.learned_params["beta"] = gamma, beta
+        pw = PointwiseConvLayer("pw", filter_block_shape=(F, C), with_bias=False)
+        pw.learned_params["weights"] = Wp
+        Do, dcache = O.depthwise_fwd(X, Wd, None, 1, 1)
+        Xh, cache, rm, rs = O.bn_fwd_train(Do, gamma, beta, None, None)
+        Yo, pcache = O.pointwise_fwd(Xh, Wp, None, 1)
+        d_out = dw.forward(X)
+        assert isinstance(d_out, LazyDWOutput) and not d_out.is_materialised
+        Y = pw.forward(bn.forward(d_out))
+        assert pw._folded_bn is bn and d_out.is_materialised
+        g_tol, w_tol = (GEMM, GEMM_W) if backend == 0 else (FP32_RED, FP32_RED)
+        assert_close(d_out.get(), Do, FP32, "depthwise output")
+        assert_close(bn.non_learned_params["running_mean"].get(), rm, FP32, "running_mean")
+        assert_close(bn.non_learned_params["running_std"].get(), rs, FP32_RED, "running_std")
+        assert_close(Y.get(), Yo, g_tol, "Y")
+        # the mean of every output channel is exact although the GEMM multiplied un-centred, truncated activations
+        ym, yo_m = Y.get().mean(axis=(0, 2, 3)), Yo.mean(axis=(0, 2, 3))
+        assert np.abs(ym - yo_m).max() <= 2e-5 * Yo.std(), "output mean %g vs %g" % (np.abs(ym - yo_m).max(), Yo.std())
+        dXh_o, pg = O.pointwise_bwd(dY, Wp, pcache, 1)
+        dDo, bg = O.bn_bwd(dXh_o, gamma, cache)
+        dXo, dg = O.depthwise_bwd(dDo, Wd, dcache, 1, 1)
+        dX = dw.backward(bn.backward(pw.backward(dY)))
+        assert_close(pw.grads["weights"].get(), pg["weights"], w_tol, "dW pointwise")
+        scale_g = float(np.max(np.abs(bg["gamma"])))
+        assert_close(bn.grads["gamma"].get(), bg["gamma"], w_tol, "dgamma", atol=w_tol * scale_g)
+        assert_close(bn.grads["beta"].get(), bg["beta"], w_tol, "dbeta", atol=w_tol * scale_g)
+        assert_close(dX.get(), dXo, 2 * g_tol, "dX")
+        assert_close(dw.grads["weights"].get(), dg["weights"], 2 * w_tol, "dW depthwise")
+        # second step: running statistics EMA through the fused path
+        X2 = (0.5 * X + 0.25).astype(np.float32)
+        Do2, _ = O.depthwise_fwd(X2, Wd, None, 1, 1)
+        _, _, rm2, rs2 = O.bn_fwd_train(Do2, gamma, beta, rm, rs)
+        pw.forward(bn.forward(dw.forward(X2)))
+        assert_close(bn.non_learned_params["running_mean"].get(), rm2, FP32, "running_mean 2")
+        assert_close(bn.non_learned_params["running_std"].get(), rs2, FP32_RED, "running_std 2")
+        # a lazy depthwise output read by anybody else is the plain forward
+        assert_close(dw.forward(X).get(), Do, FP32, "plain deferred forward")
+    finally:
+        api.dk_set_gemm_backend(0)

@@ -12,12 +12,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("backend", [0, 1])
-def test_resnet18_depsep_225_batch8_training_step(backend):
+@pytest.mark.parametrize("backend,fold", [(0, None), (0, False), (1, False), (1, None)])
+def test_resnet18_depsep_225_batch8_training_step(backend, fold):
     """cfg3's network (examples/imagenet_dogs_225_resnet_18_depsep.py:32-160) at 225x225, batch 8: loss, scores, all
-    137 parameter gradients, BatchNorm running statistics, test-mode scores after the update."""
+    137 parameter gradients, BatchNorm running statistics, test-mode scores after the update.  fold None = the product
+    default (depthwise BatchNorms folded into the pointwise GEMMs where their statistics ride on the depthwise kernel),
+    False = every BatchNorm as its own layer, the reference's operation order (the tight fp32 gates apply to that one)."""
     import net_parity
-    net_parity.run("r18", "ours", backend)
+    net_parity.run("r18", "ours", backend, fold=fold)
 
 
 @pytest.mark.parametrize("backend", [0, 1])
