@@ -97,7 +97,8 @@ class OptTensor(ctypes.Structure):
 class P2PCtx(ctypes.Structure):
     """mirror of dk_p2p_ctx"""
     _fields_ = [("world", c_int), ("rank", c_int), ("grad_delta", c_int64 * 8), ("ready", c_void_p * 8),
-                ("done", c_void_p * 8), ("epoch", c_void_p)]
+                ("done", c_void_p * 8), ("epoch", c_void_p), ("reduced", c_void_p * 8), ("grad_base", c_void_p),
+                ("nfloats", c_int64), ("slice", c_int64)]
 
 
 class SumsqTask(ctypes.Structure):

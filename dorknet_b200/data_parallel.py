@@ -105,7 +105,7 @@ class _RawCudaArray:
 class P2PExchange:
     """Peer-mapped gradient buffers + flag blocks of all ranks of one box, and the device-side dk_p2p_ctx."""
 
-    FLAG_BYTES = 256  # ready[8], done[8] (uint32, indexed by writer rank), epoch at word 32
+    FLAG_BYTES = 256  # ready[8], done[8], reduced[8] (uint32, indexed by writer rank) at bytes 0 / 32 / 64, epoch at 128
 
     def __init__(self, dist, group, nfloats):
         import torch
@@ -124,7 +124,7 @@ class P2PExchange:
         # (a rank that fell back to NCCL alone would leave the others spinning on its flags).
         err = None
         try:
-            self.grad_ptr, gh = alloc(max(self.nfloats, 1) * 4)
+            self.grad_ptr, gh = alloc((max(self.nfloats, 1) + 3) // 4 * 16)
             self.flag_ptr, fh = alloc(self.FLAG_BYTES)
         except Exception as e:  # noqa: BLE001
             err, gh, fh = str(e), None, None
@@ -157,7 +157,12 @@ class P2PExchange:
             ctx.grad_delta[p] = grad_ptrs[p] - self.grad_ptr
             ctx.ready[p] = flag_ptrs[p]
             ctx.done[p] = flag_ptrs[p] + 32
+            ctx.reduced[p] = flag_ptrs[p] + 64
         ctx.epoch = self.flag_ptr + 128
+        ctx.grad_base = self.grad_ptr
+        ctx.nfloats = (max(self.nfloats, 1) + 3) // 4 * 4
+        per = (ctx.nfloats + self.world - 1) // self.world
+        ctx.slice = (per + 3) // 4 * 4
         raw = np.frombuffer(ctypes.string_at(ctypes.addressof(ctx), ctypes.sizeof(ctx)), dtype=np.uint8).copy()
         self.ctx = torch.from_numpy(raw).to(runtime.device())
         self.flat = torch.as_tensor(_RawCudaArray(self.grad_ptr, max(self.nfloats, 1)), device=runtime.device())

@@ -288,6 +288,10 @@ typedef struct {
     unsigned int *ready[DK_P2P_MAX_RANKS];  /* rank p's flag block (uint32[8], indexed by writer), as mapped HERE */
     unsigned int *done[DK_P2P_MAX_RANKS];
     unsigned int *epoch;                    /* local step counter (device memory) */
+    unsigned int *reduced[DK_P2P_MAX_RANKS]; /* "slice p of rank p's buffer holds the sum" flags, same indexing */
+    float *grad_base;                       /* MY flat gradient buffer */
+    long long nfloats;                      /* its length (a multiple of 4) */
+    long long slice;                        /* floats per rank slice (a multiple of 4; world*slice >= nfloats) */
 } dk_p2p_ctx;
 int dk_p2p_alloc(size_t bytes, void **ptr, unsigned char *handle64);
 int dk_p2p_open(const unsigned char *handle64, void **ptr);

@@ -26,25 +26,59 @@ def main():
     dp = DataParallel(net, opt)
     assert dp.mode == "p2p", "peer-memory mode did not come up: " + dp.mode
     dp.broadcast_parameters(0)
+    from dorknet_b200.array import asarray
     step = GraphedTrainStep(net, opt, dp, warmup=1)
     worst = 0.0
-    for it in range(4):  # 1 eager step, then captured graphs
-        X, _, Y = W.synthetic_batch(8, 3, 65, 10, seed=100 * rank + it)
-        before = [l.learned_params[k].t.clone() for l, k in dp.entries]
-        step(X, Y)
-        torch.cuda.synchronize()
-        g = dp.flat.clone()  # this rank's gradients of the step (the optimiser does not modify them)
-        dist.all_reduce(g)
-        g /= world
+    nf = int(dp.p2p.nfloats)
+    nf4 = (nf + 3) // 4 * 4
+    per = (nf4 + world - 1) // world
+    sl = (per + 3) // 4 * 4  # floats per rank slice (data_parallel.P2PExchange)
+
+    def check(before, mean_grad):
+        w = 0.0
         for (l, k), b, off, n in zip(dp.entries, before, dp.offsets, dp.sizes):
             if l not in opt.learnable_layers:
                 continue
-            ref = g[off:off + n]
+            ref = mean_grad[off:off + n]
             want = b.reshape(-1) - LR * ref  # w - lr * mean gradient
             got = l.learned_params[k].t.reshape(-1)
             # (NCCL adds the ranks in another order than rank 0, 1, ...: rounding of the sum, relative to its size)
-            err = float((got - want).abs().max() / (b.abs().max() + LR * ref.abs().max() + 1e-12))
-            worst = max(worst, err)
+            w = max(w, float((got - want).abs().max() / (b.abs().max() + LR * ref.abs().max() + 1e-12)))
+        return w
+
+    for it in range(5):
+        X, _, Y = W.synthetic_batch(8, 3, 65, 10, seed=100 * rank + it)
+        before = [l.learned_params[k].t.clone() for l, k in dp.entries]
+        if it < 2:
+            # phases apart: the gradients of this rank are read BEFORE the exchange (the reduce-scatter kernel writes the
+            # sum over all ranks into slice `rank` of this buffer, in place), NCCL reduces the copy
+            net.forward(asarray(X), asarray(Y))
+            net.backward()
+            torch.cuda.synchronize()
+            g = dp.flat.clone()
+            dist.all_reduce(g)
+            g /= world
+            dp.step()
+            torch.cuda.synchronize()
+            worst = max(worst, check(before, g))
+            # and the in-place reduce-scatter itself: my slice now holds world * the NCCL mean
+            lo, hi = rank * sl, min((rank + 1) * sl, nf)
+            if hi > lo:
+                mine = dp.flat[lo:hi]
+                e = float((mine - world * g[lo:hi]).abs().max() / (world * g[lo:hi].abs().max() + 1e-12))
+                worst = max(worst, e)
+        else:
+            # the whole step as one CUDA graph (handshakes, reduce-scatter, update all captured): the update must equal
+            # -lr * (gathered reduced slices) / world
+            step(X, Y)
+            torch.cuda.synchronize()
+            pad = torch.zeros(world * sl, device=dp.flat.device)
+            lo, hi = rank * sl, min((rank + 1) * sl, nf)
+            mine = torch.zeros(sl, device=dp.flat.device)
+            if hi > lo:
+                mine[:hi - lo] = dp.flat[lo:hi]
+            dist.all_gather_into_tensor(pad, mine)
+            worst = max(worst, check(before, pad[:nf] / world))
         dist.barrier()
     chk = torch.stack([l.learned_params[k].t.double().sum() for l, k in dp.entries]).sum().reshape(1)
     allc = [torch.zeros_like(chk) for _ in range(world)]

@@ -79,7 +79,8 @@ def test_struct_layouts_match_the_header(tmp_path):
     if cc is None:
         pytest.skip("no C compiler")
     fields = {"dk_opt_tensor": (_lib.OptTensor, ["param", "grad", "state", "n"]),
-              "dk_p2p_ctx": (_lib.P2PCtx, ["world", "rank", "grad_delta", "ready", "done", "epoch"])}
+              "dk_p2p_ctx": (_lib.P2PCtx, ["world", "rank", "grad_delta", "ready", "done", "epoch", "reduced", "grad_base", "nfloats",
+                                          "slice"])}
     src = ["#include <stdio.h>", "#include <stddef.h>", '#include "dorknet_b200.h"', "int main(void) {"]
     for name, (_, fl) in fields.items():
         src.append('printf("%s %%zu", sizeof(%s));' % (name, name))
