@@ -61,6 +61,12 @@ struct TcParams {
     // epi 0: optional "+ epi_cb[n] * epi_x[(b*N + n)*ldo + m] + epi_cd[n]" -- the backward of a BatchNorm folded into this
     // dgrad GEMM (bn_fold.cu): epi_x is the BatchNorm's input, laid out like the output
     const float *epi_x, *epi_cb, *epi_cd;
+    // epi 1, split-K (mode 1) with every tile of the grid resident at once: the CTAs of an output tile add their partial
+    // sums themselves once all of them have arrived (each reduces 1/splits of the tile) -- no reduce kernel behind the GEMM
+    unsigned int *sk_counter;  // [2 * m_blocks * n_blocks], zero between launches; nullptr = partials only
+    float *sk_out;
+    const float *sk_w;
+    float sk_l2;
     int xring;       // > 0: epi_x tiles are staged by TMA into a ring of `xring` 16 KB slots (128 pixels x 32 channels) instead of
                      // being loaded by the epilogue warps themselves
     uint32_t tmem_cols, acc_stride;
@@ -708,6 +714,105 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (p.sk_counter != nullptr) {
+                // ---- cooperative split-K reduction (one tile per CTA, all CTAs resident: host guarantees) ----
+                const int et = (int)threadIdx.x - 64;  // 0..127 over the four epilogue warps
+                const int mn = p.m_blocks * p.n_blocks;
+                unsigned int *cnt = p.sk_counter + 2 * (tile - split * mn);
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    atomicAdd(cnt, 1u);
+                    const long long t0 = clock64();
+                    unsigned int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                        if (clock64() - t0 > 8000000000LL) {
+                            printf("dorknet_b200: split-K arrival wait timed out (block %d)\n", blockIdx.x);
+                            __trap();
+                        }
+                    } while (seen < (unsigned int)p.splits);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int mrows = p.M - m0 < TC_BM ? p.M - m0 : TC_BM;
+                const int cols = p.N - n0 < p.bn ? p.N - n0 : p.bn;
+                const long long plane = (long long)p.M * p.N;
+                if ((p.N & 3) == 0 && (cols & 3) == 0) {
+                    // 16-byte groups; tz threads share a group and split the partials between them (fixed shuffle tree:
+                    // deterministic), eight loads in flight per thread
+                    const int groups = (mrows * cols) >> 2;
+                    const int per = (groups + p.splits - 1) / p.splits;
+                    int tz = 1;
+                    while (tz < 32 && per * tz * 2 <= 128) tz *= 2;
+                    const int zl = et & (tz - 1);
+                    const int g_hi = (split + 1) * per < groups ? (split + 1) * per : groups;
+                    for (int g0 = split * per; g0 < g_hi; g0 += 128 / tz) {
+                        const int g = g0 + et / tz;
+                        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                        long long off = 0;
+                        if (g < g_hi) {
+                            const int e = g << 2;
+                            const int rm = e / cols, cn = e - rm * cols;
+                            off = (long long)(m0 + rm) * p.N + n0 + cn;
+                            int z = zl;
+                            for (; z + 7 * tz < p.splits; z += 8 * tz) {
+                                float4 v[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float4 *>(p.out + (z + u * tz) * plane + off));
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) { sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w; }
+                            }
+                            for (; z < p.splits; z += tz) {
+                                const float4 v = __ldcg(reinterpret_cast<const float4 *>(p.out + z * plane + off));
+                                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                            }
+                        }
+                        for (int o = tz >> 1; o > 0; o >>= 1) {
+                            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+                            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+                            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+                            sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+                        }
+                        if (g < g_hi && zl == 0) {
+                            if (p.sk_l2 != 0.0f) {
+                                const float4 wv = __ldg(reinterpret_cast<const float4 *>(p.sk_w + off));
+                                sum.x = fmaf(p.sk_l2, wv.x, sum.x); sum.y = fmaf(p.sk_l2, wv.y, sum.y);
+                                sum.z = fmaf(p.sk_l2, wv.z, sum.z); sum.w = fmaf(p.sk_l2, wv.w, sum.w);
+                            }
+                            *reinterpret_cast<float4 *>(p.sk_out + off) = sum;
+                        }
+                    }
+                } else {
+                    const int total = mrows * cols;
+                    const int per = (total + p.splits - 1) / p.splits;
+                    int tz = 1;
+                    while (tz < 32 && per * tz * 2 <= 128) tz *= 2;
+                    const int zl = et & (tz - 1);
+                    const int e_hi = (split + 1) * per < total ? (split + 1) * per : total;
+                    for (int e0 = split * per; e0 < e_hi; e0 += 128 / tz) {
+                        const int e = e0 + et / tz;
+                        float sum = 0.0f;
+                        long long off = 0;
+                        if (e < e_hi) {
+                            const int rm = e / cols, cn = e - rm * cols;
+                            off = (long long)(m0 + rm) * p.N + n0 + cn;
+                            for (int z = zl; z < p.splits; z += tz) sum += __ldcg(p.out + z * plane + off);
+                        }
+                        for (int o = tz >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                        if (e < e_hi && zl == 0) p.sk_out[off] = sum + (p.sk_l2 != 0.0f ? p.sk_l2 * __ldg(p.sk_w + off) : 0.0f);
+                    }
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    const unsigned int prev = atomicAdd(cnt + 1, 1u);
+                    if (prev == (unsigned int)p.splits - 1u) {  // everybody has read the partials: re-arm for the next launch
+                        cnt[0] = 0u;
+                        cnt[1] = 0u;
+                        __threadfence();
+                    }
+                }
+            }
         }
     }
     tc_fence_before();
@@ -729,6 +834,13 @@ static int g_hybrid_wgrad = 0;               // 1: pointwise wgrad takes X throu
 static int g_wide_items = 0;                 // wgrad k-blocks per item: 0 = automatic (pw_wgrad), 1 / 2 / 4 = forced
 static int g_two_per_sm = 1;                 // see tc_launch
 static int g_ctas_per_sm = 1;                // persistent CTAs per SM the grids / split plans are sized for
+static unsigned int *g_sk_counters = nullptr;  // arrival / departure counters of the in-kernel split-K reduction (zero at rest)
+constexpr int TC_SK_MAX_TILES = 512;
+// 1: the CTAs of a wgrad tile add their split-K partials themselves.  Parity-green but measured SLOWER than the separate
+// reduce kernel on every pointwise shape (profiles/r02w_pw_wgrad_fused_reduce.log: +0 .. +5 us of 16 .. 29 us; 128 reducing
+// threads per SM against a reduce kernel's thousands, behind the same all-CTAs-arrived barrier): off, kept behind knob 23
+static int g_fused_reduce = 0;
+static int g_wgrad_bn_cap = 0;               // pointwise wgrad: largest MMA N (0 = automatic, see pw_wgrad)
 static int g_epi_ring = 1;                   // 0: the affine dgrad epilogue loads its second operand itself (no TMA ring)
 static int g_tc_disable_mask = 0;  // bit0 fwd, bit1 dgrad, bit2 wgrad (bring-up / tests)
 
@@ -742,6 +854,13 @@ int init_gemm_tcgen05() {
         return DK_OK;
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (g_sk_counters == nullptr) {
+        if (cudaMalloc(&g_sk_counters, 2 * TC_SK_MAX_TILES * sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(g_sk_counters, 0, 2 * TC_SK_MAX_TILES * sizeof(unsigned int)) != cudaSuccess) {
+            cudaGetLastError();
+            g_sk_counters = nullptr;  // (the separate reduce kernel is used instead)
+        }
+    }
     if (const char *m = getenv("DK_TC_DISABLE_MASK")) g_tc_disable_mask = atoi(m);  // diagnostics
     if (const char *m = getenv("DK_HYBRID_WGRAD")) g_hybrid_wgrad = atoi(m);
     g_tc_ready = true;
@@ -861,8 +980,8 @@ static int tc_launch(const CUtensorMap &ta, const CUtensorMap &tb, TcParams p, c
 
 // split plan for wgrad-type GEMMs (output [M][N], reduction over `total_items` k-blocks): enough CTAs to fill the
 // machine, but the partial sums must stay small next to the inputs
-static void split_plan(int M, int N, int64_t total_items, int64_t in_bytes, int *splits, int *per) {
-    const int bn = N >= 256 ? 256 : round_up(N, 32);
+static void split_plan(int M, int N, int64_t total_items, int64_t in_bytes, int *splits, int *per, int bn_used = 0) {
+    const int bn = bn_used > 0 ? bn_used : N >= 256 ? 256 : round_up(N, 32);
     const int tiles = (int)(ceil_div(M, TC_BM) * ceil_div(N, bn));
     int64_t s = (int64_t)sm_count() * g_ctas_per_sm / tiles;
     const int64_t out_bytes = (int64_t)M * N * 4;
@@ -1064,6 +1183,25 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     q.mode = 1; q.a_mn = 0; q.b_mn = 0; q.b_batched = 1;
     q.M = F; q.N = C; q.K = (int)P; q.batches = N;
     fill_common(q);
+    {
+        // Narrower accumulators for wgrads whose output is large next to their inputs (7x7 / 14x14 planes, 256 .. 512
+        // channels): every CTA writes a 128 x bn partial tile, so with ~148 CTAs the split-K partials are 148*128*bn*4 bytes
+        // whatever the split -- 18.9 MB at bn = 256 against 12.8 MB of operands for 512 -> 512 at 7x7.
+        // Measured (tests/pw_sweep.py, batch 64, us at bn 256 / 128 / 64): 256->256 @14x14 28.5 / 19.7 / 24.4,
+        // 512->512 @7x7 33.1 / 25.4 / 32.1, 128->256 @14x14 19.3 / 19.2 / 16.0, 256->512 @7x7 24.1 / 23.5 / 21.4; planes of
+        // 28x28 and more are indifferent or lose.
+        int cap = g_wgrad_bn_cap;
+        if (cap == 0) cap = P > 196 ? 256 : C >= 256 ? 128 : C >= 128 ? 64 : 256;
+        if (cap != 64 && cap != 128) cap = 256;
+        if (q.bn > cap) {
+            q.bn = cap;
+            q.n_blocks = (int)ceil_div(q.N, q.bn);
+            q.acc_stride = q.bn <= 32 ? 32 : q.bn <= 64 ? 64 : q.bn <= 128 ? 128 : 256;
+            q.tmem_cols = 2 * q.acc_stride;
+            int st = g_smem_budget / (TC_A_BYTES + q.bn * TC_BK * 4);
+            q.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+        }
+    }
     bool a_tma = tma_ok(dy, P), b_tma = x_pitch > 0 || ((s == 1) && tma_ok(x, P));
     const bool hybrid = g_hybrid_wgrad && a_tma && b_tma && x_pitch == 0;
     if (a_tma && b_tma && !hybrid) {
@@ -1085,7 +1223,7 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
         }
     }
     q.total_items = N * q.k_blocks;
-    split_plan(F, C, q.total_items, (int64_t)N * P * (F + C) * 4, &q.splits, &q.items_per_split);
+    split_plan(F, C, q.total_items, (int64_t)N * P * (F + C) * 4, &q.splits, &q.items_per_split, q.bn);
     q.num_tiles = q.m_blocks * q.n_blocks * q.splits;
     const size_t need = (size_t)q.splits * F * C * sizeof(float);
     if (ws == nullptr || ws_bytes < need) {
@@ -1125,11 +1263,22 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     if (b_tma) rc = make_map(&tb, x, pb, C, N, TC_BK, q.bn, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const PixelGatherKM ga{dy, F, OH, OW, OW, (int)P, 1}, gb{x, C, H, W, OW, (int)P, s};
+    // every (tile, split) CTA resident at once (one CTA per SM, grid == num_tiles <= SM count): they add the partial sums
+    // themselves (sk_counter), otherwise the reduce kernel follows
+    const bool fused = g_fused_reduce && g_sk_counters != nullptr && g_ctas_per_sm == 1 && q.splits > 1 &&
+                       q.num_tiles <= sm_count() && q.m_blocks * q.n_blocks <= TC_SK_MAX_TILES;
+    if (fused) {
+        q.sk_counter = g_sk_counters;
+        q.sk_out = dw;
+        q.sk_w = w;
+        q.sk_l2 = l2;
+    }
     if (hybrid) rc = tc_launch(ta, tb, q, NoGather{}, RowsVecKM{x, C, (int)P}, st);
     else if (a_tma && b_tma) rc = tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
     else if (a_tma) rc = tc_launch(ta, tb, q, NoGather{}, gb, st);
     else rc = tc_launch(ta, tb, q, ga, gb, st);
     if (rc) return rc;
+    if (fused) return DK_OK;
     splitk_reduce_launch(q.out, w, dw, l2, (int64_t)F * C, q.splits, st);
     DK_LAUNCH_CHECK();
     return DK_OK;
@@ -1527,6 +1676,8 @@ int dk_tc_debug_set(int key, int value) {
         case 19: dk::g_ct_wgrad2 = value; break;  // 0: conv_tma wgrad through column-shifted global copies only
         case 18: dk::g_ct_kc16 = value; break;  // conv_tma forward / dgrad: 0 = 32-channel stages only
         case 17: dk::g_conv_tma_enabled = value; break;  // 0: stride-1 k x k convolutions skip conv_tma.cu (gather variants instead)
+        case 23: dk::g_fused_reduce = value; break;  // 0: pointwise wgrad partials go through the separate reduce kernel
+        case 22: dk::g_wgrad_bn_cap = value; break;  // 0 automatic, else 64 / 128 / 256
         case 21: dk::g_epi_ring = value; break;  // 0: dk_pwconv_dgrad_affine loads the BatchNorm input from the epilogue warps
         case 20: dk::g_conv_mat_enabled = value; break;  // 0: no materialised-patch path (general convolutions fall to the gather variants)
         case 8: dk::g_conv_rows_enabled = value; break;  // 0: small-K convolutions use the gather loaders, not conv_rows.cu
