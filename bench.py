@@ -709,6 +709,26 @@ def run_ours(a, spec):
                                                   "unfolded_test_mode_images_per_s": B / (msu / 1e3), "batch": B,
                                                   "note": "network.forward(test_mode=True) scores, device-resident input, "
                                                           "CUDA-graph replay; dorknet_b200.inference.fold_batchnorm"}
+        # (3) the reference's loop shape: forward / backward / update_weights as three separate calls per step
+        # (examples/imagenet_dogs_225_resnet_18_depsep.py:216-229) behind dropin.accelerate -- and as plain eager calls
+        from dorknet_b200 import dropin
+        Xl, Yl = ring[0][2], ring[0][3]
+
+        def loop_step():
+            net.forward(Xl, Yl)
+            net.backward()
+            opt.update_weights()
+        ms_eager = time_replays(loop_step)
+        ag = dropin.accelerate(net, opt, warmup=1)
+        for _ in range(3):
+            loop_step()
+        ms_auto = time_replays(loop_step)
+        ag.remove()
+        variants["unchanged_loop"] = {"value": B / (ms_auto / 1e3), "unit": UNIT, "ms_per_step": ms_auto,
+                                      "eager_ms_per_step": ms_eager, "cuda_graphs": ag.num_graphs,
+                                      "note": "network.forward(); network.backward(); optimiser.update_weights() called "
+                                              "one after the other, device-resident inputs: dropin.accelerate replays three "
+                                              "CUDA graphs per step; eager = every kernel launched from Python"}
     if rank != 0:
         return None
     cpu = None

@@ -64,3 +64,11 @@ def install(shim_cupy=True, stub_h5py=True):
             # the reference's `import h5py` (network/feed_forward_network.py:2, every layer module) gets the pure-Python
             # HDF5 subset its checkpoints use: save_weights_to_h5 / load_network_from_json_and_h5 run unchanged
             sys.modules["h5py"] = importlib.import_module("dorknet_b200.minih5")
+
+
+def accelerate(network, optimiser=None, warmup=2):
+    """Full speed behind an unchanged loop: after `warmup` steps network.forward / network.backward /
+    optimiser.update_weights of THESE INSTANCES replay CUDA graphs captured from the very same calls (one line added to a
+    reference training script, right after the network and optimiser are built).  See dorknet_b200.graph.AutoGraph."""
+    from .graph import AutoGraph
+    return AutoGraph(network, optimiser, warmup=warmup)

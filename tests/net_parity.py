@@ -309,6 +309,40 @@ def run(net_name="r18", container="ours", backend=0, verbose=True, fold=None):
         api.dk_set_gemm_backend(0)
 
 
+def autograph_check(M, steps=6):
+    """dorknet_b200.dropin.accelerate on container namespace M (the reference's own FeedForwardNetwork for --container
+    ref): the same loop as an eager twin -- forward / backward / update_weights called one after the other, the loss kept
+    as a running average like examples/imagenet_dogs_225_resnet_18_depsep.py:222-226, a test-mode forward in between, a
+    smaller last batch -- must produce bit-identical weights, and really replay graphs."""
+    from dorknet_b200 import dropin, workloads
+    rng = np.random.default_rng(5)
+    batches = [(rng.standard_normal((16 if i != 4 else 8, 1, 28, 28)).astype(np.float32), None) for i in range(steps)]
+    batches = [(x, np.eye(10, dtype=np.float32)[rng.integers(0, 10, x.shape[0])]) for x, _ in batches]
+    results = []
+    for accelerated in (False, True):
+        net = workloads.build_mnist_convnet(M, seed=3)
+        opt = M.SGDMomentum(net, 0.01, 0.9)
+        ag = dropin.accelerate(net, opt, warmup=2) if accelerated else None
+        running, test_scores = 0.0, None
+        for i, (x, y) in enumerate(batches):
+            loss, _ = net.forward(x, y)
+            net.backward()
+            opt.update_weights()
+            running = 0.9 * running + 0.1 * loss
+            if i == 3:
+                _, sc = net.forward(batches[0][0], None, test_mode=True)
+                test_scores = sc.get().copy()
+        weights = [l.learned_params[k].get().copy() for l in workloads.iter_param_layers(net) for k in sorted(l.learned_params)]
+        results.append((float(running), test_scores, weights, ag.num_graphs if ag else 0))
+    (r0, t0, w0, _), (r1, t1, w1, ng) = results
+    assert ng >= 3, "no CUDA graph was captured (%d)" % ng
+    assert r0 == r1, (r0, r1)
+    assert np.array_equal(t0, t1)
+    for a, b in zip(w0, w1):
+        assert np.array_equal(a, b)
+    return ng
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--net", default="r18", choices=["r18", "mnist"])
@@ -317,4 +351,6 @@ if __name__ == "__main__":
     ap.add_argument("--fold", default="default", choices=["default", "off", "always"])
     a = ap.parse_args()
     run(a.net, a.container, a.backend, fold={"default": None, "off": False, "always": "always"}[a.fold])
+    if a.net == "mnist":
+        print("autograph ok: %d graphs behind the unchanged loop (%s container)" % (autograph_check(container_namespace(a.container)), a.container))
     print("net_parity ok")

@@ -40,6 +40,8 @@ def test_reference_container_unchanged_drives_cuda_layers(net):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "net_parity ok" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "network.feed_forward_network" in out.stdout
+    if net == "mnist":  # dropin.accelerate: CUDA-graph replay behind the reference container's unchanged methods
+        assert "autograph ok" in out.stdout and "(ref container)" in out.stdout, out.stdout[-2000:]
 
 
 def test_p2p_gradient_exchange_two_gpus():
@@ -100,3 +102,11 @@ def test_batchnorm_folded_inference_matches_test_mode(which):
         folded.forward(Xt, terminal_layer_name=net.layers[1].layer_name)
     with pytest.raises(ValueError):
         folded.forward(Xt, Y, test_mode=False)
+
+
+def test_autograph_behind_an_unchanged_loop_is_bit_identical():
+    """dropin.accelerate (graph.AutoGraph): forward / backward / update_weights replayed from CUDA graphs after two eager
+    steps, a test-mode forward in between and a smaller last batch: bit-identical to the eager twin."""
+    import dorknet_b200.workloads as wl
+    import net_parity
+    assert net_parity.autograph_check(wl.ours()) >= 3

@@ -21,6 +21,8 @@ def load(path):
         v = v / 1e3 if u == 'ns' else v * 1e3 if u == 'ms' else v
         k = r[ki]
         k = k[:k.index('(')] if '(' in k else k
+        if 'spin_kernel' in k:
+            continue
         out.append((k.replace('void ', '').replace('dk::', ''), v, r[gi] if gi is not None else ''))
     return out
 
