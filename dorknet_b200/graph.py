@@ -42,12 +42,20 @@ class GraphedTrainStep:
         if self.dp is not None:
             self.dp.begin_step()
         loss, _ = self.net.forward(X, Y)
-        self.net.backward()
+        self._backward()
         if self.dp is not None:
             self.dp.step()
         else:
             self.opt.update_weights()
         return loss
+
+    def _backward(self):
+        """network.backward() with the weight gradients that are off the critical path on a side stream
+        (runtime.side_region; not with NCCL buckets, whose all-reduces are issued from inside backward)"""
+        if self.dp is not None and getattr(self.dp, "mode", "") == "nccl":
+            return self.net.backward()
+        with runtime.side_region():
+            self.net.backward()
 
     def _inputs(self, X, Y):
         if isinstance(X, DeviceArray) and isinstance(Y, DeviceArray):
@@ -88,7 +96,7 @@ class GraphedTrainStep:
                     if self.dp is not None:
                         self.dp.begin_step()
                     loss, _ = self.net.forward(X, Y)
-                    self.net.backward()
+                    self._backward()
                     if self.dp is None:
                         self.opt.update_weights()
                 entry = (g, loss, X, Y)
@@ -117,7 +125,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self.dp.begin_step()
             loss, _ = self.net.forward(X, Y)
-            self.net.backward()
+            self._backward()
             self.dp.finish()  # joins NCCL's stream back into the capture stream (nothing to do in p2p mode)
             self.opt.update_weights()
         return (g, loss, X, Y)
@@ -212,7 +220,8 @@ class AutoGraph:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._bwd()
+                with runtime.side_region():
+                    self._bwd()
             st["bwd"] = g
         st["bwd"].replay()
 

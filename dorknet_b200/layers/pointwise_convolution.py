@@ -118,8 +118,19 @@ class PointwiseConvLayer(Layer):
         if self._folded_bn is not None:
             return self._backward_folded(dY, N, C, H, W, F, ws, wsn, st)
         xh, xw, xs = self._xgeom  # (a compact, already subsampled operand has stride 1)
-        api.dk_pwconv_wgrad(dY.ptr, self._x.ptr, w.ptr, self._grad("weights").ptr, dbias, self._l2_strength(),
-                            N, C, xh, xw, F, xs, ws, wsn, st)
+        if runtime.side_enabled():
+            # nothing on the backward chain needs dW: inside a captured step the wgrad GEMM (and its reduce / re-pitch
+            # kernels) runs on the side stream next to the chain (runtime.side_region), on its own scratch buffer
+            dy_ptr, x_ptr, dw_ptr, l2s = dY.ptr, self._x.ptr, self._grad("weights").ptr, self._l2_strength()
+            nb = api.dk_pwconv_ws_bytes(N, C, max(H, OH * s), max(W, OW * s), F, s)
+
+            def wgrad():
+                ws2, wsn2 = runtime.side_scratch(nb)
+                api.dk_pwconv_wgrad(dy_ptr, x_ptr, w.ptr, dw_ptr, dbias, l2s, N, C, xh, xw, F, xs, ws2, wsn2, runtime.stream())
+            runtime.side_launch(wgrad)
+        else:
+            api.dk_pwconv_wgrad(dY.ptr, self._x.ptr, w.ptr, self._grad("weights").ptr, dbias, self._l2_strength(),
+                                N, C, xh, xw, F, xs, ws, wsn, st)
         # zero-stuffed dx of shape (OH*s, OW*s): for odd H this is NOT the input shape
         # (pointwise_convolution.py:68-72) -- reproduced on purpose
         dx = self._buf("dx", (N, C, OH * s, OW * s))
