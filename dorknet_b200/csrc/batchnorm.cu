@@ -528,9 +528,11 @@ static BnWs bn_ws_carve(void *ws, int C) {
 }
 
 // choose the number of splits per channel: ~4 CTAs per SM in total, each split a multiple of 4 elements
-static void bn_plan(int N, int C, int HW, int *S, int64_t *per_split) {
+int g_bn_split_ctas_per_sm = 0;  // split-kernel CTAs per SM the plan aims for (0 = default; dk_tc_debug_set key 24)
+static void bn_plan(int N, int C, int HW, int *S, int64_t *per_split, int ctas_per_sm = 8) {
     const int64_t total = (int64_t)N * HW;
-    int64_t want = ceil_div((int64_t)sm_count() * 8, C);  // 8 resident CTAs of 256 threads per SM
+    if (g_bn_split_ctas_per_sm > 0) ctas_per_sm = g_bn_split_ctas_per_sm;
+    int64_t want = ceil_div((int64_t)sm_count() * ctas_per_sm, C);  // resident CTAs of 256 threads per SM
     const int64_t max_by_work = ceil_div(total, 16 * BN_THREADS);  // at least four float4 per thread
     if (want > max_by_work) want = max_by_work;
     if (want > BN_MAX_SPLITS) want = BN_MAX_SPLITS;
@@ -554,7 +556,9 @@ static int bn_check(const char *who, int N, int C, int HW, const void *ws, size_
 static int launch_stats(const float *x, int N, int C, int HW, void *ws, const BnFinalize &fin, cudaStream_t st) {
     int S;
     int64_t per;
-    bn_plan(N, C, HW, &S, &per);
+    // statistics pass: 4 CTAs per SM (tests/bn_stats_sweep.py, batch 64, us at 2 / 4 / 8 / 16 per SM: conv0_bn 77 / 49.8 / 57.7 /
+    // 52.3; 56x56x64 27.1 / 21.3 / 24.8 / 31.6; 28x28x128 15.9 / 14.8 / 17.1 / 20.5)
+    bn_plan(N, C, HW, &S, &per, 4);
     BnWs w = bn_ws_carve(ws, C);
     dim3 grid(C, S);
     const bool vec = (HW % 4 == 0) && aligned16(x);
