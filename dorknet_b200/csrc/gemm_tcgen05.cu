@@ -263,7 +263,9 @@ template <class G> struct is_vec16<G, decltype((void)G::kVec16)> { static conste
 constexpr int TC_GATHER_THREADS = TC_THREADS + 128;
 
 template <class AG, class BG>
-__global__ void __launch_bounds__((AG::kGather || BG::kGather) ? TC_GATHER_THREADS : TC_THREADS, 1)
+// (min 2 CTAs per SM for the all-TMA variant: tc_launch runs forward / dgrad two per SM, which needs <= 168 registers -- a
+// resident-weights experiment pushed it to 172 and silently cost those GEMMs 25 -> 17.6 us's worth of overlap)
+__global__ void __launch_bounds__((AG::kGather || BG::kGather) ? TC_GATHER_THREADS : TC_THREADS, (AG::kGather || BG::kGather) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmX, const TcParams p, const AG ag, const BG bg) {
     constexpr bool kAnyGather = AG::kGather || BG::kGather;
