@@ -618,3 +618,37 @@ def test_depthwise_batchnorm_pointwise_unit_fused_vs_oracle(O, case, backend):
         assert_close(dw.forward(X).get(), Do, FP32, "plain deferred forward")
     finally:
         api.dk_set_gemm_backend(0)
+
+
+@pytest.mark.parametrize("case", [(2, 8, 12, 12, 3, 1, 1, 1), (3, 6, 15, 17, 3, 2, 1, 0), (2, 4, 9, 9, 5, 1, 2, 1)])
+def test_depthwise_input_transform_on_load_vs_oracle(O, case):
+    """dk_dwconv_fwd / dk_dwconv_bwd with in_scale / in_shift / in_relu (include/dorknet_b200.h: the input is read as
+    relu?(x*scale[c] + shift[c]), a producer's deferred BatchNorm(+ReLU) applied on load; zero padding AFTER it) against the
+    oracle run on the transformed tensor: forward, dX (gradient with respect to the TRANSFORMED input), dW."""
+    from dorknet_b200 import api, runtime
+    from dorknet_b200.array import asarray, empty
+    N, C, H, W, k, s, p, relu = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    Wd = rng.standard_normal((C, k, k)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    shift = rng.uniform(-0.5, 0.5, C).astype(np.float32)
+    Xt = X * scale[None, :, None, None] + shift[None, :, None, None]
+    if relu:
+        Xt = np.maximum(Xt, 0)
+    Xt = Xt.astype(np.float32)
+    Yo, cache = O.depthwise_fwd(Xt, Wd, None, s, p)
+    x, w, sc, sh = asarray(X), asarray(Wd), asarray(scale), asarray(shift)
+    y = empty(Yo.shape)
+    st = runtime.stream()
+    api.dk_dwconv_fwd(x.ptr, w.ptr, None, y.ptr, sc.ptr, sh.ptr, relu, N, C, H, W, k, k, s, p, st)
+    assert_close(y.get(), Yo, FP32, "Y")
+    dY = rng.standard_normal(Yo.shape).astype(np.float32)
+    dXo, g = O.depthwise_bwd(dY, Wd, cache, s, p)
+    dy, dx, dw = asarray(dY), empty(X.shape), empty(Wd.shape)
+    nb = api.dk_dwconv_ws_bytes(N, C, H, W, k, k, s, p)
+    ws, wsn = runtime.scratch(nb)
+    api.dk_dwconv_bwd(dy.ptr, x.ptr, w.ptr, dx.ptr, dw.ptr, None, sc.ptr, sh.ptr, relu, None, 0.0, N, C, H, W, k, k, s, p,
+                      ws, wsn, st)
+    assert_close(dx.get(), dXo, FP32_RED, "dX")
+    assert_close(dw.get(), g["weights"], FP32_RED, "dW")
