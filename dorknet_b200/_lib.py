@@ -53,6 +53,11 @@ PROTOS = {
     "dk_pwconv_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P, Z, P]),
     "dk_pwconv_dgrad": (I, [P, P, P, I, I, I, I, I, I, P, Z, P]),
     "dk_pwconv_wgrad": (I, [P, P, P, P, P, F, I, I, I, I, I, I, P, Z, P]),
+    "dk_pw_pack_bytes": (Z, [I, I, I, I, I]),
+    "dk_pw_pack": (I, [P, P, I, I, I, I, I, P]),
+    "dk_pwconv_fwd_packed": (I, [P, P, P, P, I, I, I, I, I, P, Z, P]),
+    "dk_pwconv_dgrad_packed": (I, [P, P, P, I, I, I, I, I, I, P, Z, P]),
+    "dk_pwconv_wgrad_packed": (I, [P, I, P, I, P, P, P, F, I, I, I, I, I, I, P, Z, P]),
     "dk_bn_fold_fwd": (I, [P, P, P, P, P, P, P, P, I, I, P]),
     "dk_dwconv_fwd_bn_ws_bytes": (Z, [I, I, I, I, I, I, I, I]),
     "dk_dwconv_fwd_bn": (I, [P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P, I, F, F, P, P, P, P, P, P, Z, P]),
@@ -86,7 +91,7 @@ PROTOS = {
 
 # value-returning (not status) functions
 _NO_CHECK = {"dk_version", "dk_last_error", "dk_sm_count", "dk_kernel_launches", "dk_gemm_call_counts", "dk_get_gemm_backend", "dk_bn_ws_bytes",
-             "dk_dwconv_ws_bytes", "dk_dwconv_fwd_bn_ws_bytes", "dk_conv2d_ws_bytes", "dk_pwconv_ws_bytes", "dk_dense_ws_bytes"}
+             "dk_dwconv_ws_bytes", "dk_dwconv_fwd_bn_ws_bytes", "dk_pw_pack_bytes", "dk_conv2d_ws_bytes", "dk_pwconv_ws_bytes", "dk_dense_ws_bytes"}
 
 
 class OptTensor(ctypes.Structure):

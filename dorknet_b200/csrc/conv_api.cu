@@ -143,6 +143,58 @@ int dk_pwconv_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     return dk_conv2d_wgrad(dy, x, w, dw, dbias, l2, N, C, H, W, F, 1, 1, stride, 0, ws, ws_bytes, stream);
 }
 
+/* ---- pointwise operands re-pitched once (gemm_tcgen05.cu: tc_pw_pack*) -------------------------------------------------- */
+size_t dk_pw_pack_bytes(int N, int C, int H, int W, int stride) {
+    return gemm_backend() == 0 ? tc_pw_pack_bytes(N, C, H, W, stride) : 0;
+}
+
+int dk_pw_pack(const float *x, float *packed, int N, int C, int H, int W, int stride, dk_stream_t stream) {
+    DK_REQUIRE(x && packed && N > 0 && C > 0 && H > 0 && W > 0 && stride > 0, "dk_pw_pack: bad arguments");
+    const int rc = tc_pw_pack(x, packed, N, C, H, W, stride, as_stream(stream));
+    DK_REQUIRE(rc != DK_ERR_UNSUPPORTED, "dk_pw_pack: this shape needs no packing (dk_pw_pack_bytes returns 0) or `packed` is misaligned");
+    return rc;
+}
+
+int dk_pwconv_fwd_packed(const float *x_packed, const float *w, const float *bias, float *y, int N, int C, int OH, int OW, int F,
+                         void *ws, size_t ws_bytes, dk_stream_t stream) {
+    int rc = conv_check("dk_pwconv_fwd_packed", N, C, OH, OW, F, 1, 1, 1, 0);
+    if (rc) return rc;
+    DK_REQUIRE(x_packed && w && y, "dk_pwconv_fwd_packed: NULL pointer");
+    rc = tc_pw_fwd_packed(x_packed, w, bias, y, N, C, OH, OW, F, ws, ws_bytes, as_stream(stream));
+    DK_REQUIRE(rc != DK_ERR_UNSUPPORTED, "dk_pwconv_fwd_packed: tensor-core path unavailable for this call");
+    if (rc == DK_OK) ++g_tc_calls;
+    return rc;
+}
+
+int dk_pwconv_dgrad_packed(const float *dy_packed, const float *w, float *dx, int N, int C, int OH, int OW, int F, int stride,
+                           void *ws, size_t ws_bytes, dk_stream_t stream) {
+    int rc = conv_check("dk_pwconv_dgrad_packed", N, C, OH * stride, OW * stride, F, 1, 1, stride, 0);
+    if (rc) return rc;
+    DK_REQUIRE(dy_packed && w && dx, "dk_pwconv_dgrad_packed: NULL pointer");
+    rc = tc_pw_dgrad_packed(dy_packed, w, dx, N, C, OH, OW, F, stride, ws, ws_bytes, as_stream(stream));
+    DK_REQUIRE(rc != DK_ERR_UNSUPPORTED, "dk_pwconv_dgrad_packed: tensor-core path unavailable for this call");
+    if (rc == DK_OK) ++g_tc_calls;
+    return rc;
+}
+
+int dk_pwconv_wgrad_packed(const float *dy, int dy_is_packed, const float *x, int x_is_packed, const float *w, float *dw,
+                           float *dbias, float l2, int N, int C, int H, int W, int F, int stride, void *ws, size_t ws_bytes,
+                           dk_stream_t stream) {
+    int rc = conv_check("dk_pwconv_wgrad_packed", N, C, H, W, F, 1, 1, stride, 0);
+    if (rc) return rc;
+    DK_REQUIRE(dy && x && w && dw, "dk_pwconv_wgrad_packed: NULL pointer");
+    DK_REQUIRE(dbias == nullptr || !dy_is_packed, "dk_pwconv_wgrad_packed: the bias gradient needs the unpacked dY");
+    const int OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+    if (dbias) {
+        rc = dk_bias_grad(dy, dbias, N, F, OH * OW, nullptr, 0, stream);
+        if (rc) return rc;
+    }
+    rc = tc_pw_wgrad_packed(dy, dy_is_packed, x, x_is_packed, w, dw, l2, N, C, H, W, F, stride, ws, ws_bytes, as_stream(stream));
+    DK_REQUIRE(rc != DK_ERR_UNSUPPORTED, "dk_pwconv_wgrad_packed: tensor-core path unavailable for this call");
+    if (rc == DK_OK) ++g_tc_calls;
+    return rc;
+}
+
 size_t dk_dense_ws_bytes(int B, int in_dim, int out_dim) {
     if (B <= 0 || in_dim <= 0 || out_dim <= 0) return 0;
     return max_sz(simt_dense_ws_bytes(B, in_dim, out_dim), tc_dense_ws_bytes(B, in_dim, out_dim)) + 256;

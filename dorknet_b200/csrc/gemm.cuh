@@ -35,6 +35,14 @@ int tc_dense_bwd(const float *dy, const float *x, const float *w, float *dx, flo
 size_t tc_conv_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
 int tc_pw_dgrad_affine(const float *dy, const float *w, const float *x, const float *cb, const float *cd, float *dx, int N,
                        int C, int OH, int OW, int F, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_pw_pack_bytes(int N, int C, int H, int W, int s);
+int tc_pw_pack(const float *x, float *packed, int N, int C, int H, int W, int s, cudaStream_t st);
+int tc_pw_fwd_packed(const float *xp, const float *w, const float *bias, float *y, int N, int C, int OH, int OW, int F, void *ws,
+                     size_t ws_bytes, cudaStream_t st);
+int tc_pw_dgrad_packed(const float *dyp, const float *w, float *dx, int N, int C, int OH, int OW, int F, int s, void *ws,
+                       size_t ws_bytes, cudaStream_t st);
+int tc_pw_wgrad_packed(const float *dy, int dy_packed, const float *x, int x_packed, const float *w, float *dw, float l2, int N,
+                       int C, int H, int W, int F, int s, void *ws, size_t ws_bytes, cudaStream_t st);
 int affine_add_launch(float *out, const float *x, const float *cb, const float *cd, int N, int C, int P, cudaStream_t st);  // bn_fold.cu
 size_t tc_dense_ws_bytes(int B, int in_dim, int out_dim);
 size_t tc_conv_mat_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);

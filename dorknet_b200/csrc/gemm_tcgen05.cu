@@ -1130,7 +1130,7 @@ static int pw_fwd(const float *x, const float *w, const float *bias, float *y, i
 
 static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, int OH, int OW, int F, int s, void *ws,
                     size_t ws_bytes, cudaStream_t st, const float *epi_x = nullptr, const float *epi_cb = nullptr,
-                    const float *epi_cd = nullptr) {
+                    const float *epi_cd = nullptr, int64_t dy_pitch = 0) {
     const int64_t P = (int64_t)OH * OW;
     if (!tma_ok(w, C) || !dims_ok(P, P * s * s)) return DK_ERR_UNSUPPORTED;
     TcParams q = {};
@@ -1147,6 +1147,11 @@ static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
     CUtensorMap ta = {}, tb;
     int rc = make_map(&tb, w, C, F, 1, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);  // B(k=f, n=c) = W[f][c]: n contiguous
     if (rc) return rc;
+    if (dy_pitch > 0) {  // dY already re-pitched by the caller (dk_pw_pack): [N][F][dy_pitch]
+        rc = make_map(&ta, dy, dy_pitch, F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
+        if (rc) return rc;
+        return tc_launch(ta, tb, q, NoGather{}, NoGather{}, st);
+    }
     if (tma_ok(dy, P)) {
         rc = make_map(&ta, dy, P, F, N, 32, TC_BK, (CUtensorMapSwizzle)g_mn_swizzle);
         if (rc) return rc;
@@ -1177,7 +1182,7 @@ static int pw_dgrad(const float *dy, const float *w, float *dx, int N, int C, in
 }
 
 static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
-                    int s, void *ws, size_t ws_bytes, cudaStream_t st, int64_t x_pitch = 0) {
+                    int s, void *ws, size_t ws_bytes, cudaStream_t st, int64_t x_pitch = 0, int64_t dy_pitch = 0) {
     const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
     const int64_t P = (int64_t)OH * OW;
     if (!dims_ok(P, (int64_t)H * W)) return DK_ERR_UNSUPPORTED;
@@ -1204,7 +1209,7 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
             q.stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
         }
     }
-    bool a_tma = tma_ok(dy, P), b_tma = x_pitch > 0 || ((s == 1) && tma_ok(x, P));
+    bool a_tma = dy_pitch > 0 || tma_ok(dy, P), b_tma = x_pitch > 0 || ((s == 1) && tma_ok(x, P));
     const bool hybrid = g_hybrid_wgrad && a_tma && b_tma && x_pitch == 0;
     if (a_tma && b_tma && !hybrid) {
         // wide pipeline items for long planes: 4 (or 2) consecutive k-blocks per item, if at least two stages still fit and
@@ -1235,7 +1240,7 @@ static int pw_wgrad(const float *dy, const float *x, const float *w, float *dw, 
     q.epi = 1; q.out = reinterpret_cast<float *>(ws); q.bias = nullptr; q.ldo = 0;
     CUtensorMap ta = {}, tb = {};
     int rc = DK_OK;
-    int64_t pa = P, pb = x_pitch > 0 ? x_pitch : P;  // row pitches of the operands the maps describe
+    int64_t pa = dy_pitch > 0 ? dy_pitch : P, pb = x_pitch > 0 ? x_pitch : P;  // row pitches of the operands the maps describe
     {
         void *rest = reinterpret_cast<char *>(ws) + need;
         size_t rest_bytes = ws_bytes - need;
@@ -1541,6 +1546,44 @@ int tc_conv_dgrad(const float *dy, const float *w, float *dx, int N, int C, int 
         if (rc != DK_ERR_UNSUPPORTED) return rc;
     }
     return cv_dgrad(dy, w, dx, N, mk_geom(C, H, W, F, kh, kw, s, p), st);
+}
+
+// ---- operands re-pitched ONCE by the caller (dk_pw_pack) ---------------------------------------------------------------
+// Planes whose pitch is not a multiple of 16 bytes (7x7) and small strided planes are copied into a padded [rows][Pp] layout
+// before they can go through TMA.  Inside the three entry points that copy happens per call: the same x twice per step
+// (forward, wgrad), the same dY twice (dgrad, wgrad).  A caller that keeps the packed copies passes them to the *_packed
+// variants instead: half the re-pitch launches and traffic of those layers.
+size_t tc_pw_pack_bytes(int N, int C, int H, int W, int s) {
+    if (!g_tc_ready || N <= 0 || C <= 0 || s < 1) return 0;
+    const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
+    const int64_t P = (int64_t)OH * OW;
+    const bool want = s == 1 ? ((g_repack_mask & 1) && (P % 4) != 0 && P <= 4 * TC_REPACK_MAX_P)
+                             : ((g_repack_mask & 2) && P <= TC_REPACK_MAX_P);
+    return want ? repack_bytes((int64_t)N * C, P) : 0;
+}
+int tc_pw_pack(const float *x, float *packed, int N, int C, int H, int W, int s, cudaStream_t st) {
+    if (tc_pw_pack_bytes(N, C, H, W, s) == 0 || !aligned16(packed)) return DK_ERR_UNSUPPORTED;
+    const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
+    return repack_launch(x, packed, (int64_t)N * C, H, W, OW, s, (int64_t)OH * OW, st);
+}
+int tc_pw_fwd_packed(const float *xp, const float *w, const float *bias, float *y, int N, int C, int OH, int OW, int F, void *ws,
+                     size_t ws_bytes, cudaStream_t st) {
+    if (!g_tc_ready || (g_tc_disable_mask & 1)) return DK_ERR_UNSUPPORTED;
+    return pw_fwd(xp, w, bias, y, N, C, OH, OW, F, 1, ws, ws_bytes, st, repack_pitch((int64_t)OH * OW));
+}
+int tc_pw_dgrad_packed(const float *dyp, const float *w, float *dx, int N, int C, int OH, int OW, int F, int s, void *ws,
+                       size_t ws_bytes, cudaStream_t st) {
+    if (!g_tc_ready || (g_tc_disable_mask & 2)) return DK_ERR_UNSUPPORTED;
+    return pw_dgrad(dyp, w, dx, N, C, OH, OW, F, s, ws, ws_bytes, st, nullptr, nullptr, nullptr, repack_pitch((int64_t)OH * OW));
+}
+// dy_packed / x_packed: which of the two operands are packed copies ([N][F][Pp] / [N][C][Pp], stride already applied)
+int tc_pw_wgrad_packed(const float *dy, int dy_packed, const float *x, int x_packed, const float *w, float *dw, float l2, int N,
+                       int C, int H, int W, int F, int s, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!g_tc_ready || (g_tc_disable_mask & 4)) return DK_ERR_UNSUPPORTED;
+    const int OH = (H - 1) / s + 1, OW = (W - 1) / s + 1;
+    const int64_t Pp = repack_pitch((int64_t)OH * OW);
+    if (x_packed) return pw_wgrad(dy, x, w, dw, l2, N, C, OH, OW, F, 1, ws, ws_bytes, st, Pp, dy_packed ? Pp : 0);
+    return pw_wgrad(dy, x, w, dw, l2, N, C, H, W, F, s, ws, ws_bytes, st, 0, dy_packed ? Pp : 0);
 }
 
 // pointwise dgrad (stride 1) whose epilogue adds cb[c]*x + cd[c]: the backward of the BatchNorm folded into this layer

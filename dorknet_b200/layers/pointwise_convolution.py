@@ -50,6 +50,8 @@ class PointwiseConvLayer(Layer):
         # BatchNorm's statistics ride on the depthwise kernel before it (always a win); "always": whenever possible; False: never
         self.fold_bn_input = {"0": False, "always": "always"}.get(os.environ.get("DK_FOLD_BN", "1"), True)
         self.trust_zero_sum = os.environ.get("DK_FOLD_ZEROSUM", "1") != "0"  # skip the channel sums of a BatchNorm's input gradient
+        self.pack_operands = os.environ.get("DK_PW_PACK", "1") != "0"  # keep re-pitched copies of 7x7 / small strided operands
+        self._x_pack = None
         self._folded_bn = None
 
     def __repr__(self):
@@ -102,6 +104,19 @@ class PointwiseConvLayer(Layer):
             self._x, self._xgeom = X, (H, W, s)
         xh, xw, xs = self._xgeom
         ws, wsn = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, xh, xw, self.num_filters, xs))
+        self._x_pack = None
+        # (the packed entry points are tensor-core only: they need the weight rows, C floats, to be TMA-addressable)
+        pb = api.dk_pw_pack_bytes(N, C, xh, xw, xs) if (self.pack_operands and C % 4 == 0) else 0
+        if pb:
+            # 7x7 planes / small strided planes: TMA needs a re-pitched copy.  It is made once here and kept for the wgrad
+            # GEMM of this step (dk_pwconv_fwd / wgrad would each make their own in the workspace)
+            xp = self._buf("x_pack", ((pb + 3) // 4,))
+            api.dk_pw_pack(self._x.ptr, xp.ptr, N, C, xh, xw, xs, runtime.stream())
+            api.dk_pwconv_fwd_packed(xp.ptr, self._param("weights").ptr, bias, y.ptr, N, C, OH, OW, self.num_filters,
+                                     ws, wsn, runtime.stream())
+            if not test_mode:
+                self._x_pack = xp
+            return y
         api.dk_pwconv_fwd(self._x.ptr, self._param("weights").ptr, bias, y.ptr, N, C, xh, xw, self.num_filters, xs,
                           ws, wsn, runtime.stream())
         return y
@@ -118,6 +133,7 @@ class PointwiseConvLayer(Layer):
         if self._folded_bn is not None:
             return self._backward_folded(dY, N, C, H, W, F, ws, wsn, st)
         xh, xw, xs = self._xgeom  # (a compact, already subsampled operand has stride 1)
+        dyp = None  # re-pitched copy of dY, when this shape needs one
         if runtime.side_enabled():
             # nothing on the backward chain needs dW: inside a captured step the wgrad GEMM (and its reduce / re-pitch
             # kernels) runs on the side stream next to the chain (runtime.side_region), on its own scratch buffer
@@ -129,8 +145,29 @@ class PointwiseConvLayer(Layer):
                 api.dk_pwconv_wgrad(dy_ptr, x_ptr, w.ptr, dw_ptr, dbias, l2s, N, C, xh, xw, F, xs, ws2, wsn2, runtime.stream())
             runtime.side_launch(wgrad)
         else:
-            api.dk_pwconv_wgrad(dY.ptr, self._x.ptr, w.ptr, self._grad("weights").ptr, dbias, self._l2_strength(),
-                                N, C, xh, xw, F, xs, ws, wsn, st)
+            # dY planes that TMA cannot take as they lie (7x7) are re-pitched once for wgrad AND dgrad; x may already have
+            # its packed copy from forward
+            gb = api.dk_pw_pack_bytes(N, F, OH, OW, 1) if (self.pack_operands and C % 4 == 0) else 0
+            if gb:
+                dyp = self._buf("dy_pack", ((gb + 3) // 4,))
+                api.dk_pw_pack(dY.ptr, dyp.ptr, N, F, OH, OW, 1, st)
+            xpk = getattr(self, "_x_pack", None)
+            if dyp is not None or xpk is not None:
+                if dbias is not None:
+                    api.dk_bias_grad(dY.ptr, dbias, N, F, OH * OW, None, 0, st)
+                api.dk_pwconv_wgrad_packed(dyp.ptr if dyp is not None else dY.ptr, int(dyp is not None),
+                                           xpk.ptr if xpk is not None else self._x.ptr, int(xpk is not None), w.ptr,
+                                           self._grad("weights").ptr, None, self._l2_strength(), N, C, xh, xw, F, xs,
+                                           ws, wsn, st)
+            else:
+                api.dk_pwconv_wgrad(dY.ptr, self._x.ptr, w.ptr, self._grad("weights").ptr, dbias, self._l2_strength(),
+                                    N, C, xh, xw, F, xs, ws, wsn, st)
+
+        def dgrad(out, stride, ws_, wsn_):
+            if dyp is not None:
+                api.dk_pwconv_dgrad_packed(dyp.ptr, w.ptr, out.ptr, N, C, OH, OW, F, stride, ws_, wsn_, runtime.stream())
+            else:
+                api.dk_pwconv_dgrad(dY.ptr, w.ptr, out.ptr, N, C, OH, OW, F, stride, ws_, wsn_, runtime.stream())
         # zero-stuffed dx of shape (OH*s, OW*s): for odd H this is NOT the input shape
         # (pointwise_convolution.py:68-72) -- reproduced on purpose
         dx = self._buf("dx", (N, C, OH * s, OW * s))
@@ -139,15 +176,15 @@ class PointwiseConvLayer(Layer):
             # form; anybody else reads the zero-stuffed tensor as before
             def full():
                 ws2, wsn2 = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, max(H, OH * s), max(W, OW * s), F, s))
-                api.dk_pwconv_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, OH, OW, F, s, ws2, wsn2, runtime.stream())
+                dgrad(dx, s, ws2, wsn2)
 
             def compact():
                 dxs = self._buf("dx_sub", (N, C, OH, OW))
                 ws2, wsn2 = runtime.scratch(api.dk_pwconv_ws_bytes(N, C, OH, OW, F, 1))
-                api.dk_pwconv_dgrad(dY.ptr, w.ptr, dxs.ptr, N, C, OH, OW, F, 1, ws2, wsn2, runtime.stream())
+                dgrad(dxs, 1, ws2, wsn2)
                 return dxs
             return LazyStridedGrad(dx, full, s, compact)
-        api.dk_pwconv_dgrad(dY.ptr, w.ptr, dx.ptr, N, C, OH, OW, F, s, ws, wsn, st)
+        dgrad(dx, s, ws, wsn)
         return dx
 
     def _backward_folded(self, dY, N, C, H, W, F, ws, wsn, st):

@@ -179,6 +179,23 @@ int dk_pwconv_wgrad(const float *dy, const float *x, const float *w, float *dw, 
                     int N, int C, int H, int W, int F, int stride,
                     void *ws, size_t ws_bytes, dk_stream_t stream);
 
+/* Operands re-pitched once.  Planes whose pitch is not a multiple of 16 bytes (7x7) and small strided planes cannot go
+ * through TMA as they lie; dk_pwconv_fwd / dgrad / wgrad copy them into a padded layout in their workspace on every call --
+ * the same x twice per training step (forward, wgrad), the same dY twice (dgrad, wgrad).  A caller that keeps the copies
+ * avoids half of that: dk_pw_pack_bytes (0 = this shape needs no packing; otherwise the buffer size) and dk_pw_pack produce
+ * [N][C][round_up(OH*OW, 4)] with the stride already applied and zero padding; the *_packed entry points take such buffers
+ * (wgrad: flags say which of dy / x is a packed copy; dbias needs the unpacked dY).  Tensor-core backend only: they fail
+ * (no fallback -- the unpacked tensor is not at hand) when C % 4 != 0 or the weights are not 16-byte aligned. */
+size_t dk_pw_pack_bytes(int N, int C, int H, int W, int stride);
+int dk_pw_pack(const float *x, float *packed, int N, int C, int H, int W, int stride, dk_stream_t stream);
+int dk_pwconv_fwd_packed(const float *x_packed, const float *w, const float *bias, float *y, int N, int C, int OH, int OW, int F,
+                         void *ws, size_t ws_bytes, dk_stream_t stream);
+int dk_pwconv_dgrad_packed(const float *dy_packed, const float *w, float *dx, int N, int C, int OH, int OW, int F, int stride,
+                           void *ws, size_t ws_bytes, dk_stream_t stream);
+int dk_pwconv_wgrad_packed(const float *dy, int dy_is_packed, const float *x, int x_is_packed, const float *w, float *dw,
+                           float *dbias, float l2, int N, int C, int H, int W, int F, int stride, void *ws, size_t ws_bytes,
+                           dk_stream_t stream);
+
 /* ---- BatchNorm (no ReLU) -> PointwiseConvLayer, folded (training): layers/batch_norm.py:54-174 applied to the input of
  * layers/pointwise_convolution.py:46-75.  Between the two layers there is no non-linearity, so with the batch statistics
  * known (dk_bn_fwd_train with y = NULL) the normalisation is absorbed by the GEMM and its backward by the GEMM's epilogue;

@@ -652,3 +652,32 @@ def test_depthwise_input_transform_on_load_vs_oracle(O, case):
                       ws, wsn, st)
     assert_close(dx.get(), dXo, FP32_RED, "dX")
     assert_close(dw.get(), g["weights"], FP32_RED, "dW")
+
+
+@pytest.mark.parametrize("case", [(6, 512, 7, 7, 512, 1), (4, 256, 14, 14, 512, 2), (3, 64, 56, 56, 128, 2), (5, 24, 7, 7, 40, 1)])
+def test_pointwise_packed_operands_match_unpacked(O, case):
+    """PointwiseConvLayer keeping ONE re-pitched copy of x (forward + wgrad) and of dY (dgrad + wgrad) through dk_pw_pack /
+    dk_pwconv_*_packed gives the results of the entry points that re-pitch per call (same operands and products; the split-K
+    plan of a strided wgrad may differ, so equal to fp32 summation order: 1e-5), and both match the oracle."""
+    from dorknet_b200.layers.pointwise_convolution import PointwiseConvLayer
+    N, C, H, W, F, s = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    X = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    Wt = (rng.standard_normal((F, C)) / np.sqrt(C)).astype(np.float32)
+    Yo, cache = O.pointwise_fwd(X, Wt, None, s)
+    dY = rng.standard_normal(Yo.shape).astype(np.float32)
+    dXo, g = O.pointwise_bwd(dY, Wt, cache, s)
+    res = []
+    for pack in (True, False):
+        pw = PointwiseConvLayer("p", stride=s, filter_block_shape=(F, C), with_bias=False)
+        pw.learned_params["weights"] = Wt
+        pw.pack_operands = pack
+        y = pw.forward(X).get().copy()
+        assert (pw._x_pack is not None) == pack
+        dx = pw.backward(dY).get().copy()
+        res.append((y, dx, pw.grads["weights"].get().copy()))
+        assert_close(y, Yo, GEMM, "Y")
+        assert_close(dx, dXo, GEMM, "dX")
+        assert_close(res[-1][2], g["weights"], GEMM_W, "dW")
+    for a, b, what in zip(res[0], res[1], ("Y", "dX", "dW")):
+        assert_close(a, b, FP32, what + " packed vs unpacked")
