@@ -1,0 +1,8 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r03m_tests.log 2>&1; tail -3 gpurun_out/r03m_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py --per-kernel gpurun_out/r03m_r18_perkernel.json > gpurun_out/r03m_bench.json 2> gpurun_out/r03m_bench.err; tail -2 gpurun_out/r03m_bench.err; cut -c1-200 gpurun_out/r03m_bench.json
+timeout 300 python bench.py --workload mnist --no-cpu-baseline > gpurun_out/r03m_mnist_bench.json 2>/dev/null; cut -c1-200 gpurun_out/r03m_mnist_bench.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r03m_launches.csv python bench.py --no-cpu-baseline --no-e2e --no-variants --no-graph --steps 3 --warmup 3 > gpurun_out/r03m_ncu.log 2>&1; tail -c 150 gpurun_out/r03m_ncu.log
