@@ -334,6 +334,19 @@ def autograph_check(M, steps=6):
                 test_scores = sc.get().copy()
         weights = [l.learned_params[k].get().copy() for l in workloads.iter_param_layers(net) for k in sorted(l.learned_params)]
         results.append((float(running), test_scores, weights, ag.num_graphs if ag else 0))
+    # and the container's own checkpoint round trip on top of the CUDA layers (feed_forward_network.py:90-139; `h5py` is
+    # dorknet_b200.minih5 under dropin.install() when the real package is missing): save, rebuild from JSON + HDF5, same scores
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        h5, js = os.path.join(tmp, "net.h5"), os.path.join(tmp, "net.json")
+        net.save_weights_to_h5(h5)
+        net.save_layer_structure_to_json(js)
+        again = M.FeedForwardNetwork("empty")
+        again.load_network_from_json_and_h5(js, h5)
+        _, a = net.forward(batches[0][0], None, test_mode=True)
+        a = a.get().copy()
+        _, b = again.forward(batches[0][0], None, test_mode=True)
+        assert np.array_equal(a, b.get()), "checkpoint round trip changed the test-mode scores"
     (r0, t0, w0, _), (r1, t1, w1, ng) = results
     assert ng >= 3, "no CUDA graph was captured (%d)" % ng
     assert r0 == r1, (r0, r1)
