@@ -456,6 +456,8 @@ struct Cw2Params {
     int bnC, a_rows, csegs, chunks, rc;   // rc = X rows per work unit, chunks = row chunks per strip
     int units, units_per_cta;
     int ring;                            // dY ring slots (+1 mirror)
+    int nb;                              // shifted-tile buffers (2 .. 4): how far the shifter warps may run ahead of the MMAs
+    int raw_stages;                      // raw X row boxes in flight
     int npairs;
     uint32_t tmem_cols, acc_stride;      // acc_stride = kw * bnC columns per row-tap pair
     float *partial;                      // [CTAs][F][C][kh][kw]
@@ -472,7 +474,8 @@ __device__ __forceinline__ void cw2_store_shifted(const float (&v)[24], uint8_t 
 
 constexpr int CW2_RAW_W = 40;  // raw X box: 4 halo pixels left, 32, 4 right
 constexpr uint32_t CW2_DY_SLOT = 8192;
-constexpr int CW2_RAW_STAGES = 6;   // raw X row boxes in flight (the shifted tiles behind them are double-buffered)
+constexpr int CW2_RAW_STAGES = 6;   // most raw X row boxes in flight (p.raw_stages)
+constexpr int CW2_NB_MAX = 4;       // most shifted-tile buffers (p.nb)
 
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmXR, const Cw2Params p) {
@@ -480,18 +483,18 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ring_base = smem_base;                                     // (ring + 1) x 8 KB
     const uint32_t b_tile = (uint32_t)(p.kw * p.bnC) * 128u;                  // kw shifted tiles of bnC rows
-    const uint32_t b_base = ring_base + (uint32_t)(p.ring + 1) * CW2_DY_SLOT;  // 2 x b_tile
+    const uint32_t b_base = ring_base + (uint32_t)(p.ring + 1) * CW2_DY_SLOT;  // p.nb x b_tile
     const uint32_t raw_bytes = (uint32_t)p.bnC * CW2_RAW_W * 4u;
-    const uint32_t raw_base = b_base + 2u * b_tile;                           // CW2_RAW_STAGES x raw box
-    const uint32_t bar_base = (raw_base + (uint32_t)CW2_RAW_STAGES * raw_bytes + 15u) & ~15u;
+    const uint32_t raw_base = b_base + (uint32_t)p.nb * b_tile;               // p.raw_stages x raw box
+    const uint32_t bar_base = (raw_base + (uint32_t)p.raw_stages * raw_bytes + 15u) & ~15u;
     auto dyfull = [&](int s) { return bar_base + 8u * s; };
     auto dyempty = [&](int s) { return bar_base + 8u * (16 + s); };
     auto rawfull = [&](int s) { return bar_base + 8u * (32 + s); };
     auto rawempty = [&](int s) { return bar_base + 8u * (40 + s); };
     auto bfull = [&](int s) { return bar_base + 8u * (48 + s); };
-    auto bempty = [&](int s) { return bar_base + 8u * (50 + s); };
-    const uint32_t tfull_bar = bar_base + 8u * 52;
-    const uint32_t tmem_slot = bar_base + 8u * 53;
+    auto bempty = [&](int s) { return bar_base + 8u * (52 + s); };
+    const uint32_t tfull_bar = bar_base + 8u * 56;
+    const uint32_t tmem_slot = bar_base + 8u * 57;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -501,11 +504,11 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
             mbar_init(dyfull(s), 1);
             mbar_init(dyempty(s), 1);
         }
-        for (int s = 0; s < CW2_RAW_STAGES; ++s) {
+        for (int s = 0; s < p.raw_stages; ++s) {
             mbar_init(rawfull(s), 1);
             mbar_init(rawempty(s), 4);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < p.nb; ++s) {
             mbar_init(bfull(s), 4);
             mbar_init(bempty(s), 1);
         }
@@ -548,8 +551,8 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
                     tma_load_4d(ring_base + (uint32_t)slot * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
                     if (slot == 0) tma_load_4d(ring_base + (uint32_t)p.ring * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
                     if (t >= run_in) {  // the X row of this step
-                        const int rs = xs % CW2_RAW_STAGES;
-                        mbar_wait(rawempty(rs), (((uint32_t)(xs / CW2_RAW_STAGES)) & 1u) ^ 1u);
+                        const int rs = xs % p.raw_stages;
+                        mbar_wait(rawempty(rs), (((uint32_t)(xs / p.raw_stages)) & 1u) ^ 1u);
                         mbar_expect_tx(rawfull(rs), raw_bytes);
                         tma_load_4d(raw_base + (uint32_t)rs * raw_bytes, &tmXR, rawfull(rs), c0 - 4, r_lo + (t - run_in), 0, n);
                         ++xs;
@@ -573,8 +576,8 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
                     // every dY load is waited for exactly once, in order (the run-in rows carry no step of their own)
                     mbar_wait(dyfull(L % p.ring), ((uint32_t)(L / p.ring)) & 1u);
                     if (t < run_in) continue;
-                    const int bs = xs & 1;
-                    mbar_wait(bfull(bs), ((uint32_t)(xs >> 1)) & 1u);
+                    const int bs = xs % p.nb;
+                    mbar_wait(bfull(bs), ((uint32_t)(xs / p.nb)) & 1u);
                     tc_fence_after();
                     const uint32_t sB = b_base + (uint32_t)bs * b_tile;
                     // row tap i pairs this X row with the dY row loaded i loads ago
@@ -614,9 +617,9 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
             total_steps += r_hi - r_lo;
         }
         for (int xs = 0; xs < total_steps; ++xs) {
-            const int rs = xs % CW2_RAW_STAGES, bs = xs & 1;
-            mbar_wait(rawfull(rs), ((uint32_t)(xs / CW2_RAW_STAGES)) & 1u);
-            mbar_wait(bempty(bs), (((uint32_t)(xs >> 1)) & 1u) ^ 1u);
+            const int rs = xs % p.raw_stages, bs = xs % p.nb;
+            mbar_wait(rawfull(rs), ((uint32_t)(xs / p.raw_stages)) & 1u);
+            mbar_wait(bempty(bs), (((uint32_t)(xs / p.nb)) & 1u) ^ 1u);
             if (c < p.bnC) {
                 // raw[c][16*hh .. 16*hh + 23] covers the 16 pixels of this half shifted by -4 .. +4
                 const float4 *src = reinterpret_cast<const float4 *>(smem_raw + (raw_base - smem_u32(smem_raw)) + (uint32_t)rs * raw_bytes +
@@ -900,6 +903,10 @@ conv_tma_shift_kernel(const float *__restrict__ x, float *__restrict__ xs, long 
     }
 }
 
+// shifted-tile buffers of conv_s1_wgrad2_kernel (dk_tc_debug_set key 26).  Measured at cfg2 (3x3 64 -> 64 @56x56, batch 128):
+// 188.2 / 188.1 / 188.1 us with 2 / 3 / 4 buffers -- letting the shifter run further ahead changes nothing, so the exposed
+// hand-over latency the stall samples suggested is NOT what holds the kernel at 25 % tensor pipe; 2 keeps all 6 raw stages.
+int g_cw2_nb = 2;
 int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
                    int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (s != 1 || !g_ct_ready || !g_conv_tma_enabled) return DK_ERR_UNSUPPORTED;
@@ -935,6 +942,17 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         q.acc_stride = (uint32_t)(kw * q.bnC);
         q.tmem_cols = ct_pow2_cols((uint32_t)q.npairs * q.acc_stride);
         q.ring = kh + 5 > 15 ? 15 : kh + 5;
+        // Shifted-tile buffers (g_cw2_nb): more than two let the shifter warps run further ahead of the MMAs, at the price of
+        // raw-box stages (measured: no effect, see g_cw2_nb).
+        q.nb = g_cw2_nb < 2 ? 2 : g_cw2_nb > CW2_NB_MAX ? CW2_NB_MAX : g_cw2_nb;
+        q.raw_stages = CW2_RAW_STAGES;
+        while (q.nb > 2 || q.raw_stages > 3) {
+            const size_t need = (size_t)(q.ring + 1) * CW2_DY_SLOT + (size_t)q.nb * (kw * q.bnC) * 128 +
+                                (size_t)q.raw_stages * q.bnC * CW2_RAW_W * 4 + 1024 + 16 + 8 * 64;
+            if (need <= (size_t)CT_SMEM_MAX) break;
+            if (q.raw_stages > 3) --q.raw_stages;
+            else --q.nb;
+        }
         const int taps = kh * kw;
         const size_t need = (size_t)ctas * F * C * taps * sizeof(float);
         if (ws == nullptr || ws_bytes < need + 1024) return DK_ERR_UNSUPPORTED;
@@ -948,7 +966,7 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         const uint32_t bbr[4] = {CW2_RAW_W, 1, (uint32_t)q.bnC, 1};
         rc2 = ct_map(&tr, x, 4, dbr, bbr, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc2) return rc2;
-        const size_t smem = (size_t)(q.ring + 1) * CW2_DY_SLOT + 2 * (size_t)(kw * q.bnC) * 128 + CW2_RAW_STAGES * (size_t)q.bnC * CW2_RAW_W * 4 + 1024 + 16 + 8 * 64;
+        const size_t smem = (size_t)(q.ring + 1) * CW2_DY_SLOT + (size_t)q.nb * (kw * q.bnC) * 128 + (size_t)q.raw_stages * q.bnC * CW2_RAW_W * 4 + 1024 + 16 + 8 * 64;
         if (smem > (size_t)CT_SMEM_MAX) return DK_ERR_UNSUPPORTED;
         conv_s1_wgrad2_kernel<<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
         DK_LAUNCH_CHECK();
