@@ -459,8 +459,9 @@ struct Cw2Params {
     int nb;                              // shifted-tile buffers (2 .. 4): how far the shifter warps may run ahead of the MMAs
     int raw_stages;                      // raw X row boxes in flight
     int npairs;
+    int dbg;                             // timing experiments only (results are garbage): 1 no shifting, 2 no MMAs, 4 no dY loads, 8 no X loads
     uint32_t tmem_cols, acc_stride;      // acc_stride = kw * bnC columns per row-tap pair
-    float *partial;                      // [CTAs][F][C][kh][kw]
+    float *partial;                      // [CTAs][tap][C][F]
 };
 
 // 16 pixels of one channel row, shifted by D columns, as four 16-byte chunks of a swizzled K-major tile row
@@ -472,6 +473,17 @@ __device__ __forceinline__ void cw2_store_shifted(const float (&v)[24], uint8_t 
             make_float4(v[4 + 4 * kk + D], v[5 + 4 * kk + D], v[6 + 4 * kk + D], v[7 + 4 * kk + D]);
 }
 
+// dbg & 256: time spent in a wait (clock64 either side); otherwise just the statement
+#define CW2_T(stmt, acc)                       \
+    do {                                       \
+        if (p.dbg & 256) {                     \
+            const long long t0_ = clock64();   \
+            stmt;                              \
+            acc += clock64() - t0_;            \
+        } else {                               \
+            stmt;                              \
+        }                                      \
+    } while (0)
 constexpr int CW2_RAW_W = 40;  // raw X box: 4 halo pixels left, 32, 4 right
 constexpr uint32_t CW2_DY_SLOT = 8192;
 constexpr int CW2_RAW_STAGES = 6;   // most raw X row boxes in flight (p.raw_stages)
@@ -528,13 +540,17 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
     const int u_lo = blockIdx.x * p.units_per_cta;
     int u_hi = u_lo + p.units_per_cta;
     if (u_hi > p.units) u_hi = p.units;
+    if (p.dbg & 64) u_hi = u_lo;
     const int run_in = p.kh - 1;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            int L = 0;        // dY loads so far (ring position)
-            int xs = 0;       // X rows so far (raw double buffer)
+            long long tw0 = 0, tw1 = 0;
+            const long long tstart = clock64();
+            int L = 0;        // dY loads so far
+            int slot = 0, rs = 0;         // dY ring slot, raw X stage
+            uint32_t dph = 1u, rph = 1u;  // phases of the "empty" waits (first lap passes)
             for (int u = u_lo; u < u_hi; ++u) {
                 const int strip = u / p.chunks, chunk = u - strip * p.chunks;
                 const int n = strip / p.csegs, c0 = (strip - n * p.csegs) * 32;
@@ -544,66 +560,100 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
                 const int oh0 = r_lo + p.p - run_in;  // first dY row of the unit (rows outside the tensor arrive as zeros)
                 const int nload = (r_hi - r_lo) + run_in;
                 for (int t = 0; t < nload; ++t, ++L) {
-                    const int slot = L % p.ring;
-                    mbar_wait(dyempty(slot), (((uint32_t)(L / p.ring)) & 1u) ^ 1u);
+                    CW2_T(mbar_wait(dyempty(slot), dph), tw0);
                     const uint32_t fb = dyfull(slot), bytes = (uint32_t)p.a_rows * 128u;
-                    mbar_expect_tx(fb, slot == 0 ? 2u * bytes : bytes);
-                    tma_load_4d(ring_base + (uint32_t)slot * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
-                    if (slot == 0) tma_load_4d(ring_base + (uint32_t)p.ring * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
-                    if (t >= run_in) {  // the X row of this step
-                        const int rs = xs % p.raw_stages;
-                        mbar_wait(rawempty(rs), (((uint32_t)(xs / p.raw_stages)) & 1u) ^ 1u);
-                        mbar_expect_tx(rawfull(rs), raw_bytes);
-                        tma_load_4d(raw_base + (uint32_t)rs * raw_bytes, &tmXR, rawfull(rs), c0 - 4, r_lo + (t - run_in), 0, n);
-                        ++xs;
+                    if (p.dbg & 4) {
+                        mbar_arrive(fb);
+                    } else {
+                        mbar_expect_tx(fb, slot == 0 ? 2u * bytes : bytes);
+                        tma_load_4d(ring_base + (uint32_t)slot * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
+                        if (slot == 0) tma_load_4d(ring_base + (uint32_t)p.ring * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
                     }
+                    if (t >= run_in) {  // the X row of this step
+                        CW2_T(mbar_wait(rawempty(rs), rph), tw1);
+                        if (p.dbg & 8) {
+                            mbar_arrive(rawfull(rs));
+                        } else {
+                            mbar_expect_tx(rawfull(rs), raw_bytes);
+                            tma_load_4d(raw_base + (uint32_t)rs * raw_bytes, &tmXR, rawfull(rs), c0 - 4, r_lo + (t - run_in), 0, n);
+                        }
+                        if (++rs == p.raw_stages) { rs = 0; rph ^= 1u; }
+                    }
+                    if (++slot == p.ring) { slot = 0; dph ^= 1u; }
                 }
             }
+            if ((p.dbg & 256) && (blockIdx.x == 0 || blockIdx.x == 73))
+                printf("cw2 cta %d producer: total %lld  wait dyempty %lld  wait rawempty %lld  (loads %d)\n", blockIdx.x,
+                       clock64() - tstart, tw0, tw1, L);
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(128, p.kw * p.bnC, 0, 0);
-            int L = 0, xs = 0;
-            uint32_t started = 0;  // bit k: accumulator k has been written
+        // The whole warp walks the loop (uniform control flow, every lane polls the barriers) and one elected lane issues: the
+        // issue stream IS the step-time floor, so ring slots and phases are carried incrementally (no divisions) and the
+        // descriptors are split into constant upper and incremented lower words (mma_tf32_k4).
+        {
+            const uint32_t idesc = idesc_tf32(128, (p.dbg & 512) ? 16 : p.kw * p.bnC, 0, 0);
+            const uint32_t d_hi = smem_desc_hi(1024u, LAYOUT_SW128);
+            int slot = 0, bs = 0, xs = 0;      // dY ring slot of the current load, shifted-tile buffer of the current step
+            uint32_t dph = 0, bph = 0;         // their phases
+            long long tw0 = 0, tw1 = 0;
+            const long long tstart = clock64();
+            uint32_t started = 0;  // accumulators written?
             for (int u = u_lo; u < u_hi; ++u) {
                 const int chunk = u % p.chunks;
                 const int r_lo = chunk * p.rc;
                 int r_hi = r_lo + p.rc;
                 if (r_hi > p.H) r_hi = p.H;
                 const int nload = (r_hi - r_lo) + run_in;
-                for (int t = 0; t < nload; ++t, ++L) {
+                for (int t = 0; t < nload; ++t) {
                     // every dY load is waited for exactly once, in order (the run-in rows carry no step of their own)
-                    mbar_wait(dyfull(L % p.ring), ((uint32_t)(L / p.ring)) & 1u);
-                    if (t < run_in) continue;
-                    const int bs = xs % p.nb;
-                    mbar_wait(bfull(bs), ((uint32_t)(xs / p.nb)) & 1u);
-                    tc_fence_after();
-                    const uint32_t sB = b_base + (uint32_t)bs * b_tile;
-                    // row tap i pairs this X row with the dY row loaded i loads ago
+                    CW2_T(mbar_wait(dyfull(slot), dph), tw0);
+                    if (t >= run_in) {
+                        CW2_T(mbar_wait(bfull(bs), bph), tw1);
+                        if (!(p.dbg & 2048)) tc_fence_after();
+                        const uint32_t b_lo = smem_desc_lo(b_base + (uint32_t)bs * b_tile, 16u);
+                        int sold = slot - run_in;
+                        if (sold < 0) sold += p.ring;
+                        // row tap i pairs this X row with the dY row loaded i loads ago
 #pragma unroll 1
-                    for (int k = 0; k < p.npairs; ++k) {
-                        const int i_lo = 2 * k;                      // tap in lanes 64-127 (or 0-63 when it has no partner)
-                        const bool paired = i_lo + 1 < p.kh;
-                        const int Ltop = L - (paired ? i_lo + 1 : i_lo);
-                        const uint32_t sA = ring_base + (uint32_t)(Ltop % p.ring) * CW2_DY_SLOT;
-                        const uint32_t d_tmem = tmem_base + (uint32_t)k * p.acc_stride;
-#pragma unroll 1
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t ad = smem_desc(sA + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                            const uint64_t bd = smem_desc(sB + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                            mma_tf32(d_tmem, ad, bd, idesc, (((started >> k) & 1u) || ks > 0) ? 1u : 0u);
+                        for (int k = 0; k < ((p.dbg & 2) ? 0 : p.npairs); ++k) {
+                            const int i_lo = 2 * k;                      // tap in lanes 64-127 (or 0-63 when it has no partner)
+                            int stop = slot - (i_lo + 1 < p.kh ? i_lo + 1 : i_lo);
+                            if (stop < 0) stop += p.ring;
+                            const uint32_t a_lo = smem_desc_lo(ring_base + (uint32_t)stop * CW2_DY_SLOT, 16u);
+                            if (elect_one())
+                                mma_tf32_k4(tmem_base + (uint32_t)k * p.acc_stride, a_lo, d_hi, b_lo, d_hi, 2u, 2u, idesc, started);
                         }
-                        started |= 1u << k;
+                        started = 1u;
+                        if (elect_one()) {
+                            if (p.dbg & 8192) {  // (only without MMAs) plain arrives instead of commits
+                                mbar_arrive(bempty(bs));
+                                mbar_arrive(dyempty(sold));
+                            } else {
+                                mma_commit(bempty(bs));
+                                mma_commit(dyempty(sold));  // the oldest dY row of this step is done
+                            }
+                        }
+                        if (t == nload - 1)
+                            for (int d = run_in - 1; d >= 0; --d) {
+                                int sd = slot - d;
+                                if (sd < 0) sd += p.ring;
+                                if (elect_one()) mma_commit(dyempty(sd));
+                            }
+                        ++xs;
+                        if (++bs == p.nb) { bs = 0; bph ^= 1u; }
                     }
-                    mma_commit(bempty(bs));
-                    mma_commit(dyempty((L - run_in) % p.ring));  // the oldest dY row of this step is done
-                    if (t == nload - 1)
-                        for (int d = run_in - 1; d >= 0; --d) mma_commit(dyempty((L - d) % p.ring));
-                    ++xs;
+                    if (++slot == p.ring) { slot = 0; dph ^= 1u; }
                 }
             }
-            mma_commit(tfull_bar);
+            if (elect_one()) mma_commit(tfull_bar);
+            if ((p.dbg & 256) && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 73)) {
+                const long long tissue = clock64() - tstart;
+                mbar_wait(tfull_bar, 0);
+                printf("cw2 cta %d mma: issue loop %lld (until done %lld)  wait dyfull %lld  wait bfull %lld  (steps %d)\n", blockIdx.x,
+                       tissue, clock64() - tstart, tw0, tw1, xs);
+            }
+            __syncwarp();
         }
     } else {
         // ================================ shifter (warps 2..5), then epilogue ==========
@@ -616,11 +666,14 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
             if (r_hi > p.H) r_hi = p.H;
             total_steps += r_hi - r_lo;
         }
+        long long tw0 = 0, tw1 = 0;
+        const long long tstart = clock64();
+        int rs = 0, bs = 0;
+        uint32_t rph = 0, bph = 1u;
         for (int xs = 0; xs < total_steps; ++xs) {
-            const int rs = xs % p.raw_stages, bs = xs % p.nb;
-            mbar_wait(rawfull(rs), ((uint32_t)(xs / p.raw_stages)) & 1u);
-            mbar_wait(bempty(bs), (((uint32_t)(xs / p.nb)) & 1u) ^ 1u);
-            if (c < p.bnC) {
+            CW2_T(mbar_wait(rawfull(rs), rph), tw0);
+            CW2_T(mbar_wait(bempty(bs), bph), tw1);
+            if (c < p.bnC && !(p.dbg & 1)) {
                 // raw[c][16*hh .. 16*hh + 23] covers the 16 pixels of this half shifted by -4 .. +4
                 const float4 *src = reinterpret_cast<const float4 *>(smem_raw + (raw_base - smem_u32(smem_raw)) + (uint32_t)rs * raw_bytes +
                                                                      (uint32_t)c * (CW2_RAW_W * 4) + (uint32_t)hh * 64u);
@@ -653,16 +706,23 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
                 mbar_arrive(bfull(bs));
                 mbar_arrive(rawempty(rs));
             }
+            if (++rs == p.raw_stages) { rs = 0; rph ^= 1u; }
+            if (++bs == p.nb) { bs = 0; bph ^= 1u; }
         }
         // epilogue: accumulator k, lanes 0-63 = tap 2k+1 (or the unpaired tap), lanes 64-127 = tap 2k
         const int q = warp & 3;
+        const long long tloop = clock64() - tstart;
         if (u_lo < u_hi) {
             mbar_wait(tfull_bar, 0);
             tc_fence_after();
         }
+        const long long ttail = clock64() - tstart;
         const int f = 32 * (q & 1) + lane;
         const int taps = p.kh * p.kw;
-        float *o = p.partial + ((long long)blockIdx.x * p.F + f) * p.C * taps;
+        // partial sums as [CTA][tap][c][f]: for every (tap, c) a warp stores 32 consecutive floats.  (The first version wrote
+        // the final [f][c][tap] order directly: 4-byte stores 36 bytes apart, 49 K of them per CTA -- ncu's stall samples put
+        // a fifth of the kernel into this epilogue.  cw2_reduce_kernel does the transposition while it adds the partials.)
+        float *o = p.partial + (long long)blockIdx.x * taps * p.C * p.F + f;
         for (int k = 0; k < p.npairs; ++k) {
             const bool paired = 2 * k + 1 < p.kh;
             const int i = paired ? (q < 2 ? 2 * k + 1 : 2 * k) : 2 * k;
@@ -678,18 +738,55 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
                     }
-                    if (live && f < p.F) {
+                    if (live && f < p.F && !(p.dbg & 16)) {
+                        float *ot = o + (long long)((i * p.kw + j) * p.C + cc) * p.F;
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj)
-                            if (cc + jj < p.C) o[(long long)(cc + jj) * taps + i * p.kw + j] = __uint_as_float(v[jj]);
+                            if (cc + jj < p.C) ot[(long long)jj * p.F] = __uint_as_float(v[jj]);
                     }
                 }
             }
         }
+        if ((p.dbg & 256) && warp == 2 && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 73))
+            printf("cw2 cta %d shifter: loop %lld  accumulators ready %lld  stores issued %lld  wait rawfull %lld  wait bempty %lld\n",
+                   blockIdx.x, tloop, ttail, clock64() - tstart, tw0, tw1);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// dW[f][c][tap] = sum_z partial[z][tap][c][f] + l2 * W[f][c][tap]: reads coalesced along f, the Z partials spread over 32
+// thread rows and combined in a fixed order (deterministic), one scattered write per output element
+__global__ void __launch_bounds__(1024)
+cw2_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ w, float *__restrict__ dw, float l2, int F, int C,
+                  int taps, int Z) {
+    __shared__ float red[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long mn = (long long)taps * C * F;
+    const long long i = (long long)blockIdx.x * 32 + tx;
+    float s = 0.0f;
+    if (i < mn) {
+        int z = ty;
+        for (; z + 96 < Z; z += 128) {
+            const float a = partial[(long long)z * mn + i], b = partial[(long long)(z + 32) * mn + i];
+            const float c2 = partial[(long long)(z + 64) * mn + i], d = partial[(long long)(z + 96) * mn + i];
+            s += (a + b) + (c2 + d);
+        }
+        for (; z < Z; z += 32) s += partial[(long long)z * mn + i];
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < mn) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int y = 1; y < 32; ++y) t += red[y][tx];
+        const int f = (int)(i % F);
+        const long long r = i / F;
+        const int c = (int)(r % C), tap = (int)(r / C);
+        const long long o = ((long long)f * C + c) * taps + tap;
+        dw[o] = t + (l2 != 0.0f ? l2 * w[o] : 0.0f);
+    }
 }
 
 // filters -> [tap][out channel][in channel padded to 32]:  mode 0 (forward) Wp[(i,j)][f][c] = W[f][c][i][j];
@@ -907,6 +1004,7 @@ conv_tma_shift_kernel(const float *__restrict__ x, float *__restrict__ xs, long 
 // 188.2 / 188.1 / 188.1 us with 2 / 3 / 4 buffers -- letting the shifter run further ahead changes nothing, so the exposed
 // hand-over latency the stall samples suggested is NOT what holds the kernel at 25 % tensor pipe; 2 keeps all 6 raw stages.
 int g_cw2_nb = 2;
+int g_cw2_dbg = 0;  // dk_tc_debug_set key 27: Cw2Params::dbg
 int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
                    int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (s != 1 || !g_ct_ready || !g_conv_tma_enabled) return DK_ERR_UNSUPPORTED;
@@ -946,6 +1044,7 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         // raw-box stages (measured: no effect, see g_cw2_nb).
         q.nb = g_cw2_nb < 2 ? 2 : g_cw2_nb > CW2_NB_MAX ? CW2_NB_MAX : g_cw2_nb;
         q.raw_stages = CW2_RAW_STAGES;
+        q.dbg = g_cw2_dbg;
         while (q.nb > 2 || q.raw_stages > 3) {
             const size_t need = (size_t)(q.ring + 1) * CW2_DY_SLOT + (size_t)q.nb * (kw * q.bnC) * 128 +
                                 (size_t)q.raw_stages * q.bnC * CW2_RAW_W * 4 + 1024 + 16 + 8 * 64;
@@ -970,7 +1069,8 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         if (smem > (size_t)CT_SMEM_MAX) return DK_ERR_UNSUPPORTED;
         conv_s1_wgrad2_kernel<<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
         DK_LAUNCH_CHECK();
-        splitk_reduce_launch(q.partial, w, dw, l2, (int64_t)F * C * taps, ctas, st);
+        if (!(q.dbg & 32))
+            cw2_reduce_kernel<<<(unsigned)ceil_div((int64_t)F * C * taps, 32), 1024, 0, st>>>(q.partial, w, dw, l2, F, C, taps, ctas);
         DK_LAUNCH_CHECK();
         return DK_OK;
     }

@@ -88,6 +88,50 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (the lowest).  The issuing warp keeps its control flow warp-uniform and elects a lane only
+// around the tcgen05 instructions: addresses and descriptors then live in uniform registers.  Inside an `if (lane == 0)` region
+// the compiler must assume divergence and wraps EVERY tcgen05.mma / commit in an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY
+// waterfall: ~100 cycles of issue latency per MMA (measured), more than a 128 x 192 x 8 MMA takes to execute.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Four consecutive K = 8 slices of one operand pair from ONE inline block: the descriptors' upper words (stride / layout
+// fields) are loop constants and the lower words advance by a fixed step (bytes >> 4), so an MMA costs two adds and two
+// register pairs.  (The issuing thread is a single lane: building both 64-bit descriptors from scratch for every MMA, as
+// smem_desc() + mma_tf32() do, takes ~200 cycles of dependent scalar work -- more than a 128 x 192 x 8 MMA takes to
+// execute.  Measured on conv_s1_wgrad2_kernel: the issue loop, not the tensor pipe, set the step time.)
+// The first MMA accumulates iff acc0 != 0, the other three always do.
+__device__ __forceinline__ void mma_tf32_k4(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t a_step, uint32_t b_step, uint32_t idesc, uint32_t acc0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "add.u32 al, %1, %7;\n\tadd.u32 bl, %3, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "add.u32 al, al, %7;\n\tadd.u32 bl, bl, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc0), "r"(a_step), "r"(b_step)
+        : "memory");
+}
+// one MMA from split descriptor words (see mma_tf32_k4)
+__device__ __forceinline__ void mma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // mbarrier arrive once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -130,6 +174,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)(layout & 7u) << 61;
     return d;
+}
+
+// the two 32-bit halves of smem_desc(): lo = start address | leading byte offset, hi = stride byte offset | version | layout
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout & 7u) << 29);
 }
 
 // Instruction descriptor for kind::tf32, fp32 accumulate, dense: c_format [4,6) = 1 (F32), a_format [7,10) = 2
