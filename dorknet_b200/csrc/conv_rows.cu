@@ -355,8 +355,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
 
     if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        // whole warp, uniform control flow, one elected lane issues (no per-MMA ELECT / R2UR waterfall); descriptors as
+        // constant upper and incremented lower words
+        {
             const uint32_t idesc = idesc_tf32(128, p.bn, 1, 0);
+            const uint32_t a_hi = smem_desc_hi(512u, LAYOUT_SW128_BASE32B), b_hi = smem_desc_hi(1024u, LAYOUT_SW128);
             int it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int a = it & 1;
@@ -367,19 +370,28 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_rows_fwd_kernel(const Conv
                 const uint32_t d_tmem = tmem_base + (uint32_t)a * p.acc_stride;
                 const uint32_t sAa = sA + (uint32_t)a * a_bytes;
                 uint32_t accum = 0;
+#pragma unroll 1
                 for (int kc = 0; kc < p.KC; ++kc) {
                     const int rem = p.KP - kc * 32;
                     const int nks = rem >= 32 ? 4 : rem / 8;
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint64_t ad = smem_desc(sAa + (uint32_t)kc * 16384u + (uint32_t)ks * 1024u, 4096u, 512u, LAYOUT_SW128_BASE32B);
-                        const uint64_t bd = smem_desc(sB + (uint32_t)kc * (uint32_t)p.bn * 128u + (uint32_t)ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                        mma_tf32(d_tmem, ad, bd, idesc, accum);
-                        accum = 1;
+                    const uint32_t a_lo = smem_desc_lo(sAa + (uint32_t)kc * 16384u, 4096u);
+                    const uint32_t b_lo = smem_desc_lo(sB + (uint32_t)kc * (uint32_t)p.bn * 128u, 16u);
+                    if (nks == 4) {
+                        if (elect_one()) mma_tf32_k4(d_tmem, a_lo, a_hi, b_lo, b_hi, 64u, 2u, idesc, accum);
+                    } else {
+#pragma unroll 1
+                        for (int ks = 0; ks < nks; ++ks)
+                            if (elect_one())
+                                mma_tf32_lohi(d_tmem, a_lo + 64u * (uint32_t)ks, a_hi, b_lo + 2u * (uint32_t)ks, b_hi, idesc, (accum || ks > 0) ? 1u : 0u);
                     }
+                    accum = 1;
                 }
-                mma_commit(a_empty(a));
-                mma_commit(t_full(a));
+                if (elect_one()) {
+                    mma_commit(a_empty(a));
+                    mma_commit(t_full(a));
+                }
             }
+            __syncwarp();
         }
     } else if (warp >= 6) {
         // ================================ loaders =====================================
@@ -602,29 +614,42 @@ conv_rows_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const ConvRowsP
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        // (whole warp, uniform control flow, one elected lane issues: see conv_rows_fwd_kernel)
+        {
             const uint32_t idesc = idesc_tf32(128, p.KP, 0, 0);
+            const uint32_t d_hi = smem_desc_hi(1024u, LAYOUT_SW128);
             uint32_t accum = 0;
-            int it = 0;
+            int it = 0, sa = 0;
+            uint32_t aph = 0;
             for (int r = r_beg; r < r_end; ++r, ++it) {
-                const int sa = it % p.a_stages, sb = it & 1;
-                mbar_wait(a_full(sa), (uint32_t)(it / p.a_stages) & 1u);
+                const int sb = it & 1;
+                mbar_wait(a_full(sa), aph);
                 mbar_wait(b_full(sb), (uint32_t)(it >> 1) & 1u);
                 tc_fence_after();
+#pragma unroll 1
                 for (int pc = 0; pc < p.PC; ++pc) {
                     const int rem = p.OW - pc * 32;
                     const int nks = rem >= 32 ? 4 : (rem + 7) / 8;
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint64_t ad = smem_desc(sA + (uint32_t)sa * a_bytes + (uint32_t)pc * a_chunk + (uint32_t)ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                        const uint64_t bd = smem_desc(sB + (uint32_t)sb * b_bytes + (uint32_t)pc * b_chunk + (uint32_t)ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                        mma_tf32(tmem_base, ad, bd, idesc, accum);
-                        accum = 1;
+                    const uint32_t a_lo = smem_desc_lo(sA + (uint32_t)sa * a_bytes + (uint32_t)pc * a_chunk, 16u);
+                    const uint32_t b_lo = smem_desc_lo(sB + (uint32_t)sb * b_bytes + (uint32_t)pc * b_chunk, 16u);
+                    if (nks == 4) {
+                        if (elect_one()) mma_tf32_k4(tmem_base, a_lo, d_hi, b_lo, d_hi, 2u, 2u, idesc, accum);
+                    } else {
+#pragma unroll 1
+                        for (int ks = 0; ks < nks; ++ks)
+                            if (elect_one())
+                                mma_tf32_lohi(tmem_base, a_lo + 2u * (uint32_t)ks, d_hi, b_lo + 2u * (uint32_t)ks, d_hi, idesc, (accum || ks > 0) ? 1u : 0u);
                     }
+                    accum = 1;
                 }
-                mma_commit(a_empty(sa));
-                mma_commit(b_empty(sb));
+                if (elect_one()) {
+                    mma_commit(a_empty(sa));
+                    mma_commit(b_empty(sb));
+                }
+                if (++sa == p.a_stages) { sa = 0; aph ^= 1u; }
             }
-            mma_commit(t_full);
+            if (elect_one()) mma_commit(t_full);
+            __syncwarp();
         }
     } else if (warp >= 6) {
         // ================================ loaders =====================================

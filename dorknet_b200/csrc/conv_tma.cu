@@ -153,11 +153,14 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        // whole warp, uniform control flow, one elected lane issues; descriptors as constant upper / incremented lower words
+        // (an `if (lane == 0)` region costs an ELECT / R2UR.BROADCAST waterfall per tcgen05.mma: ~100 cycles of issue latency each)
+        {
             if (p.w_resident) {
                 mbar_wait(wfull_bar, 0);
                 tc_fence_after();
             }
+            const uint32_t a_hi = smem_desc_hi(CT_MN_SBO, LAYOUT_SW128_BASE32B), b_hi = smem_desc_hi(1024u, LAYOUT_SW128);
             int s = 0, local = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
@@ -178,26 +181,31 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                                                       : sA + (uint32_t)p.nbox * p.box_bytes) + (uint32_t)(ch & 31) * 4u;
 #pragma unroll 1
                     for (int i = 0; i < p.kh; ++i) {
-                        const uint32_t a0 = sA + (uint32_t)(i * p.nb) * p.box_bytes;
+                        const uint32_t a_lo = smem_desc_lo(sA + (uint32_t)(i * p.nb) * p.box_bytes, p.box_bytes);
 #pragma unroll 1
                         for (int j0 = 0; j0 < p.kw; j0 += p.jchunk) {
                             const int nj = p.kw - j0 < p.jchunk ? p.kw - j0 : p.jchunk;
                             const uint32_t idesc = idesc_tf32(128, nj * p.bnF, 1, 0);
-                            const uint32_t b0 = wt + (uint32_t)(i * p.kw + j0) * p.b_bytes;
+                            const uint32_t b_lo = smem_desc_lo(wt + (uint32_t)(i * p.kw + j0) * p.b_bytes, 16u);
                             const uint32_t dd = d_tmem + (uint32_t)(j0 * p.bnF);
+                            const uint32_t acc0 = (ch > 0 || i > 0) ? 1u : 0u;
+                            if (nks == 4) {
+                                if (elect_one()) mma_tf32_k4(dd, a_lo, a_hi, b_lo, b_hi, CT_MN_KSTEP >> 4, 2u, idesc, acc0);
+                            } else {
 #pragma unroll 1
-                            for (int ks = 0; ks < nks; ++ks) {
-                                const uint64_t ad = smem_desc(a0 + ks * CT_MN_KSTEP, p.box_bytes, CT_MN_SBO, LAYOUT_SW128_BASE32B);
-                                const uint64_t bd = smem_desc(b0 + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                                mma_tf32(dd, ad, bd, idesc, (ch > 0 || i > 0 || ks > 0) ? 1u : 0u);
+                                for (int ks = 0; ks < nks; ++ks)
+                                    if (elect_one())
+                                        mma_tf32_lohi(dd, a_lo + (uint32_t)ks * (CT_MN_KSTEP >> 4), a_hi, b_lo + 2u * (uint32_t)ks, b_hi, idesc,
+                                                      (acc0 || ks > 0) ? 1u : 0u);
                             }
                         }
                     }
-                    mma_commit(empty_bar(s));
+                    if (elect_one()) mma_commit(empty_bar(s));
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                mma_commit(tfull_bar(acc));
+                if (elect_one()) mma_commit(tfull_bar(acc));
             }
+            __syncwarp();
         }
     } else {
         // ================================ epilogue (warps 2..9) ========================
@@ -366,8 +374,10 @@ conv_s1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // (whole warp, uniform control flow, one elected lane issues: see conv_s1_kernel)
+        {
             const uint32_t idesc = idesc_tf32(128, p.bnC, 0, 0);
+            const uint32_t d_hi = smem_desc_hi(1024u, LAYOUT_SW128);
             int s = 0;
             uint32_t ph = 0;
             bool first = true;
@@ -384,30 +394,27 @@ conv_s1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
                             if (sx < 0) sx += p.stages;
                             const uint32_t sB = smem_base + (uint32_t)sx * p.stage_bytes + p.a_bytes;
                             const uint32_t d_tmem = tmem_base + (uint32_t)i * p.acc_stride;
-#pragma unroll 1
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = smem_desc(sA + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                                const uint64_t bd = smem_desc(sB + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                                mma_tf32(d_tmem, ad, bd, idesc, (!first || ks > 0) ? 1u : 0u);
-                            }
+                            if (elect_one())
+                                mma_tf32_k4(d_tmem, smem_desc_lo(sA, 16u), d_hi, smem_desc_lo(sB, 16u), d_hi, 2u, 2u, idesc, first ? 0u : 1u);
                         }
                         first = false;
                         // the oldest X row of this step is not needed again
                         int so = s - (p.kh - 1);
                         if (so < 0) so += p.stages;
-                        mma_commit(empty_bar(so));
+                        if (elect_one()) mma_commit(empty_bar(so));
                         if (t == steps - 1) {  // end of the strip: the remaining run-out stages
                             for (int d = p.kh - 2; d >= 0; --d) {
                                 int sr = s - d;
                                 if (sr < 0) sr += p.stages;
-                                mma_commit(empty_bar(sr));
+                                if (elect_one()) mma_commit(empty_bar(sr));
                             }
                         }
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
-            mma_commit(tfull_bar);
+            if (elect_one()) mma_commit(tfull_bar);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;

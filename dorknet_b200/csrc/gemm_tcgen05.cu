@@ -328,7 +328,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (kAnyTma && lane == 0) {
+        // (whole warp, uniform control flow; one elected lane issues -- see the MMA issuer below)
+        if (kAnyTma) {
             int s = 0, xs = 0;
             uint32_t ph = 0, xph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -355,9 +356,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int c = 0; c < p.bn && p.xring > 0; c += 32) {
                             mbar_wait(xempty_bar(xs), xph ^ 1u);
                             const uint32_t xb = xfull_bar(xs), dst = xs_base + (uint32_t)xs * TC_X_SLOT;
-                            mbar_expect_tx(xb, TC_X_SLOT);
+                            if (elect_one()) {
+                                mbar_expect_tx(xb, TC_X_SLOT);
 #pragma unroll
-                            for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(dst + j * 4096u, &tmX, xb, m0 + 32 * j, n0 + c, b);
+                                for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(dst + j * 4096u, &tmX, xb, m0 + 32 * j, n0 + c, b);
+                            }
                             if (++xs == p.xring) { xs = 0; xph ^= 1u; }
                         }
                         break;
@@ -365,7 +368,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sA = smem_base + (uint32_t)s * stage_bytes, sB = sA + kpi * TC_A_BYTES;
                     const uint32_t fb = full_bar(s);
-                    mbar_expect_tx(fb, kpi * ((AG::kGather ? 0u : p.a_tx) + (BG::kGather ? 0u : b_bytes)));
+                    const bool issuer = elect_one();
+                    if (issuer) mbar_expect_tx(fb, kpi * ((AG::kGather ? 0u : p.a_tx) + (BG::kGather ? 0u : b_bytes)));
                     int kb = it, bb = b;
                     if (p.mode == 1) {
                         const int kk = item0 + it;
@@ -377,14 +381,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // wide items (wgrad, K-major operands): kpi consecutive 128-byte k-blocks of every row arrive
                         // together -- 512 B of each (n, f) plane row per item instead of 128 B, which is what the DRAM pages
                         // want; k-blocks past the plane are zero-filled by the TMA unit
-                        for (uint32_t j = 0; j < kpi; ++j) {
-                            tma_load_3d(sA + j * TC_A_BYTES, &tmA, fb, k0 + (int)j * TC_BK, m0, bb);
-                            tma_load_3d(sB + j * b_bytes, &tmB, fb, k0 + (int)j * TC_BK, n0, bb);
+                        if (issuer) {
+                            for (uint32_t j = 0; j < kpi; ++j) {
+                                tma_load_3d(sA + j * TC_A_BYTES, &tmA, fb, k0 + (int)j * TC_BK, m0, bb);
+                                tma_load_3d(sB + j * b_bytes, &tmB, fb, k0 + (int)j * TC_BK, n0, bb);
+                            }
                         }
                         if (++s == p.stages) { s = 0; ph ^= 1u; }
                         continue;
                     }
-                    if (!AG::kGather) {
+                    if (!AG::kGather && issuer) {
                         if (p.a_mn) {
 #pragma unroll
                             for (int j = 0; j < TC_BM / 32; ++j) tma_load_3d(sA + j * 4096u, &tmA, fb, m0 + 32 * j, k0, bb);
@@ -392,7 +398,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_load_3d(sA, &tmA, fb, k0, m0, bb);
                         }
                     }
-                    if (!BG::kGather) {
+                    if (!BG::kGather && issuer) {
                         const int bbB = (p.mode == 1 || p.b_batched) ? bb : 0;
                         if (p.b_mn) {
                             for (int j = 0; j < p.bn / 32; ++j) tma_load_3d(sB + j * 4096u, &tmB, fb, n0 + 32 * j, k0, bbB);
@@ -406,8 +412,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        // The whole warp walks the loop (uniform control flow: barrier addresses and descriptors stay in uniform registers) and
+        // one elected lane issues; the descriptors' upper words are kernel constants, the lower words advance by a fixed step
+        // per K = 8 slice.  (Inside an `if (lane == 0)` region every tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST /
+        // BRA.U.ANY waterfall after ~20 scalar instructions of descriptor building: ~100-200 cycles of issue latency per MMA.)
+        {
             const uint32_t idesc = idesc_tf32(TC_BM, p.bn, p.a_mn, p.b_mn);
+            const uint32_t a_hi = p.a_mn ? smem_desc_hi(p.mn_sbo, p.mn_layout) : smem_desc_hi(1024u, LAYOUT_SW128);
+            const uint32_t b_hi = p.b_mn ? smem_desc_hi(p.mn_sbo, p.mn_layout) : smem_desc_hi(1024u, LAYOUT_SW128);
+            const uint32_t a_lbo = p.a_mn ? p.mn_lbo : 16u, b_lbo = p.b_mn ? p.mn_lbo : 16u;
+            const uint32_t a_step = (p.a_mn ? p.mn_kstep : 32u) >> 4, b_step = (p.b_mn ? p.mn_kstep : 32u) >> 4;
             int s = 0;
             uint32_t ph = 0;
             int local = 0;
@@ -429,21 +443,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
 #pragma unroll 1
                     for (uint32_t j = 0; j < kpi; ++j) {
-                        const uint32_t sA = sA0 + j * TC_A_BYTES, sB = sB0 + j * b_bytes;
+                        const uint32_t a_lo = smem_desc_lo(sA0 + j * TC_A_BYTES, a_lbo), b_lo = smem_desc_lo(sB0 + j * b_bytes, b_lbo);
+                        const uint32_t acc0 = (it > 0 || j > 0) ? 1u : 0u;
+                        if (nks == 4) {
+                            if (elect_one()) mma_tf32_k4(d_tmem, a_lo, a_hi, b_lo, b_hi, a_step, b_step, idesc, acc0);
+                        } else {
 #pragma unroll 1
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const uint64_t ad = p.a_mn ? smem_desc(sA + ks * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                                       : smem_desc(sA + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                            const uint64_t bd = p.b_mn ? smem_desc(sB + ks * p.mn_kstep, p.mn_lbo, p.mn_sbo, p.mn_layout)
-                                                       : smem_desc(sB + ks * 32u, 16u, 1024u, LAYOUT_SW128);
-                            mma_tf32(d_tmem, ad, bd, idesc, (it > 0 || j > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < nks; ++ks)
+                                if (elect_one())
+                                    mma_tf32_lohi(d_tmem, a_lo + (uint32_t)ks * a_step, a_hi, b_lo + (uint32_t)ks * b_step, b_hi, idesc,
+                                                  (acc0 || ks > 0) ? 1u : 0u);
                         }
                     }
-                    mma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
+                    if (elect_one()) mma_commit(empty_bar(s));  // frees the stage once these MMAs have read it
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                mma_commit(tfull_bar(acc));  // accumulator complete
+                if (elect_one()) mma_commit(tfull_bar(acc));  // accumulator complete
             }
+            __syncwarp();
         }
     } else if (warp >= 6) {
         // ================================ gather loaders (warps 6..9) ===================
