@@ -119,9 +119,11 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        // lane 0 owns the barriers; the boxes of a stage are issued by as many lanes as there are boxes (a single thread
-        // issuing them one after the other was the bottleneck of the first version)
-        if (p.w_resident && lane == 0) {
+        // Whole warp, uniform control flow; ONE elected lane issues every box of a stage from uniform registers (a few cycles
+        // per box).  History: a single lane inside `if (lane == 0)` was the bottleneck of the first version, one box per lane
+        // (divergent coordinates) the second -- both pay an ELECT / R2UR.BROADCAST waterfall of ~100 cycles per box, which for
+        // 12-21 boxes per stage is more than the stage's MMAs take.
+        if (p.w_resident && elect_one()) {
             mbar_expect_tx(wfull_bar, (uint32_t)(taps * p.cblocks) * p.b_bytes);
             for (int cb = 0; cb < p.cblocks; ++cb)
                 for (int t = 0; t < taps; ++t)
@@ -134,19 +136,17 @@ conv_s1_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             const int n = tile / p.rgroups, r0 = (tile - n * p.rgroups) * p.nr;
             for (int ch = 0; ch < p.Cin; ch += p.kc) {  // one stage per kc channels
                 const uint32_t sA = stage0 + (uint32_t)s * p.stage_bytes, fb = full_bar(s);
-                if (lane == 0) {
-                    mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                if (elect_one()) {
                     mbar_expect_tx(fb, tx);
-                }
-                __syncwarp();
-                for (int b = lane; b < p.nbox; b += 32) {
-                    const int rr = b / p.nb, cb = b - rr * p.nb;
-                    tma_load_4d(sA + (uint32_t)b * p.box_bytes, &tmX, fb, 32 * cb, r0 + rr - p.ph, ch, n);
-                }
-                if (!p.w_resident) {  // (kc == 32 here)
-                    const uint32_t sB = sA + (uint32_t)p.nbox * p.box_bytes;
-                    for (int t = lane; t < taps; t += 32)
-                        tma_load_3d(sB + (uint32_t)t * p.b_bytes, &tmW, fb, ch, 0, t);
+                    uint32_t dst = sA;
+                    for (int rr = 0; rr * p.nb < p.nbox; ++rr)
+                        for (int cb = 0; cb < p.nb; ++cb, dst += p.box_bytes)
+                            tma_load_4d(dst, &tmX, fb, 32 * cb, r0 + rr - p.ph, ch, n);
+                    if (!p.w_resident) {  // (kc == 32 here)
+                        const uint32_t sB = sA + (uint32_t)p.nbox * p.box_bytes;
+                        for (int t = 0; t < taps; ++t) tma_load_3d(sB + (uint32_t)t * p.b_bytes, &tmW, fb, ch, 0, t);
+                    }
                 }
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
@@ -354,7 +354,8 @@ conv_s1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     const int steps = p.OH + p.kh - 1;  // per strip: kh - 1 rows of run-in, then one output row per step
 
     if (warp == 0) {
-        if (lane == 0) {
+        // (whole warp, uniform control flow, one elected lane issues)
+        {
             int s = 0;
             uint32_t ph = 0;
             for (int strip = sb; strip < se; ++strip) {
@@ -363,12 +364,14 @@ conv_s1_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sA = smem_base + (uint32_t)s * p.stage_bytes, sB = sA + p.a_bytes, fb = full_bar(s);
                     const int oh = t - (p.kh - 1);
-                    mbar_expect_tx(fb, p.b_bytes + (oh >= 0 ? (uint32_t)p.a_rows * 128u : 0u));
-                    // X row t - p (zero rows above / below) of the copy shifted by j - p columns: aligned boxes only (a box
-                    // starting at an odd column traps); the unshifted tap column reads X itself
-                    if (j == p.p) tma_load_4d(sB, &tmX, fb, c0, t - p.p, 0, n);
-                    else tma_load_4d(sB, &tmXS, fb, c0, t - p.p, 0, (j < p.p ? j : j - 1) * p.N + n);
-                    if (oh >= 0) tma_load_4d(sA, &tmDY, fb, c0, oh, 0, n);
+                    if (elect_one()) {
+                        mbar_expect_tx(fb, p.b_bytes + (oh >= 0 ? (uint32_t)p.a_rows * 128u : 0u));
+                        // X row t - p (zero rows above / below) of the copy shifted by j - p columns: aligned boxes only (a box
+                        // starting at an odd column traps); the unshifted tap column reads X itself
+                        if (j == p.p) tma_load_4d(sB, &tmX, fb, c0, t - p.p, 0, n);
+                        else tma_load_4d(sB, &tmXS, fb, c0, t - p.p, 0, (j < p.p ? j : j - 1) * p.N + n);
+                        if (oh >= 0) tma_load_4d(sA, &tmDY, fb, c0, oh, 0, n);
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -462,11 +465,10 @@ struct Cw2Params {
     int N, C, H, W, F, OH, OW, kh, kw, p;
     int bnC, a_rows, csegs, chunks, rc;   // rc = X rows per work unit, chunks = row chunks per strip
     int units, units_per_cta;
-    int ring;                            // dY ring slots (+1 mirror)
-    int nb;                              // shifted-tile buffers (2 .. 4): how far the shifter warps may run ahead of the MMAs
-    int raw_stages;                      // raw X row boxes in flight
+    int ring;                            // dY ring slots (+1 mirror), a multiple of the rows per step
+    int nb;                              // shifted-tile buffers (of R rows each)
+    int raw_stages;                      // raw X stages (of R row boxes each) in flight
     int npairs;
-    int dbg;                             // timing experiments only (results are garbage): 1 no shifting, 2 no MMAs, 4 no dY loads, 8 no X loads
     uint32_t tmem_cols, acc_stride;      // acc_stride = kw * bnC columns per row-tap pair
     float *partial;                      // [CTAs][tap][C][F]
 };
@@ -480,34 +482,30 @@ __device__ __forceinline__ void cw2_store_shifted(const float (&v)[24], uint8_t 
             make_float4(v[4 + 4 * kk + D], v[5 + 4 * kk + D], v[6 + 4 * kk + D], v[7 + 4 * kk + D]);
 }
 
-// dbg & 256: time spent in a wait (clock64 either side); otherwise just the statement
-#define CW2_T(stmt, acc)                       \
-    do {                                       \
-        if (p.dbg & 256) {                     \
-            const long long t0_ = clock64();   \
-            stmt;                              \
-            acc += clock64() - t0_;            \
-        } else {                               \
-            stmt;                              \
-        }                                      \
-    } while (0)
 constexpr int CW2_RAW_W = 40;  // raw X box: 4 halo pixels left, 32, 4 right
 constexpr uint32_t CW2_DY_SLOT = 8192;
-constexpr int CW2_RAW_STAGES = 6;   // most raw X row boxes in flight (p.raw_stages)
-constexpr int CW2_NB_MAX = 4;       // most shifted-tile buffers (p.nb)
 
+// R = X rows per pipeline step.  Every role of this kernel is a single warp (or four) walking a loop of mbarrier waits,
+// address arithmetic and issues, i.e. bound by instruction LATENCY: ~600 cycles of such overhead per step were measured in
+// the MMA warp with every load, shift and MMA removed, against 768 cycles of tensor work (8 MMAs of 128 x 192 x 8) in a 3 x 3
+// one-row step -- and tcgen05.mma itself occupies its issuing warp for ~70 cycles.  Two rows per step (R = 2: one barrier
+// round trip, 16 MMAs) halve that overhead per MMA; data stays row-granular (8 KB dY slots, one raw box and kw shifted
+// tiles per row), only the hand-shakes cover R rows.  R = 2 needs kh == 3 (the run-in of kh - 1 dY rows is then exactly one group).
+// KH = kh as a compile-time constant (0: read it from the parameters): unrolls the row-tap pairs of the issue loop.
+template <int R, int KH>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmXR, const Cw2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ring_base = smem_base;                                     // (ring + 1) x 8 KB
-    const uint32_t b_tile = (uint32_t)(p.kw * p.bnC) * 128u;                  // kw shifted tiles of bnC rows
-    const uint32_t b_base = ring_base + (uint32_t)(p.ring + 1) * CW2_DY_SLOT;  // p.nb x b_tile
+    const uint32_t b_row = (uint32_t)(p.kw * p.bnC) * 128u;                   // kw shifted tiles of bnC rows: one X row
+    const uint32_t b_buf = (uint32_t)R * b_row;
+    const uint32_t b_base = ring_base + (uint32_t)(p.ring + 1) * CW2_DY_SLOT;  // p.nb buffers of R rows
     const uint32_t raw_bytes = (uint32_t)p.bnC * CW2_RAW_W * 4u;
-    const uint32_t raw_base = b_base + (uint32_t)p.nb * b_tile;               // p.raw_stages x raw box
-    const uint32_t bar_base = (raw_base + (uint32_t)p.raw_stages * raw_bytes + 15u) & ~15u;
-    auto dyfull = [&](int s) { return bar_base + 8u * s; };
-    auto dyempty = [&](int s) { return bar_base + 8u * (16 + s); };
+    const uint32_t raw_base = b_base + (uint32_t)p.nb * b_buf;                // p.raw_stages stages of R raw boxes
+    const uint32_t bar_base = (raw_base + (uint32_t)(p.raw_stages * R) * raw_bytes + 15u) & ~15u;
+    auto dyfull = [&](int g) { return bar_base + 8u * g; };          // per GROUP of R dY rows
+    auto dyempty = [&](int g) { return bar_base + 8u * (16 + g); };
     auto rawfull = [&](int s) { return bar_base + 8u * (32 + s); };
     auto rawempty = [&](int s) { return bar_base + 8u * (40 + s); };
     auto bfull = [&](int s) { return bar_base + 8u * (48 + s); };
@@ -515,13 +513,14 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
     const uint32_t tfull_bar = bar_base + 8u * 56;
     const uint32_t tmem_slot = bar_base + 8u * 57;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int groups = p.ring / R;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmDY);
         tma_prefetch_desc(&tmXR);
-        for (int s = 0; s < p.ring; ++s) {
-            mbar_init(dyfull(s), 1);
-            mbar_init(dyempty(s), 1);
+        for (int g = 0; g < groups; ++g) {
+            mbar_init(dyfull(g), 1);
+            mbar_init(dyempty(g), 1);
         }
         for (int s = 0; s < p.raw_stages; ++s) {
             mbar_init(rawfull(s), 1);
@@ -547,188 +546,200 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
     const int u_lo = blockIdx.x * p.units_per_cta;
     int u_hi = u_lo + p.units_per_cta;
     if (u_hi > p.units) u_hi = p.units;
-    if (p.dbg & 64) u_hi = u_lo;
-    const int run_in = p.kh - 1;
+    const int kh = KH ? KH : p.kh, npairs = (kh + 1) / 2;
+    const int run_in = kh - 1;     // dY rows loaded ahead of the first step of a unit (a multiple of R)
+    const int lag = run_in / R;    // a dY group is last read `lag` steps after the one that waited for it
 
+    // Roles keep their control flow warp-uniform and elect one lane around the issues (see elect_one()); ring positions and
+    // phases are carried incrementally -- the loops below ARE the step time, every division or branch in them counts.
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
-            long long tw0 = 0, tw1 = 0;
-            const long long tstart = clock64();
-            int L = 0;        // dY loads so far
-            int slot = 0, rs = 0;         // dY ring slot, raw X stage
-            uint32_t dph = 1u, rph = 1u;  // phases of the "empty" waits (first lap passes)
-            for (int u = u_lo; u < u_hi; ++u) {
-                const int strip = u / p.chunks, chunk = u - strip * p.chunks;
-                const int n = strip / p.csegs, c0 = (strip - n * p.csegs) * 32;
-                const int r_lo = chunk * p.rc;
-                int r_hi = r_lo + p.rc;
-                if (r_hi > p.H) r_hi = p.H;
-                const int oh0 = r_lo + p.p - run_in;  // first dY row of the unit (rows outside the tensor arrive as zeros)
-                const int nload = (r_hi - r_lo) + run_in;
-                for (int t = 0; t < nload; ++t, ++L) {
-                    CW2_T(mbar_wait(dyempty(slot), dph), tw0);
-                    const uint32_t fb = dyfull(slot), bytes = (uint32_t)p.a_rows * 128u;
-                    if (p.dbg & 4) {
-                        mbar_arrive(fb);
-                    } else {
-                        mbar_expect_tx(fb, slot == 0 ? 2u * bytes : bytes);
-                        tma_load_4d(ring_base + (uint32_t)slot * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
-                        if (slot == 0) tma_load_4d(ring_base + (uint32_t)p.ring * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t, 0, n);
-                    }
-                    if (t >= run_in) {  // the X row of this step
-                        CW2_T(mbar_wait(rawempty(rs), rph), tw1);
-                        if (p.dbg & 8) {
-                            mbar_arrive(rawfull(rs));
-                        } else {
-                            mbar_expect_tx(rawfull(rs), raw_bytes);
-                            tma_load_4d(raw_base + (uint32_t)rs * raw_bytes, &tmXR, rawfull(rs), c0 - 4, r_lo + (t - run_in), 0, n);
-                        }
-                        if (++rs == p.raw_stages) { rs = 0; rph ^= 1u; }
-                    }
-                    if (++slot == p.ring) { slot = 0; dph ^= 1u; }
+        int gs = 0, rs = 0;           // dY group slot, raw X stage
+        uint32_t dph = 1u, rph = 1u;  // phases of the "empty" waits (first lap passes)
+        const uint32_t dy_bytes = (uint32_t)p.a_rows * 128u;
+        for (int u = u_lo; u < u_hi; ++u) {
+            const int strip = u / p.chunks, chunk = u - strip * p.chunks;
+            const int n = strip / p.csegs, c0 = (strip - n * p.csegs) * 32;
+            const int r_lo = chunk * p.rc;
+            int r_hi = r_lo + p.rc;
+            if (r_hi > p.H) r_hi = p.H;
+            const int oh0 = r_lo + p.p - run_in;  // first dY row of the unit (rows outside the tensor arrive as zeros)
+            const int nload = (r_hi - r_lo) + run_in;
+            for (int t0 = 0; t0 < nload; t0 += R) {
+                const int nv = nload - t0 < R ? nload - t0 : R;
+                mbar_wait(dyempty(gs), dph);
+                if (elect_one()) {
+                    const uint32_t fb = dyfull(gs);
+                    mbar_expect_tx(fb, (uint32_t)(nv + (gs == 0 ? 1 : 0)) * dy_bytes);
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr)
+                        if (rr < nv) tma_load_4d(ring_base + (uint32_t)(gs * R + rr) * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t0 + rr, 0, n);
+                    // slot 0 is mirrored behind the last slot: a pair of consecutive rows never wraps
+                    if (gs == 0) tma_load_4d(ring_base + (uint32_t)p.ring * CW2_DY_SLOT, &tmDY, fb, c0, oh0 + t0, 0, n);
                 }
+                if (t0 >= run_in) {  // the X rows of this step
+                    mbar_wait(rawempty(rs), rph);
+                    if (elect_one()) {
+                        mbar_expect_tx(rawfull(rs), (uint32_t)nv * raw_bytes);
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr)
+                            if (rr < nv)
+                                tma_load_4d(raw_base + (uint32_t)(rs * R + rr) * raw_bytes, &tmXR, rawfull(rs), c0 - 4,
+                                            r_lo + (t0 - run_in) + rr, 0, n);
+                    }
+                    if (++rs == p.raw_stages) { rs = 0; rph ^= 1u; }
+                }
+                if (++gs == groups) { gs = 0; dph ^= 1u; }
             }
-            if ((p.dbg & 256) && (blockIdx.x == 0 || blockIdx.x == 73))
-                printf("cw2 cta %d producer: total %lld  wait dyempty %lld  wait rawempty %lld  (loads %d)\n", blockIdx.x,
-                       clock64() - tstart, tw0, tw1, L);
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        // The whole warp walks the loop (uniform control flow, every lane polls the barriers) and one elected lane issues: the
-        // issue stream IS the step-time floor, so ring slots and phases are carried incrementally (no divisions) and the
-        // descriptors are split into constant upper and incremented lower words (mma_tf32_k4).
-        {
-            const uint32_t idesc = idesc_tf32(128, (p.dbg & 512) ? 16 : p.kw * p.bnC, 0, 0);
-            const uint32_t d_hi = smem_desc_hi(1024u, LAYOUT_SW128);
-            int slot = 0, bs = 0, xs = 0;      // dY ring slot of the current load, shifted-tile buffer of the current step
-            uint32_t dph = 0, bph = 0;         // their phases
-            long long tw0 = 0, tw1 = 0;
-            const long long tstart = clock64();
-            uint32_t started = 0;  // accumulators written?
-            for (int u = u_lo; u < u_hi; ++u) {
-                const int chunk = u % p.chunks;
-                const int r_lo = chunk * p.rc;
-                int r_hi = r_lo + p.rc;
-                if (r_hi > p.H) r_hi = p.H;
-                const int nload = (r_hi - r_lo) + run_in;
-                for (int t = 0; t < nload; ++t) {
-                    // every dY load is waited for exactly once, in order (the run-in rows carry no step of their own)
-                    CW2_T(mbar_wait(dyfull(slot), dph), tw0);
-                    if (t >= run_in) {
-                        CW2_T(mbar_wait(bfull(bs), bph), tw1);
-                        if (!(p.dbg & 2048)) tc_fence_after();
-                        const uint32_t b_lo = smem_desc_lo(b_base + (uint32_t)bs * b_tile, 16u);
-                        int sold = slot - run_in;
-                        if (sold < 0) sold += p.ring;
-                        // row tap i pairs this X row with the dY row loaded i loads ago
-#pragma unroll 1
-                        for (int k = 0; k < ((p.dbg & 2) ? 0 : p.npairs); ++k) {
-                            const int i_lo = 2 * k;                      // tap in lanes 64-127 (or 0-63 when it has no partner)
-                            int stop = slot - (i_lo + 1 < p.kh ? i_lo + 1 : i_lo);
-                            if (stop < 0) stop += p.ring;
-                            const uint32_t a_lo = smem_desc_lo(ring_base + (uint32_t)stop * CW2_DY_SLOT, 16u);
-                            if (elect_one())
-                                mma_tf32_k4(tmem_base + (uint32_t)k * p.acc_stride, a_lo, d_hi, b_lo, d_hi, 2u, 2u, idesc, started);
-                        }
-                        started = 1u;
-                        if (elect_one()) {
-                            if (p.dbg & 8192) {  // (only without MMAs) plain arrives instead of commits
-                                mbar_arrive(bempty(bs));
-                                mbar_arrive(dyempty(sold));
-                            } else {
-                                mma_commit(bempty(bs));
-                                mma_commit(dyempty(sold));  // the oldest dY row of this step is done
-                            }
-                        }
-                        if (t == nload - 1)
-                            for (int d = run_in - 1; d >= 0; --d) {
-                                int sd = slot - d;
-                                if (sd < 0) sd += p.ring;
-                                if (elect_one()) mma_commit(dyempty(sd));
-                            }
-                        ++xs;
-                        if (++bs == p.nb) { bs = 0; bph ^= 1u; }
-                    }
-                    if (++slot == p.ring) { slot = 0; dph ^= 1u; }
-                }
-            }
-            if (elect_one()) mma_commit(tfull_bar);
-            if ((p.dbg & 256) && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 73)) {
-                const long long tissue = clock64() - tstart;
-                mbar_wait(tfull_bar, 0);
-                printf("cw2 cta %d mma: issue loop %lld (until done %lld)  wait dyfull %lld  wait bfull %lld  (steps %d)\n", blockIdx.x,
-                       tissue, clock64() - tstart, tw0, tw1, xs);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ================================ shifter (warps 2..5), then epilogue ==========
-        const int t128 = threadIdx.x - 64;          // 0..127
-        const int c = t128 >> 1, hh = t128 & 1;      // channel row, 16-pixel half
-        int total_steps = 0;
+        // tcgen05.mma blocks its issuing warp until the tensor pipe accepts it and the pipe queues next to nothing, so every
+        // cycle this warp spends between two steps is a cycle the pipe idles (measured: 769 cycles per 8 MMAs of N = 192
+        // back to back, ~1200 with this loop's first version).  Hence ONE barrier per step here -- the shifter warps wait for
+        // the dY groups and their "tiles ready" arrival covers both operands -- and one elected block with all the issues.
+        const uint32_t idesc = idesc_tf32(128, p.kw * p.bnC, 0, 0);
+        const uint32_t d_hi = smem_desc_hi(1024u, LAYOUT_SW128);
+        int gs = 0, bs = 0;
+        uint32_t bph = 0, started = 0;
         for (int u = u_lo; u < u_hi; ++u) {
             const int r_lo = (u % p.chunks) * p.rc;
             int r_hi = r_lo + p.rc;
             if (r_hi > p.H) r_hi = p.H;
-            total_steps += r_hi - r_lo;
-        }
-        long long tw0 = 0, tw1 = 0;
-        const long long tstart = clock64();
-        int rs = 0, bs = 0;
-        uint32_t rph = 0, bph = 1u;
-        for (int xs = 0; xs < total_steps; ++xs) {
-            CW2_T(mbar_wait(rawfull(rs), rph), tw0);
-            CW2_T(mbar_wait(bempty(bs), bph), tw1);
-            if (c < p.bnC && !(p.dbg & 1)) {
-                // raw[c][16*hh .. 16*hh + 23] covers the 16 pixels of this half shifted by -4 .. +4
-                const float4 *src = reinterpret_cast<const float4 *>(smem_raw + (raw_base - smem_u32(smem_raw)) + (uint32_t)rs * raw_bytes +
-                                                                     (uint32_t)c * (CW2_RAW_W * 4) + (uint32_t)hh * 64u);
-                float v[24];
+            const int nrows = r_hi - r_lo;
+            gs += lag;  // the run-in groups
+            if (gs >= groups) gs -= groups;
+            for (int x0 = 0; x0 < nrows; x0 += R) {
+                const int nv = nrows - x0 < R ? nrows - x0 : R;
+                int gold = gs - lag;  // the oldest dY group of this step
+                if (gold < 0) gold += groups;
+                const uint32_t b_lo = smem_desc_lo(b_base + (uint32_t)bs * b_buf, 16u);
+                const uint32_t a_slot = smem_desc_lo(ring_base + (uint32_t)(gs * R) * CW2_DY_SLOT, 16u);
+                const uint32_t a_wrap = (uint32_t)p.ring * (CW2_DY_SLOT >> 4);
+                const uint32_t a_min = smem_desc_lo(ring_base, 16u);
+                mbar_wait(bfull(bs), bph);
+                tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int k4 = 0; k4 < 6; ++k4) {
-                    const float4 t4 = src[k4];
-                    v[4 * k4] = t4.x; v[4 * k4 + 1] = t4.y; v[4 * k4 + 2] = t4.z; v[4 * k4 + 3] = t4.w;
+                    for (int rr = 0; rr < R; ++rr) {
+                        if (rr < nv) {
+                            // row tap i pairs this X row with the dY row loaded i loads ago: accumulator k holds taps 2k + 1
+                            // (TMEM lanes 0-63) and 2k (lanes 64-127), or the unpaired last tap in lanes 0-63
+#pragma unroll
+                            for (int k = 0; k < (KH ? (KH + 1) / 2 : 3); ++k) {
+                                if (k < npairs) {
+                                    const int back = (2 * k + 1 < kh ? 2 * k + 1 : 2 * k) - rr;  // slots behind the group's first
+                                    uint32_t a_lo = a_slot - (uint32_t)back * (CW2_DY_SLOT >> 4);
+                                    if ((int)(a_lo - a_min) < 0) a_lo += a_wrap;
+                                    mma_tf32_k4(tmem_base + (uint32_t)k * p.acc_stride, a_lo, d_hi, b_lo + (uint32_t)rr * (b_row >> 4), d_hi, 2u,
+                                                2u, idesc, started | (uint32_t)rr);
+                                }
+                            }
+                        }
+                    }
+                    mma_commit(bempty(bs));
+                    mma_commit(dyempty(gold));
+                    if (x0 + R >= nrows)  // end of the unit: the groups a next step would still have read
+                        for (int d = lag - 1; d >= 0; --d) {
+                            int gd = gs - d;
+                            if (gd < 0) gd += groups;
+                            mma_commit(dyempty(gd));
+                        }
                 }
-                uint8_t *bt = smem_raw + (b_base - smem_u32(smem_raw)) + (uint32_t)bs * b_tile + (uint32_t)c * 128u;
-                for (int j = 0; j < p.kw; ++j) {
-                    uint8_t *row = bt + (uint32_t)(j * p.bnC) * 128u;
-                    const uint32_t sw = (uint32_t)(c & 7), ch0 = 4u * (uint32_t)hh;
-                    switch (j - p.p) {  // tile j holds X[col + d]: raw index 4 + col + d (uniform branch)
-                        case -4: cw2_store_shifted<-4>(v, row, ch0, sw); break;
-                        case -3: cw2_store_shifted<-3>(v, row, ch0, sw); break;
-                        case -2: cw2_store_shifted<-2>(v, row, ch0, sw); break;
-                        case -1: cw2_store_shifted<-1>(v, row, ch0, sw); break;
-                        case 0: cw2_store_shifted<0>(v, row, ch0, sw); break;
-                        case 1: cw2_store_shifted<1>(v, row, ch0, sw); break;
-                        case 2: cw2_store_shifted<2>(v, row, ch0, sw); break;
-                        case 3: cw2_store_shifted<3>(v, row, ch0, sw); break;
-                        default: cw2_store_shifted<4>(v, row, ch0, sw); break;
+                started = 1u;
+                if (++bs == p.nb) { bs = 0; bph ^= 1u; }
+                if (++gs == groups) gs = 0;
+            }
+        }
+        if (elect_one()) mma_commit(tfull_bar);
+        __syncwarp();
+    } else {
+        // ================================ shifter (warps 2..5), then epilogue ==========
+        const int t128 = threadIdx.x - 64;          // 0..127
+        const int c = t128 >> 1, hh = t128 & 1;      // channel row, 16-pixel half
+        int rs = 0, bs = 0, gs = 0;
+        uint32_t rph = 0, bph = 1u, dph = 0;
+        for (int u = u_lo; u < u_hi; ++u) {
+            const int r_lo = (u % p.chunks) * p.rc;
+            int r_hi = r_lo + p.rc;
+            if (r_hi > p.H) r_hi = p.H;
+            const int nrows = r_hi - r_lo;
+            // every dY group is waited for exactly once, in order, HERE: the "tiles ready" arrival below then tells the MMA warp
+            // that both operands of the step have landed (TMA loads may complete out of order; the run-in groups carry no step)
+            for (int d = 0; d < lag; ++d) {
+                mbar_wait(dyfull(gs), dph);
+                if (++gs == groups) { gs = 0; dph ^= 1u; }
+            }
+            for (int x0 = 0; x0 < nrows; x0 += R) {
+                const int nv = nrows - x0 < R ? nrows - x0 : R;
+                mbar_wait(rawfull(rs), rph);
+                mbar_wait(bempty(bs), bph);
+                if (c < p.bnC) {
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        if (rr < nv) {
+                            // raw[c][16*hh .. 16*hh + 23] covers the 16 pixels of this half shifted by -4 .. +4
+                            const float4 *src = reinterpret_cast<const float4 *>(smem_raw + (raw_base - smem_u32(smem_raw)) +
+                                                                                 (uint32_t)(rs * R + rr) * raw_bytes +
+                                                                                 (uint32_t)c * (CW2_RAW_W * 4) + (uint32_t)hh * 64u);
+                            // The 160-byte row pitch puts channels c and c + 4 of a quarter-warp (threads c = 4 consecutive channels x
+                            // two halves) on the same banks: odd channel pairs read their six chunks rotated by one and
+                            // un-rotate in registers (selects) -- conflict-free instead of two wavefronts per load.
+                            const bool rot = (c >> 1) & 1;
+                            float4 w4[6];
+#pragma unroll
+                            for (int k4 = 0; k4 < 6; ++k4) w4[k4] = src[rot ? (k4 == 5 ? 0 : k4 + 1) : k4];
+                            float v[24];
+#pragma unroll
+                            for (int k4 = 0; k4 < 6; ++k4) {
+                                const float4 a4 = w4[k4], b4 = w4[k4 == 0 ? 5 : k4 - 1];
+                                const float4 t4 = rot ? b4 : a4;
+                                v[4 * k4] = t4.x; v[4 * k4 + 1] = t4.y; v[4 * k4 + 2] = t4.z; v[4 * k4 + 3] = t4.w;
+                            }
+                            uint8_t *bt = smem_raw + (b_base - smem_u32(smem_raw)) + (uint32_t)bs * b_buf + (uint32_t)rr * b_row +
+                                          (uint32_t)c * 128u;
+                            for (int j = 0; j < p.kw; ++j) {
+                                uint8_t *row = bt + (uint32_t)(j * p.bnC) * 128u;
+                                const uint32_t sw = (uint32_t)(c & 7), ch0 = 4u * (uint32_t)hh;
+                                switch (j - p.p) {  // tile j holds X[col + d]: raw index 4 + col + d (uniform branch)
+                                    case -4: cw2_store_shifted<-4>(v, row, ch0, sw); break;
+                                    case -3: cw2_store_shifted<-3>(v, row, ch0, sw); break;
+                                    case -2: cw2_store_shifted<-2>(v, row, ch0, sw); break;
+                                    case -1: cw2_store_shifted<-1>(v, row, ch0, sw); break;
+                                    case 0: cw2_store_shifted<0>(v, row, ch0, sw); break;
+                                    case 1: cw2_store_shifted<1>(v, row, ch0, sw); break;
+                                    case 2: cw2_store_shifted<2>(v, row, ch0, sw); break;
+                                    case 3: cw2_store_shifted<3>(v, row, ch0, sw); break;
+                                    default: cw2_store_shifted<4>(v, row, ch0, sw); break;
+                                }
+                            }
+                        }
                     }
                 }
+                fence_proxy_async();
+                mbar_wait(dyfull(gs), dph);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bfull(bs));
+                    mbar_arrive(rawempty(rs));
+                }
+                if (++rs == p.raw_stages) { rs = 0; rph ^= 1u; }
+                if (++bs == p.nb) { bs = 0; bph ^= 1u; }
+                if (++gs == groups) { gs = 0; dph ^= 1u; }
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bfull(bs));
-                mbar_arrive(rawempty(rs));
-            }
-            if (++rs == p.raw_stages) { rs = 0; rph ^= 1u; }
-            if (++bs == p.nb) { bs = 0; bph ^= 1u; }
         }
         // epilogue: accumulator k, lanes 0-63 = tap 2k+1 (or the unpaired tap), lanes 64-127 = tap 2k
         const int q = warp & 3;
-        const long long tloop = clock64() - tstart;
         if (u_lo < u_hi) {
             mbar_wait(tfull_bar, 0);
             tc_fence_after();
         }
-        const long long ttail = clock64() - tstart;
         const int f = 32 * (q & 1) + lane;
         const int taps = p.kh * p.kw;
         // partial sums as [CTA][tap][c][f]: for every (tap, c) a warp stores 32 consecutive floats.  (The first version wrote
-        // the final [f][c][tap] order directly: 4-byte stores 36 bytes apart, 49 K of them per CTA -- ncu's stall samples put
-        // a fifth of the kernel into this epilogue.  cw2_reduce_kernel does the transposition while it adds the partials.)
+        // the final [f][c][tap] order directly: 4-byte stores 36 bytes apart, 49 K of them per CTA -- a fifth of the kernel, and
+        // 173 MB of DRAM read-for-ownership.  cw2_reduce_kernel does the transposition while it adds the partials.)
         float *o = p.partial + (long long)blockIdx.x * taps * p.C * p.F + f;
         for (int k = 0; k < p.npairs; ++k) {
             const bool paired = 2 * k + 1 < p.kh;
@@ -745,7 +756,7 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
                     }
-                    if (live && f < p.F && !(p.dbg & 16)) {
+                    if (live && f < p.F) {
                         float *ot = o + (long long)((i * p.kw + j) * p.C + cc) * p.F;
 #pragma unroll
                         for (int jj = 0; jj < 32; ++jj)
@@ -754,9 +765,6 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
                 }
             }
         }
-        if ((p.dbg & 256) && warp == 2 && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 73))
-            printf("cw2 cta %d shifter: loop %lld  accumulators ready %lld  stores issued %lld  wait rawfull %lld  wait bempty %lld\n",
-                   blockIdx.x, tloop, ttail, clock64() - tstart, tw0, tw1);
     }
     tc_fence_before();
     __syncthreads();
@@ -836,7 +844,9 @@ int init_conv_tma() {
     g_ct_encode = reinterpret_cast<EncodeTiledFn>(fn);
     if (cudaFuncSetAttribute(conv_s1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess ||
         cudaFuncSetAttribute(conv_s1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_s1_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess) {
+        cudaFuncSetAttribute(conv_s1_wgrad2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_s1_wgrad2_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_s1_wgrad2_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_MAX + 2048) != cudaSuccess) {
         cudaGetLastError();
         return DK_OK;
     }
@@ -1007,11 +1017,10 @@ conv_tma_shift_kernel(const float *__restrict__ x, float *__restrict__ xs, long 
     }
 }
 
-// shifted-tile buffers of conv_s1_wgrad2_kernel (dk_tc_debug_set key 26).  Measured at cfg2 (3x3 64 -> 64 @56x56, batch 128):
-// 188.2 / 188.1 / 188.1 us with 2 / 3 / 4 buffers -- letting the shifter run further ahead changes nothing, so the exposed
-// hand-over latency the stall samples suggested is NOT what holds the kernel at 25 % tensor pipe; 2 keeps all 6 raw stages.
-int g_cw2_nb = 2;
-int g_cw2_dbg = 0;  // dk_tc_debug_set key 27: Cw2Params::dbg
+// X rows per step of conv_s1_wgrad2_kernel (dk_tc_debug_set key 26): 0 = two when kh == 3 and the buffers fit, else one.
+// (More shifted-tile buffers -- 2 / 3 / 4, measured 188.2 / 188.1 / 188.1 us on the first version -- never helped: the step
+// time is the issue warps' instruction latency, not a hand-over the shifter could hide by running ahead.)
+int g_cw2_rows = 0;
 int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
                    int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st) {
     if (s != 1 || !g_ct_ready || !g_conv_tma_enabled) return DK_ERR_UNSUPPORTED;
@@ -1046,18 +1055,23 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         q.npairs = (kh + 1) / 2;
         q.acc_stride = (uint32_t)(kw * q.bnC);
         q.tmem_cols = ct_pow2_cols((uint32_t)q.npairs * q.acc_stride);
-        q.ring = kh + 5 > 15 ? 15 : kh + 5;
-        // Shifted-tile buffers (g_cw2_nb): more than two let the shifter warps run further ahead of the MMAs, at the price of
-        // raw-box stages (measured: no effect, see g_cw2_nb).
-        q.nb = g_cw2_nb < 2 ? 2 : g_cw2_nb > CW2_NB_MAX ? CW2_NB_MAX : g_cw2_nb;
-        q.raw_stages = CW2_RAW_STAGES;
-        q.dbg = g_cw2_dbg;
-        while (q.nb > 2 || q.raw_stages > 3) {
-            const size_t need = (size_t)(q.ring + 1) * CW2_DY_SLOT + (size_t)q.nb * (kw * q.bnC) * 128 +
-                                (size_t)q.raw_stages * q.bnC * CW2_RAW_W * 4 + 1024 + 16 + 8 * 64;
-            if (need <= (size_t)CT_SMEM_MAX) break;
-            if (q.raw_stages > 3) --q.raw_stages;
-            else --q.nb;
+        q.nb = 2;
+        const size_t b_row = (size_t)(kw * q.bnC) * 128, raw_box = (size_t)q.bnC * CW2_RAW_W * 4, fixed = 1024 + 16 + 8 * 64;
+        auto smem_need = [&](int rows) {
+            return (size_t)(q.ring + 1) * CW2_DY_SLOT + (size_t)q.nb * rows * b_row + (size_t)q.raw_stages * rows * raw_box + fixed;
+        };
+        // two rows per step (kh == 3: the run-in is one group): 4 groups of dY rows, the raw stages that still fit (>= 2)
+        int rows = 1;
+        if (kh == 3 && g_cw2_rows != 1) {
+            q.ring = 8;
+            q.raw_stages = 3;
+            if (smem_need(2) > (size_t)CT_SMEM_MAX) q.raw_stages = 2;
+            if (smem_need(2) <= (size_t)CT_SMEM_MAX) rows = 2;
+        }
+        if (rows == 1) {
+            q.ring = kh + 5 > 15 ? 15 : kh + 5;
+            q.raw_stages = 6;
+            while (q.raw_stages > 3 && smem_need(1) > (size_t)CT_SMEM_MAX) --q.raw_stages;
         }
         const int taps = kh * kw;
         const size_t need = (size_t)ctas * F * C * taps * sizeof(float);
@@ -1072,12 +1086,13 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         const uint32_t bbr[4] = {CW2_RAW_W, 1, (uint32_t)q.bnC, 1};
         rc2 = ct_map(&tr, x, 4, dbr, bbr, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc2) return rc2;
-        const size_t smem = (size_t)(q.ring + 1) * CW2_DY_SLOT + (size_t)q.nb * (kw * q.bnC) * 128 + (size_t)q.raw_stages * q.bnC * CW2_RAW_W * 4 + 1024 + 16 + 8 * 64;
+        const size_t smem = smem_need(rows);
         if (smem > (size_t)CT_SMEM_MAX) return DK_ERR_UNSUPPORTED;
-        conv_s1_wgrad2_kernel<<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
+        if (rows == 2) conv_s1_wgrad2_kernel<2, 3><<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
+        else if (kh == 3) conv_s1_wgrad2_kernel<1, 3><<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
+        else conv_s1_wgrad2_kernel<1, 0><<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
         DK_LAUNCH_CHECK();
-        if (!(q.dbg & 32))
-            cw2_reduce_kernel<<<(unsigned)ceil_div((int64_t)F * C * taps, 32), 1024, 0, st>>>(q.partial, w, dw, l2, F, C, taps, ctas);
+        cw2_reduce_kernel<<<(unsigned)ceil_div((int64_t)F * C * taps, 32), 1024, 0, st>>>(q.partial, w, dw, l2, F, C, taps, ctas);
         DK_LAUNCH_CHECK();
         return DK_OK;
     }

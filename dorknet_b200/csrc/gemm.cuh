@@ -63,7 +63,7 @@ int conv_tma_dgrad(const float *dy, const float *w, float *dx, int N, int C, int
 int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, float l2, int N, int C, int H, int W, int F,
                    int kh, int kw, int s, int p, void *ws, size_t ws_bytes, cudaStream_t st);
 size_t conv_tma_ws_bytes(int N, int C, int H, int W, int F, int kh, int kw, int s, int p);
-extern int g_conv_tma_enabled, g_ct_kc16, g_ct_wgrad2, g_cw2_nb, g_cw2_dbg;
+extern int g_conv_tma_enabled, g_ct_kc16, g_ct_wgrad2, g_cw2_rows;
 void splitk_reduce_launch(const float *partial, const float *w, float *out, float l2, int64_t mn, int Z, cudaStream_t st);
 
 }  // namespace dk

@@ -1738,8 +1738,7 @@ int dk_tc_debug_set(int key, int value) {
         case 19: dk::g_ct_wgrad2 = value; break;  // 0: conv_tma wgrad through column-shifted global copies only
         case 18: dk::g_ct_kc16 = value; break;  // conv_tma forward / dgrad: 0 = 32-channel stages only
         case 17: dk::g_conv_tma_enabled = value; break;  // 0: stride-1 k x k convolutions skip conv_tma.cu (gather variants instead)
-        case 26: dk::g_cw2_nb = value; break;  // conv_tma wgrad: shifted-tile buffers (2 .. 4)
-        case 27: dk::g_cw2_dbg = value; break; // conv_tma wgrad timing experiments (results invalid): 1 no shift, 2 no MMA, 4 no dY loads, 8 no X loads
+        case 26: dk::g_cw2_rows = value; break;  // conv_tma wgrad: X rows per step (0 auto, 1, 2)
         case 24: dk::g_bn_split_ctas_per_sm = value; break;  // CTAs per SM the split BatchNorm kernels are planned for
         case 23: dk::g_fused_reduce = value; break;  // 0: pointwise wgrad partials go through the separate reduce kernel
         case 22: dk::g_wgrad_bn_cap = value; break;  // 0 automatic, else 64 / 128 / 256

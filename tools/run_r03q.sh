@@ -1,10 +1,6 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
-for d in 15 8207 10255; do
-  echo "dbg=$d $(timeout 60 python tests/kernel_bench.py --only conv3x3_wgrad --knobs 27=$d 2>&1 | tail -1)"
-done
-for d in 271 8463; do
-  echo "=== dbg=$d"
-  timeout 60 python tests/kernel_bench.py --only conv3x3_wgrad --iters 1 --knobs 27=$d > /tmp/o.txt 2>&1
-  for r in producer mma shifter; do grep "cw2 cta 73 $r" /tmp/o.txt | tail -1; done
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_network.py -x -q -m gpu -k "conv_tma or conv_tcgen05 or mnist" > gpurun_out/r03q_tests.log 2>&1; tail -3 gpurun_out/r03q_tests.log
+for k in "26=0" "26=1"; do
+  echo "knobs=$k $(timeout 60 python tests/kernel_bench.py --only conv3x3_wgrad --knobs $k 2>&1 | tail -1)"
 done
