@@ -470,7 +470,7 @@ struct Cw2Params {
     int raw_stages;                      // raw X stages (of R row boxes each) in flight
     int npairs;
     uint32_t tmem_cols, acc_stride;      // acc_stride = kw * bnC columns per row-tap pair
-    float *partial;                      // [CTAs][tap][C][F]
+    float *partial;                      // [CTAs][tap][F][C]
 };
 
 // 16 pixels of one channel row, shifted by D columns, as four 16-byte chunks of a swizzled K-major tile row
@@ -737,10 +737,12 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
         }
         const int f = 32 * (q & 1) + lane;
         const int taps = p.kh * p.kw;
-        // partial sums as [CTA][tap][c][f]: for every (tap, c) a warp stores 32 consecutive floats.  (The first version wrote
-        // the final [f][c][tap] order directly: 4-byte stores 36 bytes apart, 49 K of them per CTA -- a fifth of the kernel, and
-        // 173 MB of DRAM read-for-ownership.  cw2_reduce_kernel does the transposition while it adds the partials.)
-        float *o = p.partial + (long long)blockIdx.x * taps * p.C * p.F + f;
+        // partial sums as [CTA][tap][f][c]: a lane owns filter f and stores its 32 channels of a tap as eight 16-byte vectors.
+        // (The first version wrote the final [f][c][tap] order directly: 4-byte stores 36 bytes apart, 49 K of them per CTA -- a
+        // fifth of the kernel, and 173 MB of DRAM read-for-ownership; the second, [tap][c][f] with coalesced 4-byte stores, was
+        // still 1152 store instructions per warp.  cw2_reduce_kernel transposes while it adds the partials.)
+        float *o = p.partial + ((long long)blockIdx.x * taps * p.F + f) * p.C;
+        const bool vec4 = (p.C & 3) == 0;
         for (int k = 0; k < p.npairs; ++k) {
             const bool paired = 2 * k + 1 < p.kh;
             const int i = paired ? (q < 2 ? 2 * k + 1 : 2 * k) : 2 * k;
@@ -757,10 +759,18 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
                         for (int jj = 0; jj < 32; ++jj) v[jj] = 0u;
                     }
                     if (live && f < p.F) {
-                        float *ot = o + (long long)((i * p.kw + j) * p.C + cc) * p.F;
+                        float *ot = o + (long long)(i * p.kw + j) * p.F * p.C + cc;
+                        if (vec4) {
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj)
-                            if (cc + jj < p.C) ot[(long long)jj * p.F] = __uint_as_float(v[jj]);
+                            for (int e = 0; e < 8; ++e)
+                                if (cc + 4 * e < p.C)
+                                    *reinterpret_cast<float4 *>(ot + 4 * e) = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
+                                                                                          __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj)
+                                if (cc + jj < p.C) ot[jj] = __uint_as_float(v[jj]);
+                        }
                     }
                 }
             }
@@ -771,36 +781,47 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
     if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// dW[f][c][tap] = sum_z partial[z][tap][c][f] + l2 * W[f][c][tap]: reads coalesced along f, the Z partials spread over 32
-// thread rows and combined in a fixed order (deterministic), one scattered write per output element
+// dW[f][c][tap] = sum_z partial[z][tap][f][c] + l2 * W[f][c][tap]: V consecutive channels per thread (16-byte loads when C % 4
+// == 0), the Z partials spread over 32 thread rows and combined in a fixed order (deterministic), scattered 4-byte writes of
+// the (small) result
+template <int V>
 __global__ void __launch_bounds__(1024)
 cw2_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ w, float *__restrict__ dw, float l2, int F, int C,
                   int taps, int Z) {
-    __shared__ float red[32][33];
+    __shared__ float red[32][32 * V + 1];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long long mn = (long long)taps * C * F;
-    const long long i = (long long)blockIdx.x * 32 + tx;
-    float s = 0.0f;
-    if (i < mn) {
-        int z = ty;
-        for (; z + 96 < Z; z += 128) {
-            const float a = partial[(long long)z * mn + i], b = partial[(long long)(z + 32) * mn + i];
-            const float c2 = partial[(long long)(z + 64) * mn + i], d = partial[(long long)(z + 96) * mn + i];
-            s += (a + b) + (c2 + d);
-        }
-        for (; z < Z; z += 32) s += partial[(long long)z * mn + i];
-    }
-    red[ty][tx] = s;
-    __syncthreads();
-    if (ty == 0 && i < mn) {
-        float t = red[0][tx];
+    const long long i = ((long long)blockIdx.x * 32 + tx) * V;
+    float s[V];
 #pragma unroll
-        for (int y = 1; y < 32; ++y) t += red[y][tx];
-        const int f = (int)(i % F);
-        const long long r = i / F;
-        const int c = (int)(r % C), tap = (int)(r / C);
-        const long long o = ((long long)f * C + c) * taps + tap;
-        dw[o] = t + (l2 != 0.0f ? l2 * w[o] : 0.0f);
+    for (int e = 0; e < V; ++e) s[e] = 0.0f;
+    if (i < mn) {
+        for (int z = ty; z < Z; z += 32) {
+            const float *q = partial + (long long)z * mn + i;
+            if (V == 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(q);
+                s[0] += t.x; s[V > 1 ? 1 : 0] += t.y; s[V > 2 ? 2 : 0] += t.z; s[V > 3 ? 3 : 0] += t.w;
+            } else {
+                s[0] += q[0];
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) red[ty][tx * V + e] = s[e];
+    __syncthreads();
+    // 32 * V results per block: thread t < 32 * V adds the 32 rows of column t
+    if (threadIdx.x < 32 * V) {
+        const long long ii = (long long)blockIdx.x * 32 * V + threadIdx.x;
+        if (ii < mn) {
+            float t = red[0][threadIdx.x];
+#pragma unroll
+            for (int y = 1; y < 32; ++y) t += red[y][threadIdx.x];
+            const int c = (int)(ii % C);
+            const long long r = ii / C;
+            const int f = (int)(r % F), tap = (int)(r / F);
+            const long long o = ((long long)f * C + c) * taps + tap;
+            dw[o] = t + (l2 != 0.0f ? l2 * w[o] : 0.0f);
+        }
     }
 }
 
@@ -1017,7 +1038,8 @@ conv_tma_shift_kernel(const float *__restrict__ x, float *__restrict__ xs, long 
     }
 }
 
-// X rows per step of conv_s1_wgrad2_kernel (dk_tc_debug_set key 26): 0 = two when kh == 3 and the buffers fit, else one.
+// X rows per step of conv_s1_wgrad2_kernel (dk_tc_debug_set key 26): 2 = two when kh == 3 and the buffers fit; default one
+// (measured at cfg2: 104.7 us with two, 105.5 us with one -- the hand-shakes are not what bounds the loop).
 // (More shifted-tile buffers -- 2 / 3 / 4, measured 188.2 / 188.1 / 188.1 us on the first version -- never helped: the step
 // time is the issue warps' instruction latency, not a hand-over the shifter could hide by running ahead.)
 int g_cw2_rows = 0;
@@ -1062,7 +1084,7 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         };
         // two rows per step (kh == 3: the run-in is one group): 4 groups of dY rows, the raw stages that still fit (>= 2)
         int rows = 1;
-        if (kh == 3 && g_cw2_rows != 1) {
+        if (kh == 3 && g_cw2_rows == 2) {
             q.ring = 8;
             q.raw_stages = 3;
             if (smem_need(2) > (size_t)CT_SMEM_MAX) q.raw_stages = 2;
@@ -1092,7 +1114,8 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         else if (kh == 3) conv_s1_wgrad2_kernel<1, 3><<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
         else conv_s1_wgrad2_kernel<1, 0><<<ctas, CT_THREADS, smem, st>>>(ta, tr, q);
         DK_LAUNCH_CHECK();
-        cw2_reduce_kernel<<<(unsigned)ceil_div((int64_t)F * C * taps, 32), 1024, 0, st>>>(q.partial, w, dw, l2, F, C, taps, ctas);
+        if (C % 4 == 0) cw2_reduce_kernel<4><<<(unsigned)ceil_div((int64_t)F * C * taps, 128), 1024, 0, st>>>(q.partial, w, dw, l2, F, C, taps, ctas);
+        else cw2_reduce_kernel<1><<<(unsigned)ceil_div((int64_t)F * C * taps, 32), 1024, 0, st>>>(q.partial, w, dw, l2, F, C, taps, ctas);
         DK_LAUNCH_CHECK();
         return DK_OK;
     }

@@ -171,6 +171,18 @@ def test_conv_tma_stride1_vs_oracle(O, case):
     assert tc1 - tc0 == 3 and s1 == s0, "expected forward, dgrad and wgrad on the tensor-core path"
 
 
+@pytest.mark.parametrize("case", [(2, 64, 56, 56, 64, 3, 1, 1), (2, 40, 13, 36, 48, 3, 1, 1), (3, 32, 28, 28, 32, 3, 1, 1)])
+def test_conv_tma_wgrad_two_rows_per_step(O, case):
+    """conv_s1_wgrad2_kernel<2, 3> (two X rows per pipeline step; dk_tc_debug_set key 26): an odd row count per unit
+    ends in a one-row step.  The default is one row per step (same speed at cfg2, deeper buffering)."""
+    from dorknet_b200 import _lib
+    _lib.api.dk_tc_debug_set(26, 2)
+    try:
+        _conv_case(O, case)
+    finally:
+        _lib.api.dk_tc_debug_set(26, 0)
+
+
 CONV_MAT_CASES = [
     # N, C, H, W, F, k, s, p -- shapes outside conv_tma.cu / conv_rows.cu: materialised transposed patches + the all-TMA
     # pointwise GEMMs (gemm_tcgen05.cu cvm_*), dX by gather-form col2im
