@@ -558,8 +558,10 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
         uint32_t dph = 1u, rph = 1u;  // phases of the "empty" waits (first lap passes)
         const uint32_t dy_bytes = (uint32_t)p.a_rows * 128u;
         for (int u = u_lo; u < u_hi; ++u) {
-            const int strip = u / p.chunks, chunk = u - strip * p.chunks;
-            const int n = strip / p.csegs, c0 = (strip - n * p.csegs) * 32;
+            // unit order (image, row chunk, column segment): the segments of a row band follow each other on the same CTA, so the
+            // 64-byte DRAM granules and the halo columns they share are still in L2 when the second one asks for them
+            const int cseg = u % p.csegs, t = u / p.csegs;
+            const int chunk = t % p.chunks, n = t / p.chunks, c0 = cseg * 32;
             const int r_lo = chunk * p.rc;
             int r_hi = r_lo + p.rc;
             if (r_hi > p.H) r_hi = p.H;
@@ -604,7 +606,7 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
         int gs = 0, bs = 0;
         uint32_t bph = 0, started = 0;
         for (int u = u_lo; u < u_hi; ++u) {
-            const int r_lo = (u % p.chunks) * p.rc;
+            const int r_lo = ((u / p.csegs) % p.chunks) * p.rc;
             int r_hi = r_lo + p.rc;
             if (r_hi > p.H) r_hi = p.H;
             const int nrows = r_hi - r_lo;
@@ -661,7 +663,7 @@ conv_s1_wgrad2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_con
         int rs = 0, bs = 0, gs = 0;
         uint32_t rph = 0, bph = 1u, dph = 0;
         for (int u = u_lo; u < u_hi; ++u) {
-            const int r_lo = (u % p.chunks) * p.rc;
+            const int r_lo = ((u / p.csegs) % p.chunks) * p.rc;
             int r_hi = r_lo + p.rc;
             if (r_hi > p.H) r_hi = p.H;
             const int nrows = r_hi - r_lo;
@@ -1038,8 +1040,8 @@ conv_tma_shift_kernel(const float *__restrict__ x, float *__restrict__ xs, long 
     }
 }
 
-// X rows per step of conv_s1_wgrad2_kernel (dk_tc_debug_set key 26): 2 = two when kh == 3 and the buffers fit; default one
-// (measured at cfg2: 104.7 us with two, 105.5 us with one -- the hand-shakes are not what bounds the loop).
+// X rows per step of conv_s1_wgrad2_kernel (dk_tc_debug_set key 26): 0 = two when kh == 3 and the buffers fit, 1 = always one
+// (measured at cfg2: 87.6 us with two, 90.6 us with one).
 // (More shifted-tile buffers -- 2 / 3 / 4, measured 188.2 / 188.1 / 188.1 us on the first version -- never helped: the step
 // time is the issue warps' instruction latency, not a hand-over the shifter could hide by running ahead.)
 int g_cw2_rows = 0;
@@ -1084,7 +1086,7 @@ int conv_tma_wgrad(const float *dy, const float *x, const float *w, float *dw, f
         };
         // two rows per step (kh == 3: the run-in is one group): 4 groups of dY rows, the raw stages that still fit (>= 2)
         int rows = 1;
-        if (kh == 3 && g_cw2_rows == 2) {
+        if (kh == 3 && g_cw2_rows != 1) {
             q.ring = 8;
             q.raw_stages = 3;
             if (smem_need(2) > (size_t)CT_SMEM_MAX) q.raw_stages = 2;

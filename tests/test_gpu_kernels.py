@@ -172,11 +172,11 @@ def test_conv_tma_stride1_vs_oracle(O, case):
 
 
 @pytest.mark.parametrize("case", [(2, 64, 56, 56, 64, 3, 1, 1), (2, 40, 13, 36, 48, 3, 1, 1), (3, 32, 28, 28, 32, 3, 1, 1)])
-def test_conv_tma_wgrad_two_rows_per_step(O, case):
-    """conv_s1_wgrad2_kernel<2, 3> (two X rows per pipeline step; dk_tc_debug_set key 26): an odd row count per unit
-    ends in a one-row step.  The default is one row per step (same speed at cfg2, deeper buffering)."""
+def test_conv_tma_wgrad_one_row_per_step(O, case):
+    """conv_s1_wgrad2_kernel<1, 3> (one X row per pipeline step; dk_tc_debug_set key 26 = 1).  The default for 3 x 3 is two
+    rows per step (an odd row count per unit then ends in a one-row step: the 13-row case of CONV_TMA_CASES' sibling here)."""
     from dorknet_b200 import _lib
-    _lib.api.dk_tc_debug_set(26, 2)
+    _lib.api.dk_tc_debug_set(26, 1)
     try:
         _conv_case(O, case)
     finally:
