@@ -361,8 +361,9 @@ dw_planes_reduce_kernel(const float *__restrict__ partial, const float *__restri
 // and db in registers across ALL its planes -- one block reduction at the very end instead of one per plane, and no
 // [N*C][10] partial buffer.  The R CTAs of a channel form a thread-block cluster; rank 0 adds their partials in rank
 // order through distributed shared memory (deterministic, no atomics, no second kernel).
-constexpr int DC_THREADS = 224;  // 7 warps: 14 bands x 14 strips of a 56x56 plane (and 4 x 7x7 of 28x28) fill them exactly once
+constexpr int DC_THREADS = 224;  // 7 compute warps: 14 bands x 14 strips of a 56x56 plane (and 4 x 7x7 of 28x28) fill them exactly once
 constexpr int DC_WARPS = DC_THREADS / 32;
+constexpr int DC_BLOCK = DC_THREADS + 32;  // + the copy warp
 constexpr int DC_MAX_STAGES = 8;
 constexpr int DC_SMEM_2CTA = 100 * 1024;  // ring bytes that still let two CTAs share an SM
 constexpr int DC_SMEM_MAX = 200 * 1024;
@@ -417,12 +418,12 @@ __device__ __forceinline__ void dc_load_row(const float *row, bool sl, bool sr, 
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(DC_THREADS, 2)
+__global__ void __launch_bounds__(DC_BLOCK, 2)
 dw_chan_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, const float *__restrict__ w,
                    float *__restrict__ dx, const float *__restrict__ dx_add, float *__restrict__ dw,
                    float *__restrict__ dbias, float l2, const DcGeom g) {
     extern __shared__ __align__(16) float sm[];
-    __shared__ __align__(8) uint64_t bars[DC_MAX_STAGES];
+    __shared__ __align__(8) uint64_t bars[DC_MAX_STAGES], ebars[DC_MAX_STAGES];  // stage filled / stage consumed
     __shared__ float red[DC_WARPS][10];
     __shared__ float xch[10];
     const int c = blockIdx.x, rank = blockIdx.y;
@@ -433,11 +434,18 @@ dw_chan_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, co
     const int groups = n1 > n0 ? (n1 - n0 + g.P - 1) / g.P : 0;
     const int stage_floats = 2 * g.P * HW;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < g.nst; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        for (int s = 0; s < g.nst; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&ebars[s]), DC_WARPS);
+        }
         fence_barrier_init();
     }
     __syncthreads();
-    // warp 0: fill stage (gi % nst) with the planes of images na .. na+cnt-1 (one bulk copy per plane and tensor)
+    // The copy warp (warp DC_WARPS) refills a stage as soon as the seven compute warps have each released it; the compute
+    // warps never wait for one another.  (The first version ended every stage with __syncthreads() and let warp 0 issue the
+    // refill: ncu showed 1.07 warps stalled at that barrier per issued instruction -- a third of all warp time -- because the
+    // 196 items of a plane leave one warp of seven half empty and everybody waited for the slowest.)
+    // fill stage (gi % nst) with the planes of images na .. na+cnt-1 (one bulk copy per plane and tensor)
     auto issue = [&](int gi) {
         const int slot = gi % g.nst;
         const uint32_t bar = smem_u32(&bars[slot]);
@@ -452,7 +460,7 @@ dw_chan_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, co
             dp_bulk_g2s(smem_u32(sx + (size_t)j * HW), x + off, (uint32_t)HW * 4u, bar);
         }
     };
-    if (warp == 0)
+    if (warp == DC_WARPS)
         for (int gi = 0; gi < g.nst && gi < groups; ++gi) issue(gi);
     float k[9];
 #pragma unroll
@@ -467,8 +475,14 @@ dw_chan_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, co
     const int SP = W / VEC, NB = (H + DC_RB - 1) / DC_RB;
     // a row of zeros behind the ring: what out-of-image rows and idle lanes read
     float *zrow = sm + (size_t)g.nst * stage_floats + 4;
-    for (int i = threadIdx.x; i < W + 8; i += DC_THREADS) zrow[i - 4] = 0.0f;
+    for (int i = threadIdx.x; i < W + 8; i += DC_BLOCK) zrow[i - 4] = 0.0f;
     __syncthreads();
+    if (warp == DC_WARPS) {
+        for (int gi = g.nst; gi < groups; ++gi) {
+            mbar_wait(smem_u32(&ebars[gi % g.nst]), (uint32_t)(gi / g.nst - 1) & 1u);
+            issue(gi);
+        }
+    }
     // item t = (plane p, band, strip sp) for t = tid, and how it moves when t advances by the CTA size
     int sp_0, band_0, p_0;
     {
@@ -479,7 +493,7 @@ dw_chan_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, co
     }
     const int d_sp = DC_THREADS % SP, d_pb = DC_THREADS / SP;
     const int d_band = d_pb % NB, d_p = d_pb / NB;
-    for (int gi = 0; gi < groups; ++gi) {
+    for (int gi = 0; gi < (warp < DC_WARPS ? groups : 0); ++gi) {
         const int slot = gi % g.nst;
         mbar_wait(smem_u32(&bars[slot]), (uint32_t)(gi / g.nst) & 1u);
         const int na = n0 + gi * g.P;
@@ -568,12 +582,12 @@ dw_chan_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, co
             if (band >= NB) { band -= NB; carry = 1; }
             p += d_p + carry;
         }
-        __syncthreads();  // everybody is done with this stage: refill it
-        if (warp == 0 && gi + g.nst < groups) issue(gi + g.nst);
+        __syncwarp();  // this warp is done with the stage
+        if (lane == 0) mbar_arrive(smem_u32(&ebars[slot]));
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
+    if (lane == 0 && warp < DC_WARPS) {
 #pragma unroll
         for (int i = 0; i < 10; ++i) red[warp][i] = acc[i];
     }
@@ -700,7 +714,7 @@ int dw_chan_bwd(const float *dy, const float *x, const float *w, float *dx, floa
     if (!dc_plan(g, N, C, H, W, &smem)) return DK_ERR_UNSUPPORTED;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)C, (unsigned)g.R, 1);
-    cfg.blockDim = dim3(DC_THREADS, 1, 1);
+    cfg.blockDim = dim3(DC_BLOCK, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
