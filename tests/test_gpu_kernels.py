@@ -183,6 +183,15 @@ def test_conv_tma_wgrad_one_row_per_step(O, case):
         _lib.api.dk_tc_debug_set(26, 0)
 
 
+def test_conv_tma_wgrad_channels_not_multiple_of_four(O):
+    """C = 10: the wgrad kernel's scalar partial-sum stores and cw2_reduce_kernel<1> (the 16-byte paths need C % 4 == 0)"""
+    from dorknet_b200 import _lib
+    tc0, _ = _lib.gemm_call_counts()
+    _conv_case(O, (2, 10, 12, 16, 12, 3, 1, 1))
+    tc1, _ = _lib.gemm_call_counts()
+    assert tc1 - tc0 >= 1, "expected the weight gradient on the tensor-core path"
+
+
 CONV_MAT_CASES = [
     # N, C, H, W, F, k, s, p -- shapes outside conv_tma.cu / conv_rows.cu: materialised transposed patches + the all-TMA
     # pointwise GEMMs (gemm_tcgen05.cu cvm_*), dX by gather-form col2im
